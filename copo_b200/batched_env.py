@@ -1,0 +1,120 @@
+"""Device-resident batch of S driving scenes x A agent slots behind the C ABI (b2c_env_*).
+
+This is the native tensor API of the environment; the RLlib-style dict API of the reference
+(`MultiAgent*Env.reset/step` wrapped by `get_lcf_env` / `get_ccenv`, utils/env_wrappers.py:30-471) is a
+thin host view over it in copo_b200/envs.py.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .maps import build_map
+
+MAP_OF_ENV = {
+    "MultiAgentIntersectionEnv": "intersection",
+    "MultiAgentRoundaboutEnv": "roundabout",
+    "MultiAgentTollgateEnv": "tollgate",
+    "MultiAgentBottleneckEnv": "bottleneck",
+    "MultiAgentParkingLotEnv": "parking_lot",
+}
+DEFAULT_NUM_AGENTS = {"intersection": 30, "roundabout": 40, "tollgate": 40, "bottleneck": 20, "parking_lot": 10}
+
+FLAG_VALID, FLAG_DONE, FLAG_ARRIVE, FLAG_CRASH, FLAG_OUT, FLAG_MAXSTEP, FLAG_SPAWNED, FLAG_ALIVE = (
+    1 << k for k in range(8))
+
+
+class BatchedDrivingEnv:
+    def __init__(self, map_name="intersection", num_scenes=1, num_slots=None, num_agents=None, delay_done=25,
+                 horizon=1000, agent_horizon=1000, neighbours_distance=40.0, mf_nei_distance=10.0,
+                 allow_respawn=True, auto_reset=True, append_lcf=True, lcf_uniform=False, seed=0, scene_offset=0,
+                 lcf_mean=0.0, lcf_std=0.1, force_lcf=-100.0, device=None, map_kwargs=None):
+        self.lib = _lib.require_device()
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.tables = build_map(map_name, **(map_kwargs or {}))
+        self.map_name = map_name
+        num_agents = num_agents or DEFAULT_NUM_AGENTS[map_name]
+        num_slots = num_slots or num_agents
+        self.S, self.A = int(num_scenes), int(num_slots)
+        self.cfg = _lib.EnvConfig(
+            num_scenes=self.S, num_slots=self.A, num_agents=int(num_agents), delay_done=int(delay_done),
+            horizon=int(horizon), agent_horizon=int(agent_horizon), allow_respawn=int(allow_respawn),
+            auto_reset=int(auto_reset), append_lcf=int(append_lcf), lcf_uniform=int(lcf_uniform),
+            scene_offset=int(scene_offset), seed=int(seed) & 0xFFFFFFFF,
+            neighbours_distance=float(neighbours_distance), mf_nei_distance=float(mf_nei_distance),
+            lcf_mean=float(lcf_mean), lcf_std=float(lcf_std), force_lcf=float(force_lcf))
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            blob = self.tables.blob
+            _lib.check(self.lib.b2c_env_create(ctypes.byref(self.cfg), blob.ctypes.data_as(ctypes.c_void_p),
+                                               int(blob.size), ctypes.byref(self._h)))
+        self.D = int(self.lib.b2c_env_obs_dim(self._h))
+        self.tile_words = int(self.lib.b2c_env_state_words(self._h))
+        self.num_agents = int(num_agents)
+        self.lcf_mean, self.lcf_std, self.force_lcf = float(lcf_mean), float(lcf_std), float(force_lcf)
+        self.out = self.alloc_outputs()
+
+    # -- buffers -------------------------------------------------------------------------------------------
+    def alloc_outputs(self):
+        S, A, D, dev = self.S, self.A, self.D, self.device
+        z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=dev)
+        return dict(obs=z((S, A, D), torch.float32), reward=z((S, A), torch.float32), flags=z((S, A), torch.uint8),
+                    nei_mask=z((S, A), torch.int64), mf_mask=z((S, A), torch.int64),
+                    nei_reward=z((S, A), torch.float32), global_reward=z((S,), torch.float32),
+                    nei_list=z((S, A, 4), torch.int8), agent_id=z((S, A), torch.int32), lcf=z((S, A), torch.float32),
+                    scene_done=z((S,), torch.uint8))
+
+    def _io(self, out):
+        return _lib.EnvIO(*[_lib.ptr(out.get(k)) for k in _lib.ENV_IO_FIELDS])
+
+    # -- stepping ------------------------------------------------------------------------------------------
+    def reset(self, out=None, new_episode=False):
+        out = out if out is not None else self.out
+        io = self._io(out)
+        _lib.check(self.lib.b2c_env_reset(self._h, ctypes.byref(io), int(new_episode), _lib.stream_ptr()))
+        return out
+
+    def step(self, actions, out=None):
+        """actions: float32 device tensor [S, A, 2]; returns the dict of output tensors (views, not copies)."""
+        out = out if out is not None else self.out
+        assert actions.dtype == torch.float32 and actions.is_cuda and actions.is_contiguous()
+        assert tuple(actions.shape) == (self.S, self.A, 2), actions.shape
+        io = self._io(out)
+        _lib.check(self.lib.b2c_env_step(self._h, _lib.ptr(actions), ctypes.byref(io), _lib.stream_ptr()))
+        return out
+
+    # -- trainer-driven controls (utils/env_wrappers.py:420-430, 450-454) ----------------------------------
+    def set_lcf_dist(self, mean, std):
+        _lib.check(self.lib.b2c_env_set_lcf_dist(self._h, ctypes.c_float(mean), ctypes.c_float(std)))
+        self.lcf_mean, self.lcf_std = float(mean), float(std)
+
+    def set_force_lcf(self, v):
+        _lib.check(self.lib.b2c_env_set_force_lcf(self._h, ctypes.c_float(v)))
+        self.force_lcf = float(v)
+
+    def set_num_agents(self, n):
+        _lib.check(self.lib.b2c_env_set_num_agents(self._h, int(n)))
+        self.num_agents = int(n)
+
+    # -- state access (info dicts, tests) -------------------------------------------------------------------
+    def get_state(self):
+        buf = np.zeros((self.S, self.tile_words), np.uint32)
+        _lib.check(self.lib.b2c_env_get_state(self._h, buf.ctypes.data_as(ctypes.c_void_p), _lib.stream_ptr()))
+        return buf
+
+    def set_state(self, tiles):
+        tiles = np.ascontiguousarray(tiles, np.uint32)
+        assert tiles.shape == (self.S, self.tile_words)
+        _lib.check(self.lib.b2c_env_set_state(self._h, tiles.ctypes.data_as(ctypes.c_void_p), _lib.stream_ptr()))
+
+    def close(self):
+        if self._h:
+            self.lib.b2c_env_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
