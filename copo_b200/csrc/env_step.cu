@@ -84,16 +84,16 @@ env_step_kernel(const __grid_constant__ EnvConfig cfg, const __grid_constant__ E
     float* s_obs = reinterpret_cast<float*>(s_st + io.tile_words);
     float* s_f = s_obs + ((A * D + 3) & ~3);
     int* s_i = reinterpret_cast<int*>(s_f + 6 * A);
-    uint8_t* s_cand = reinterpret_cast<uint8_t*>(s_i + 5 * A);
+    int* s_place = s_i + 5 * A;
+    uint8_t* s_cand = reinterpret_cast<uint8_t*>(s_place + MAX_SPAWN);
     __shared__ int s_scene_done;
-    __shared__ float s_global;
 
     SceneView v;
     v.map = s_map; v.st = s_st; v.obs = s_obs;
     v.cs = s_f; v.sn = s_f + A; v.rew = s_f + 2 * A; v.long_last = s_f + 3 * A; v.loc_s = s_f + 4 * A;
     v.loc_l = s_f + 5 * A;
     v.flags = s_i; v.crash = s_i + A; v.acted = s_i + 2 * A; v.linger = s_i + 3 * A; v.ncand = s_i + 4 * A;
-    v.cand = s_cand;
+    v.cand = s_cand; v.place_free = s_place;
     v.A = A; v.AP = AP; v.D = D;
 
     const uint32_t tile_bytes = (uint32_t)io.tile_words * 4u;
@@ -137,6 +137,8 @@ env_step_kernel(const __grid_constant__ EnvConfig cfg, const __grid_constant__ E
         }
         __syncthreads();
         if (tid < A) phase_outcome(v, cfg, tid);
+        __syncthreads();
+        if (tid < (int)s_map[M_NSPAWN]) phase_place_free(v, cfg, tid);
         __syncthreads();
         if (tid == 0) s_scene_done = phase_respawn(v, cfg, scene);
         __syncthreads();
@@ -189,7 +191,7 @@ env_step_kernel(const __grid_constant__ EnvConfig cfg, const __grid_constant__ E
 }
 
 size_t env_smem_bytes(int A, int D, int map_words, int tile_words) {
-    size_t words = 4 + (size_t)map_words + tile_words + ((A * D + 3) & ~3) + 6 * A + 5 * A;
+    size_t words = 4 + (size_t)map_words + tile_words + ((A * D + 3) & ~3) + 6 * A + 5 * A + MAX_SPAWN;
     return words * 4 + (size_t)A * A + 16;
 }
 
@@ -219,6 +221,8 @@ int b2c_env_create(const b2c_env_config* c, const uint32_t* map_blob, int map_wo
     if (c->lcf_std <= 0.0f) return b2c_set_error(B2C_ERR_ARG, "lcf_std must be > 0 (env_wrappers.py:425)");
     int base = (int)map_blob[M_BASE_OBS];
     int D = base + (c->append_lcf ? 1 : 0);
+    if ((int)map_blob[M_NSPAWN] > MAX_SPAWN || (int)map_blob[M_NSPAWN] > ENV_THREADS)
+        return b2c_set_error(B2C_ERR_ARG, "map has more than 64 spawn places");
     if (EGO_DIM + NAVI_DIM + (int)map_blob[M_NRAY] + (int)map_blob[M_NSIDE] != base)
         return b2c_set_error(B2C_ERR_ARG, "map obs layout does not add up");
     b2c_env* e = new b2c_env();

@@ -20,7 +20,7 @@ extern "C" int hostsim_step(const EnvConfig* cfgp, const uint32_t* map, int map_
     const int A = cfg.A, AP = cfg.AP, D = cfg.D;
     const int tile_words = NUM_FIELDS * AP + HEADER_WORDS;
     std::vector<float> fbuf(6 * A), obs((size_t)A * D);
-    std::vector<int> ibuf(5 * A);
+    std::vector<int> ibuf(5 * A + MAX_SPAWN);
     std::vector<uint8_t> cand((size_t)A * A);
     for (int scene = 0; scene < cfg.S; ++scene) {
         SceneView v;
@@ -29,7 +29,7 @@ extern "C" int hostsim_step(const EnvConfig* cfgp, const uint32_t* map, int map_
         v.cs = s_f; v.sn = s_f + A; v.rew = s_f + 2 * A; v.long_last = s_f + 3 * A; v.loc_s = s_f + 4 * A;
         v.loc_l = s_f + 5 * A;
         v.flags = s_i; v.crash = s_i + A; v.acted = s_i + 2 * A; v.linger = s_i + 3 * A; v.ncand = s_i + 4 * A;
-        v.cand = cand.data(); v.A = A; v.AP = AP; v.D = D;
+        v.cand = cand.data(); v.place_free = s_i + 5 * A; v.A = A; v.AP = AP; v.D = D;
         if (cfg.do_reset) {
             for (int i = 0; i < A; ++i) phase_reset_slot(v, cfg, i);
             phase_reset_scene(v, cfg);
@@ -46,6 +46,7 @@ extern "C" int hostsim_step(const EnvConfig* cfgp, const uint32_t* map, int map_
                 for (int j = i + 1; j < A; ++j)
                     if (phase_pair_crash(v, i, j)) { v.crash[i] = 1; v.crash[j] = 1; }
         for (int i = 0; i < A; ++i) phase_outcome(v, cfg, i);
+        for (int p = 0; p < (int)map[M_NSPAWN]; ++p) phase_place_free(v, cfg, p);
         int sd = phase_respawn(v, cfg, scene);
         for (int i = 0; i < A; ++i) phase_pose_refresh(v, i);
         for (int i = 0; i < A; ++i) {

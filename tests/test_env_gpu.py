@@ -62,7 +62,7 @@ def test_env_step_bit_exact(map_name, S, A, T, kw):
         seen["crash"] += int(((r["flags"] & osim.F_CRASH) > 0).sum())
         seen["spawn"] += int(((r["flags"] & osim.F_SPAWNED) > 0).sum())
     env.close()
-    if kw.get("allow_respawn", True) and T >= 120:
+    if kw.get("allow_respawn", True) and T >= 200:
         assert seen["crash"] > 0 and seen["spawn"] > 0
 
 
