@@ -84,6 +84,41 @@ class BatchedDrivingEnv:
         _lib.check(self.lib.b2c_env_step(self._h, _lib.ptr(actions), ctypes.byref(io), _lib.stream_ptr()))
         return out
 
+    # -- host-buffer stepping (what a CPU-side caller of the reference's env.step sees) ---------------------
+    HOST_KEYS = ("obs", "reward", "flags", "nei_mask", "nei_reward", "global_reward", "nei_list", "agent_id", "lcf",
+                 "scene_done")
+
+    def _host_buffers(self):
+        if getattr(self, "_host", None) is None:
+            self._host = {k: torch.empty(self.out[k].shape, dtype=self.out[k].dtype).pin_memory()
+                          for k in self.HOST_KEYS}
+            self._host_act = torch.empty((self.S, self.A, 2), dtype=torch.float32).pin_memory()
+            self._dev_act = torch.empty((self.S, self.A, 2), dtype=torch.float32, device=self.device)
+            self.h2d_bytes_per_step = self._host_act.numel() * 4
+            self.d2h_bytes_per_step = sum(v.numel() * v.element_size() for v in self._host.values())
+        return self._host
+
+    def step_host(self, actions_host):
+        """actions_host: float32 [S, A, 2] numpy array or CPU tensor.  Copies it to the device, steps every scene
+        and returns pinned host tensors of every output (valid until the next call)."""
+        host = self._host_buffers()
+        a = torch.as_tensor(actions_host, dtype=torch.float32)
+        assert tuple(a.shape) == (self.S, self.A, 2), a.shape
+        if a.data_ptr() != self._host_act.data_ptr():
+            self._host_act.copy_(a)
+        self._dev_act.copy_(self._host_act, non_blocking=True)
+        self.step(self._dev_act)
+        for k in self.HOST_KEYS:
+            host[k].copy_(self.out[k], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return host
+
+    def agent_steps(self):
+        """Running count of agent-env-steps (agents that received an action), summed over scenes."""
+        st = self.get_state()
+        ap = (self.A + 3) // 4 * 4
+        return int(st[:, 16 * ap + 4].astype(np.int64).sum())
+
     # -- trainer-driven controls (utils/env_wrappers.py:420-430, 450-454) ----------------------------------
     def set_lcf_dist(self, mean, std):
         _lib.check(self.lib.b2c_env_set_lcf_dist(self._h, ctypes.c_float(mean), ctypes.c_float(std)))

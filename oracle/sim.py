@@ -107,6 +107,7 @@ class OracleSim:
         self.next_id = np.zeros(S, np.int32)
         self.episode = np.zeros(S, np.int32)
         self.rng_ctr = np.zeros(S, np.int32)
+        self.agent_steps = np.zeros(S, np.int32)          # running count of agent-env-steps (metric counter)
         self.scene_id = (np.arange(S) + scene_offset).astype(np.int64)
         self.obs_dim = tables.base_obs_dim + (1 if cfg.append_lcf else 0)
 
@@ -164,6 +165,7 @@ class OracleSim:
         act = np.asarray(actions, dtype=f32)
         active = self.status == ACTIVE
         self.ep_step = (self.ep_step + 1).astype(np.int32)
+        self.agent_steps = (self.agent_steps + active.sum(axis=1)).astype(np.int32)
 
         # ---- 1. kinematic bicycle, NSUB sub-steps ------------------------------------------------
         a0 = np.where(act[..., 0] < -ONE, -ONE, np.where(act[..., 0] > ONE, ONE, act[..., 0])).astype(f32)
@@ -533,5 +535,5 @@ class OracleSim:
     # convenience for tests -------------------------------------------------------------------------
     def state_dict(self):
         keys = ("x", "y", "h", "v", "steer", "thr", "seg_s", "done_len", "route", "seg_k", "ep_len", "ep_rew", "lcf",
-                "status", "linger", "agent_id", "yaw", "ep_step", "next_id", "episode", "rng_ctr")
+                "status", "linger", "agent_id", "yaw", "ep_step", "next_id", "episode", "rng_ctr", "agent_steps")
         return {k: getattr(self, k).copy() for k in keys}

@@ -10,7 +10,7 @@ from oracle import sim as osim
 FIELDS = ("x", "y", "h", "v", "steer", "thr", "seg_s", "done_len", "route", "seg_k", "ep_len", "ep_rew", "lcf",
           "status", "agent_id", "yaw")
 INT_FIELDS = {"route", "seg_k", "ep_len", "status", "agent_id"}
-HDR = ("ep_step", "next_id", "episode", "rng_ctr")
+HDR = ("ep_step", "next_id", "episode", "rng_ctr", "agent_steps")
 OUT_KEYS = ("obs", "reward", "flags", "nei_mask", "mf_mask", "nei_reward", "global_reward", "nei_list", "agent_id",
             "lcf", "scene_done")
 
