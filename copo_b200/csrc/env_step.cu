@@ -12,6 +12,7 @@
 // LCFEnv._add_lcf (env_wrappers.py:393-418).  Build with -fmad=false (bit-exact spec, oracle/sim.py).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include "sim_core.cuh"
 #include "b2c_internal.h"
 
@@ -34,7 +35,8 @@ struct EnvIO {
     uint8_t* scene_done;
     int map_words;
     int tile_words;
-    int obs_bulk;   // 1 when the obs tile can leave through a bulk store (16-byte multiple + aligned base)
+    int obs_bulk;   // 1 when the obs tiles can leave through a bulk store (16-byte aligned base)
+    int group;      // scenes one CTA works on at a time
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -70,31 +72,57 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-static constexpr int ENV_THREADS = 256;
+static constexpr int ENV_MAX_THREADS = 256;
+static constexpr int ENV_MAX_GROUP = 16;      // scene tag in a queue entry is 4 bits
 
-__global__ void __launch_bounds__(ENV_THREADS)
+// Shared-memory plan of one CTA working on `G` scenes at a time (offsets in bytes, every region 16-byte aligned).
+struct SmemPlan {
+    int map, st, obs, f, i, need, masks, queue, total;
+};
+__host__ __device__ inline SmemPlan smem_plan(int G, int A, int D, int map_words, int tile_words) {
+    SmemPlan p;
+    int o = 16;                                          // mbarrier
+    p.map = o;   o += map_words * 4;
+    p.st = o;    o += G * tile_words * 4;
+    p.obs = o;   o += ((G * A * D + 3) & ~3) * 4;
+    p.f = o;     o += ((G * 6 * A + 3) & ~3) * 4;
+    p.i = o;     o += ((G * (4 * A + MAX_SPAWN) + 3) & ~3) * 4;
+    p.need = o;  o += ((2 * G + 4 + 3) & ~3) * 4;        // need[G], scene_done[G], queue fill
+    p.masks = o; o += G * 2 * 8;                         // per scene: participant / present slot masks
+    p.queue = o; o += ((G * A * A + 7) & ~7) * 2;
+    p.total = o;
+    return p;
+}
+
+__global__ void __launch_bounds__(ENV_MAX_THREADS, 2)
 env_step_kernel(const __grid_constant__ EnvConfig cfg, const __grid_constant__ EnvIO io) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    const int A = cfg.A, AP = cfg.AP, D = cfg.D;
-    const int tid = threadIdx.x;
-    // ---- carve shared memory ------------------------------------------------------------------------
+    const int A = cfg.A, AP = cfg.AP, D = cfg.D, G = io.group;
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const SmemPlan pl = smem_plan(G, A, D, io.map_words, io.tile_words);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
-    uint32_t* s_map = reinterpret_cast<uint32_t*>(smem_raw + 16);
-    uint32_t* s_st = s_map + io.map_words;
-    float* s_obs = reinterpret_cast<float*>(s_st + io.tile_words);
-    float* s_f = s_obs + ((A * D + 3) & ~3);
-    int* s_i = reinterpret_cast<int*>(s_f + 6 * A);
-    int* s_place = s_i + 5 * A;
-    uint8_t* s_cand = reinterpret_cast<uint8_t*>(s_place + MAX_SPAWN);
-    __shared__ int s_scene_done;
+    uint32_t* s_map = reinterpret_cast<uint32_t*>(smem_raw + pl.map);
+    uint32_t* s_st = reinterpret_cast<uint32_t*>(smem_raw + pl.st);
+    float* s_obs = reinterpret_cast<float*>(smem_raw + pl.obs);
+    float* s_f = reinterpret_cast<float*>(smem_raw + pl.f);
+    int* s_i = reinterpret_cast<int*>(smem_raw + pl.i);
+    int* s_need = reinterpret_cast<int*>(smem_raw + pl.need);
+    int* s_done = s_need + G;
+    int* s_nq = s_need + 2 * G;
+    uint16_t* s_queue = reinterpret_cast<uint16_t*>(smem_raw + pl.queue);
+    unsigned long long* s_masks = reinterpret_cast<unsigned long long*>(smem_raw + pl.masks);
 
-    SceneView v;
-    v.map = s_map; v.st = s_st; v.obs = s_obs;
-    v.cs = s_f; v.sn = s_f + A; v.rew = s_f + 2 * A; v.long_last = s_f + 3 * A; v.loc_s = s_f + 4 * A;
-    v.loc_l = s_f + 5 * A;
-    v.flags = s_i; v.crash = s_i + A; v.acted = s_i + 2 * A; v.linger = s_i + 3 * A; v.ncand = s_i + 4 * A;
-    v.cand = s_cand; v.place_free = s_place;
-    v.A = A; v.AP = AP; v.D = D;
+    auto view = [&](int sl) {
+        SceneView v;
+        v.map = s_map; v.st = s_st + sl * io.tile_words; v.obs = s_obs + (size_t)sl * A * D;
+        float* f = s_f + sl * 6 * A;
+        v.cs = f; v.sn = f + A; v.rew = f + 2 * A; v.long_last = f + 3 * A; v.loc_s = f + 4 * A; v.loc_l = f + 5 * A;
+        int* q = s_i + sl * (4 * A + MAX_SPAWN);
+        v.flags = q; v.crash = q + A; v.acted = q + 2 * A; v.linger = q + 3 * A; v.place_free = q + 4 * A;
+        v.nqueue = s_nq; v.queue = s_queue; v.scene_local = sl; v.masks = s_masks + 2 * sl;
+        v.A = A; v.AP = AP; v.D = D;
+        return v;
+    };
 
     const uint32_t tile_bytes = (uint32_t)io.tile_words * 4u;
     const uint32_t map_bytes = (uint32_t)io.map_words * 4u;
@@ -102,51 +130,81 @@ env_step_kernel(const __grid_constant__ EnvConfig cfg, const __grid_constant__ E
     if (tid == 0) mbar_init(bar, 1);
     __syncthreads();
     bool first = true;
+    const int sl_a = tid / A, ia = tid - sl_a * A;       // this thread's (scene in group, slot)
+    const int n_warps = NT >> 5;
+    const int n_groups = (cfg.S + G - 1) / G;
 
-    for (int scene = blockIdx.x; scene < cfg.S; scene += gridDim.x) {
-        uint32_t* g_tile = io.state + (size_t)scene * io.tile_words;
-        // ---- stage map (first iteration) + state tile ------------------------------------------------
+    for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+        const int scene0 = grp * G;
+        const int ng = (cfg.S - scene0 < G) ? cfg.S - scene0 : G;
+        uint32_t* g_tiles = io.state + (size_t)scene0 * io.tile_words;
+        const bool has_agent = tid < ng * A;
+        // ---- stage map (first iteration) + the group's state tiles (1-D TMA bulk copies) -----------------
         if (tid == 0) {
-            mbar_expect_tx(bar, tile_bytes + (first ? map_bytes : 0u));
+            bulk_wait_read0();                           // the previous group's stores have left shared memory
+            mbar_expect_tx(bar, (uint32_t)ng * tile_bytes + (first ? map_bytes : 0u));
             if (first) bulk_g2s(s_map, io.map, map_bytes, bar);
-            bulk_g2s(s_st, g_tile, tile_bytes, bar);
+            bulk_g2s(s_st, g_tiles, (uint32_t)ng * tile_bytes, bar);
+            *s_nq = 0;
         }
         float act0 = 0.0f, act1 = 0.0f;
-        if (tid < A && !cfg.do_reset) {
-            float2 a = reinterpret_cast<const float2*>(io.actions)[(size_t)scene * A + tid];
+        if (has_agent && !cfg.do_reset) {
+            float2 a = reinterpret_cast<const float2*>(io.actions)[(size_t)scene0 * A + tid];
             act0 = a.x; act1 = a.y;
         }
         mbar_wait(bar, parity);
         parity ^= 1u;
         first = false;
 
-        if (cfg.do_reset) {
-            if (tid < A) phase_reset_slot(v, cfg, tid);
-            if (tid == 0) phase_reset_scene(v, cfg);
-        } else if (tid == 0) {
-            v.hdr(H_EP_STEP) += 1;
+        SceneView v = view(has_agent ? sl_a : 0);
+        // ---- P1: header + dynamics + localisation (thread = slot) ----------------------------------------
+        if (has_agent) {
+            if (cfg.do_reset) phase_reset_slot(v, cfg, ia);
+            if (ia == 0) {
+                if (cfg.do_reset) phase_reset_scene(v, cfg); else v.hdr(H_EP_STEP) += 1;
+                s_need[sl_a] = cfg.do_reset ? 1 : 0;
+                v.masks[0] = 0ull; v.masks[1] = 0ull;
+            }
+            phase_dynamics(v, cfg, ia, act0, act1);
         }
         __syncthreads();
-        if (tid < A) phase_dynamics(v, cfg, tid, act0, act1);
+        // ---- P2: box overlap, balanced ring pairing (thread = slot) --------------------------------------
+        if (has_agent && !cfg.do_reset) phase_crash_slot(v, ia);
         __syncthreads();
-        if (!cfg.do_reset) {
-            for (int idx = tid; idx < A * A; idx += ENV_THREADS) {
-                int i = idx / A, j = idx - i * A;
-                if (i < j && phase_pair_crash(v, i, j)) { v.crash[i] = 1; v.crash[j] = 1; }
+        // ---- P3: reward / termination (thread = slot) ----------------------------------------------------
+        if (has_agent) {
+            phase_outcome(v, cfg, ia);
+            if (v.status(ia) == ST_EMPTY || v.hdr(H_EP_STEP) >= cfg.horizon) s_need[sl_a] = 1;
+        }
+        __syncthreads();
+        // ---- P4: spawn-place occupancy, only for scenes that have something to spawn ----------------------
+        const int n_sp = (int)s_map[M_NSPAWN];
+        for (int idx = tid; idx < ng * n_sp; idx += NT) {
+            int sl = idx / n_sp, p = idx - sl * n_sp;
+            if (s_need[sl]) phase_place_free(view(sl), cfg, p);
+        }
+        __syncthreads();
+        // ---- P5: respawn, sequential per scene; scenes are spread over distinct warps ---------------------
+        {
+            int w = tid >> 5, lane = tid & 31;
+            int sl = lane * n_warps + w;
+            if (sl < ng) {
+                int need = s_need[sl];
+                s_done[sl] = need ? phase_respawn(view(sl), cfg, scene0 + sl) : 0;
             }
         }
         __syncthreads();
-        if (tid < A) phase_outcome(v, cfg, tid);
+        // ---- P6a: slot masks (participants / present vehicles) ---------------------------------------------
+        if (has_agent) {
+            phase_pose_refresh(v, ia);
+            phase_masks(v, ia);
+        }
         __syncthreads();
-        if (tid < (int)s_map[M_NSPAWN]) phase_place_free(v, cfg, tid);
-        __syncthreads();
-        if (tid == 0) s_scene_done = phase_respawn(v, cfg, scene);
-        __syncthreads();
-        if (tid < A) phase_pose_refresh(v, tid);
-        __syncthreads();
-        if (tid < A) {
-            NeiOut n = phase_neighbours(v, cfg, tid);
-            size_t g = (size_t)scene * A + tid;
+        // ---- P6b: neighbours (+ lidar pair queue), per-slot outputs, ego/navi features (thread = slot) ----
+        const bool spare = (NT - ng * A) >= ng;          // idle threads take the per-scene reductions
+        if (has_agent) {
+            NeiOut n = phase_neighbours(v, cfg, ia);
+            size_t g = (size_t)scene0 * A + tid;
             if (io.nei_mask) io.nei_mask[g] = n.nei_mask;
             if (io.mf_mask) io.mf_mask[g] = n.mf_mask;
             if (io.nei_reward) io.nei_reward[g] = n.nei_reward;
@@ -155,44 +213,89 @@ env_step_kernel(const __grid_constant__ EnvConfig cfg, const __grid_constant__ E
                               ((uint32_t)(uint8_t)n.list[2] << 16) | ((uint32_t)(uint8_t)n.list[3] << 24);
                 reinterpret_cast<uint32_t*>(io.nei_list)[g] = pk;
             }
-            io.reward[g] = v.rew[tid];
-            io.flags[g] = (uint8_t)v.flags[tid];
-            if (io.agent_id) io.agent_id[g] = v.geti(F_ID, tid);
-            if (io.lcf) io.lcf[g] = v.f(F_LCF, tid);
-            phase_observe_ego(v, cfg, tid);
-        } else if (tid == ENV_THREADS - 1) {
-            float g = phase_global_reward(v);
-            if (io.global_reward) io.global_reward[scene] = g;
-            if (io.scene_done) io.scene_done[scene] = (uint8_t)s_scene_done;
+            io.reward[g] = v.rew[ia];
+            io.flags[g] = (uint8_t)v.flags[ia];
+            if (io.agent_id) io.agent_id[g] = v.geti(F_ID, ia);
+            if (io.lcf) io.lcf[g] = v.f(F_LCF, ia);
+            phase_observe_ego(v, cfg, ia);
+            phase_lidar_init(v, ia);
+        }
+        {
+            int sl = spare ? tid - ng * A : ((has_agent && ia == A - 1) ? sl_a : -1);
+            if (sl >= 0 && sl < ng) {
+                float gr = phase_global_reward(view(sl));
+                if (io.global_reward) io.global_reward[scene0 + sl] = gr;
+                if (io.scene_done) io.scene_done[scene0 + sl] = (uint8_t)s_done[sl];
+            }
         }
         __syncthreads();
-        const int n_ray = (int)s_map[M_NRAY];
-        for (int idx = tid; idx < A * n_ray; idx += ENV_THREADS) {
-            int i = idx / n_ray, k = idx - i * n_ray;
-            phase_lidar(v, i, k);
+        // ---- P7: lidar.  Each warp takes 32 queued (observer, box) pairs, sets them up one per lane, then
+        // spreads the pairs' lasers evenly over its lanes (prefix sum + search through shuffles) -------------
+        {
+            const int nq = *s_nq;
+            const int lane = tid & 31, warp = tid >> 5;
+            const int n_ray = (int)s_map[M_NRAY];
+            const float2* ray2 = reinterpret_cast<const float2*>(s_map + s_map[M_OFF_RAY]);
+            for (int base = warp * 32; base < nq; base += n_warps * 32) {
+                const int e = base + lane;
+                PairGeom g;
+                g.nx1 = g.nx2 = g.ny1 = g.ny2 = g.cc = g.ss = 0.0f; g.k0 = 0; g.cnt = 0;
+                int lid_off = 0;
+                if (e < nq) {
+                    int code = s_queue[e];
+                    int sl = code >> 12, oi = (code >> 6) & 63, oj = code & 63;
+                    lidar_pair_setup(view(sl), oi, oj, g);
+                    lid_off = (sl * A + oi) * D + EGO_DIM + NAVI_DIM;
+                }
+                int incl = g.cnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    int nb = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += nb;
+                }
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                const int excl = incl - g.cnt;
+                for (int r0 = 0; r0 < total; r0 += 32) {
+                    const int r = r0 + lane;
+                    const bool act = r < total;
+                    const int rr = act ? r : 0;
+                    int lo = 0;
+#pragma unroll
+                    for (int step = 16; step >= 1; step >>= 1) {
+                        int ex = __shfl_sync(0xffffffffu, excl, lo + step);
+                        if (ex <= rr) lo += step;
+                    }
+                    const int ex0 = __shfl_sync(0xffffffffu, excl, lo);
+                    const int k0 = __shfl_sync(0xffffffffu, g.k0, lo);
+                    const int off = __shfl_sync(0xffffffffu, lid_off, lo);
+                    const float nx1 = __shfl_sync(0xffffffffu, g.nx1, lo), nx2 = __shfl_sync(0xffffffffu, g.nx2, lo);
+                    const float ny1 = __shfl_sync(0xffffffffu, g.ny1, lo), ny2 = __shfl_sync(0xffffffffu, g.ny2, lo);
+                    const float cc = __shfl_sync(0xffffffffu, g.cc, lo), ss = __shfl_sync(0xffffffffu, g.ss, lo);
+                    if (act) {
+                        int k = k0 + (rr - ex0);
+                        k = (k >= n_ray) ? k - n_ray : k;
+                        float2 rd = ray2[k];
+                        lidar_ray(nx1, nx2, ny1, ny2, cc, ss, rd.x, rd.y, s_obs + off + k);
+                    }
+                }
+            }
         }
-        // persist linger counters were folded into the status word by phase_outcome / phase_respawn
-        if (tid < A) v.seti(F_STATUS, tid, v.status(tid) | (v.linger[tid] << 8));
         fence_async_smem();
         __syncthreads();
-        // ---- write back: state tile + obs tile through bulk stores ------------------------------------
-        float* g_obs = io.obs + (size_t)scene * A * D;
+        // ---- write back: state tiles + observation tiles through bulk stores ------------------------------
+        float* g_obs = io.obs + (size_t)scene0 * A * D;
+        const uint32_t obs_bytes = (uint32_t)(ng * A * D * 4);
+        const bool obs_bulk = io.obs_bulk && (obs_bytes % 16u == 0u);
         if (tid == 0) {
-            bulk_s2g(g_tile, s_st, tile_bytes);
-            if (io.obs_bulk) bulk_s2g(g_obs, s_obs, (uint32_t)(A * D * 4));
+            bulk_s2g(g_tiles, s_st, (uint32_t)ng * tile_bytes);
+            if (obs_bulk) bulk_s2g(g_obs, s_obs, obs_bytes);
             bulk_commit();
         }
-        if (!io.obs_bulk) {
-            for (int idx = tid; idx < A * D; idx += ENV_THREADS) g_obs[idx] = s_obs[idx];
+        if (!obs_bulk) {
+            for (int idx = tid; idx < ng * A * D; idx += NT) g_obs[idx] = s_obs[idx];
         }
-        if (tid == 0) bulk_wait_read0();
-        __syncthreads();
     }
-}
-
-size_t env_smem_bytes(int A, int D, int map_words, int tile_words) {
-    size_t words = 4 + (size_t)map_words + tile_words + ((A * D + 3) & ~3) + 6 * A + 5 * A + MAX_SPAWN;
-    return words * 4 + (size_t)A * A + 16;
+    if (tid == 0) bulk_wait_read0();
 }
 
 }  // namespace b2c
@@ -202,6 +305,8 @@ using namespace b2c;
 
 struct b2c_env {
     EnvConfig cfg;
+    int group;
+    int threads;
     uint32_t* d_map;
     uint32_t* d_state;
     int map_words;
@@ -221,7 +326,7 @@ int b2c_env_create(const b2c_env_config* c, const uint32_t* map_blob, int map_wo
     if (c->lcf_std <= 0.0f) return b2c_set_error(B2C_ERR_ARG, "lcf_std must be > 0 (env_wrappers.py:425)");
     int base = (int)map_blob[M_BASE_OBS];
     int D = base + (c->append_lcf ? 1 : 0);
-    if ((int)map_blob[M_NSPAWN] > MAX_SPAWN || (int)map_blob[M_NSPAWN] > ENV_THREADS)
+    if ((int)map_blob[M_NSPAWN] > MAX_SPAWN)
         return b2c_set_error(B2C_ERR_ARG, "map has more than 64 spawn places");
     if (EGO_DIM + NAVI_DIM + (int)map_blob[M_NRAY] + (int)map_blob[M_NSIDE] != base)
         return b2c_set_error(B2C_ERR_ARG, "map obs layout does not add up");
@@ -239,7 +344,21 @@ int b2c_env_create(const b2c_env_config* c, const uint32_t* map_blob, int map_wo
     e->tile_words = NUM_FIELDS * k.AP + HEADER_WORDS;
     B2C_CUDA_OR(cudaGetDevice(&e->device), delete e);
     B2C_CUDA_OR(cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, e->device), delete e);
-    e->smem = env_smem_bytes(k.A, k.D, map_words, e->tile_words);
+    // scenes per CTA: one thread per slot in the per-slot phases, as many scenes as keep two CTAs per SM
+    e->threads = ENV_MAX_THREADS;
+    if (const char* t = getenv("B2C_ENV_THREADS")) e->threads = atoi(t);
+    if (e->threads < 32 || e->threads > ENV_MAX_THREADS || (e->threads & 31)) e->threads = ENV_MAX_THREADS;
+    int fit = e->threads / k.A;
+    if (fit > ENV_MAX_GROUP) fit = ENV_MAX_GROUP;
+    if (fit > k.S) fit = k.S;
+    if (fit < 1) { delete e; return b2c_set_error(B2C_ERR_ARG, "num_slots does not fit one CTA"); }
+    e->group = fit;
+    while (e->group > 1 && smem_plan(e->group, k.A, k.D, map_words, e->tile_words).total > 112 * 1024) e->group -= 1;
+    if (const char* g = getenv("B2C_ENV_GROUP")) {
+        int gg = atoi(g);
+        if (gg >= 1 && gg <= fit) e->group = gg;
+    }
+    e->smem = (size_t)smem_plan(e->group, k.A, k.D, map_words, e->tile_words).total;
     B2C_CUDA_OR(cudaFuncSetAttribute(env_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem),
                 delete e);
     B2C_CUDA_OR(cudaMalloc(&e->d_map, (size_t)map_words * 4), delete e);
@@ -271,13 +390,16 @@ static int launch_env(b2c_env* e, const float* actions, const b2c_env_io* o, int
     io.nei_reward = o->nei_reward; io.global_reward = o->global_reward; io.nei_list = o->nei_list;
     io.agent_id = o->agent_id; io.lcf = o->lcf; io.scene_done = o->scene_done;
     io.map_words = e->map_words; io.tile_words = e->tile_words;
-    io.obs_bulk = (((size_t)cfg.A * cfg.D * 4) % 16 == 0) && (((uintptr_t)o->obs) % 16 == 0);
-    int ctas_per_sm = (int)(200 * 1024 / (e->smem + 1024));
-    if (ctas_per_sm > 8) ctas_per_sm = 8;
+    io.obs_bulk = ((((size_t)cfg.A * cfg.D * 4) % 16 == 0) && (((uintptr_t)o->obs) % 16 == 0)) ? 1 : 0;
+    io.group = e->group;
+    int ctas_per_sm = (int)(227 * 1024 / (e->smem + 1024));
+    int by_threads = 2048 / e->threads;
+    if (ctas_per_sm > by_threads) ctas_per_sm = by_threads;
     if (ctas_per_sm < 1) ctas_per_sm = 1;
+    int n_groups = (cfg.S + e->group - 1) / e->group;
     int grid = e->num_sms * ctas_per_sm;
-    if (grid > cfg.S) grid = cfg.S;
-    env_step_kernel<<<grid, ENV_THREADS, e->smem, (cudaStream_t)stream>>>(cfg, io);
+    if (grid > n_groups) grid = n_groups;
+    env_step_kernel<<<grid, e->threads, e->smem, (cudaStream_t)stream>>>(cfg, io);
     B2C_CUDA(cudaGetLastError());
     return B2C_OK;
 }

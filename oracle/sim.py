@@ -497,40 +497,52 @@ class OracleSim:
         return out
 
     def _lidar(self, cn, sn):
-        """Brute force: every laser of every slot against every other present box (slab test)."""
+        """Brute force: every laser of every slot against every other present box (slab test in the box frame).
+
+        Per ordered pair (i observes j): ego position (ox, oy) in j's frame and the relative rotation
+        C = cos(th_i - th_j), SN = sin(th_i - th_j); per laser k with ego-frame direction (rx, ry):
+        direction in j's frame (rx*C - ry*SN, ry*C + rx*SN), two correctly rounded reciprocals, four products.
+        """
         S, A, m = self.S, self.A, self.m
         R = m.n_ray
         present = (self.status == ACTIVE) | (self.status == LINGER)
         rx = m.ray[:, 0][None, None, :]
         ry = m.ray[:, 1][None, None, :]
-        dxw = cn[:, :, None] * rx - sn[:, :, None] * ry          # [S,A,R]
-        dyw = sn[:, :, None] * rx + cn[:, :, None] * ry
-        best = np.full((S, A, R), LIDAR_RANGE, f32)
+        best = np.full((S, A, R), LIDAR_RANGE * INV_LIDAR_RANGE, f32)      # == 1.0
         with np.errstate(divide="ignore", invalid="ignore"):
             for j in range(A):
                 relx = self.x - self.x[:, j][:, None]            # [S,A]
                 rely = self.y - self.y[:, j][:, None]
                 cj = cn[:, j][:, None]
                 sj = sn[:, j][:, None]
-                ox = (relx * cj + rely * sj)[:, :, None]
-                oy = (rely * cj - relx * sj)[:, :, None]
-                ddx = dxw * cj[:, :, None] + dyw * sj[:, :, None]
-                ddy = dyw * cj[:, :, None] - dxw * sj[:, :, None]
-                t1 = (-HALF_L - ox) / ddx
-                t2 = (HALF_L - ox) / ddx
+                ox = relx * cj + rely * sj
+                oy = rely * cj - relx * sj
+                cc = (cn * cj + sn * sj)[:, :, None]
+                ss = (sn * cj - cn * sj)[:, :, None]
+                nx1 = (-HALF_L - ox)[:, :, None]
+                nx2 = (HALF_L - ox)[:, :, None]
+                ny1 = (-HALF_W - oy)[:, :, None]
+                ny2 = (HALF_W - oy)[:, :, None]
+                ddx = rx * cc - ry * ss                          # [S,A,R]
+                ddy = ry * cc + rx * ss
+                ix = ONE / ddx
+                iy = ONE / ddy
+                t1 = nx1 * ix
+                t2 = nx2 * ix
                 tnx = np.where(t1 < t2, t1, t2)
                 tfx = np.where(t1 < t2, t2, t1)
-                t3 = (-HALF_W - oy) / ddy
-                t4 = (HALF_W - oy) / ddy
+                t3 = ny1 * iy
+                t4 = ny2 * iy
                 tny = np.where(t3 < t4, t3, t4)
                 tfy = np.where(t3 < t4, t4, t3)
                 tn = np.where(tnx > tny, tnx, tny)
                 tf = np.where(tfx < tfy, tfx, tfy)
                 hit = (tn <= tf) & (tf >= ZERO)
                 t = np.where(tn > ZERO, tn, ZERO)
+                ts = (t * INV_LIDAR_RANGE).astype(f32)
                 ok = hit & present[:, j][:, None, None] & (np.arange(A) != j)[None, :, None]
-                best = np.where(ok & (t < best), t, best)
-        return (best * INV_LIDAR_RANGE).astype(f32)
+                best = np.where(ok & (ts < best), ts, best)
+        return best.astype(f32)
 
     # convenience for tests -------------------------------------------------------------------------
     def state_dict(self):
