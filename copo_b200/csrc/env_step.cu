@@ -344,16 +344,18 @@ int b2c_env_create(const b2c_env_config* c, const uint32_t* map_blob, int map_wo
     e->tile_words = NUM_FIELDS * k.AP + HEADER_WORDS;
     B2C_CUDA_OR(cudaGetDevice(&e->device), delete e);
     B2C_CUDA_OR(cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, e->device), delete e);
-    // scenes per CTA: one thread per slot in the per-slot phases, as many scenes as keep two CTAs per SM
-    e->threads = ENV_MAX_THREADS;
+    // scenes per CTA: one thread per slot in the per-slot phases, as many scenes as keep four CTAs per SM
+    // (measured on B200, profiles/r01_sweep.txt: small CTAs hide the phase barriers best)
+    e->threads = 128;
     if (const char* t = getenv("B2C_ENV_THREADS")) e->threads = atoi(t);
-    if (e->threads < 32 || e->threads > ENV_MAX_THREADS || (e->threads & 31)) e->threads = ENV_MAX_THREADS;
+    if (e->threads < 32 || e->threads > ENV_MAX_THREADS || (e->threads & 31)) e->threads = 128;
+    while (e->threads < k.A) e->threads += 32;
     int fit = e->threads / k.A;
     if (fit > ENV_MAX_GROUP) fit = ENV_MAX_GROUP;
     if (fit > k.S) fit = k.S;
     if (fit < 1) { delete e; return b2c_set_error(B2C_ERR_ARG, "num_slots does not fit one CTA"); }
     e->group = fit;
-    while (e->group > 1 && smem_plan(e->group, k.A, k.D, map_words, e->tile_words).total > 112 * 1024) e->group -= 1;
+    while (e->group > 1 && smem_plan(e->group, k.A, k.D, map_words, e->tile_words).total > 56 * 1024) e->group -= 1;
     if (const char* g = getenv("B2C_ENV_GROUP")) {
         int gg = atoi(g);
         if (gg >= 1 && gg <= fit) e->group = gg;
