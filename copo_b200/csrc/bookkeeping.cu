@@ -1,0 +1,279 @@
+// bookkeeping.cu - CoPO rollout bookkeeping on the device (rows a8-a13, a15 of SURVEY.md section 8) + optimiser.
+//
+//   gae3                three reverse scans (native / neighbourhood / global) over the [T][N] rollout columns
+//                       (rllib compute_advantages; torch_copo/algo_copo.py:189-204, 473-502; bootstrap rule
+//                       algo_ccppo.py:362-365)
+//   lcf_mix_stats/apply LCF-mixed advantage + whole-batch standardisation (algo_copo.py:539-551)
+//   cc_obs_fuse         centralized-critic observation: mean-field / concat / none (algo_ccppo.py:225-355)
+//   gather_rows         minibatch assembly (rllib minibatches(): shuffled row subsets)
+//   adam_step, dot      torch.optim.Adam update (PPO lr 3e-4, LCF lr 1e-4) and <g_new, g_old> (algo_copo.py:274-278)
+// All HBM-bound: one pass over their inputs, coalesced along the slot/row dimension.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include "b2c_internal.h"
+
+namespace b2c {
+
+constexpr int FLAG_VALID = 1, FLAG_DONE = 2;
+
+struct GaeArgs {
+    const uint8_t* flags;          // [T][N]
+    const float* rew[3];           // [T][N] (head 2 may be per scene: index n / g_div)
+    const float* val[3];           // [T][N]
+    float* adv[3];
+    float* tgt[3];
+    int T, N, heads, g_div;        // g_div: slots per scene when the global reward is stored per scene, else 1
+    int g_ld;                      // row length of rew[2]
+    float gamma, lambda_;
+};
+
+__global__ void gae3_kernel(const GaeArgs a) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= a.N) return;
+    double nv[3] = {0, 0, 0}, nadv[3] = {0, 0, 0};
+    bool has_next = false;
+    for (int t = a.T - 1; t >= 0; --t) {
+        const size_t idx = (size_t)t * a.N + n;
+        const int f = a.flags[idx];
+        if (!(f & FLAG_VALID)) {
+            for (int h = 0; h < a.heads; ++h) { a.adv[h][idx] = 0.0f; a.tgt[h][idx] = 0.0f; }
+            continue;
+        }
+        const bool done = f & FLAG_DONE;
+        for (int h = 0; h < a.heads; ++h) {
+            const double g = (h == 2) ? 1.0 : (double)a.gamma;              // global head: gamma = 1 (algo_copo.py:498)
+            const float r = (h == 2) ? a.rew[2][(size_t)t * a.g_ld + n / a.g_div] : a.rew[h][idx];
+            const double v = (double)a.val[h][idx];
+            double next_v = nv[h], next_adv = nadv[h];
+            if (done) { next_v = 0.0; next_adv = 0.0; }
+            else if (!has_next) { next_v = v; next_adv = 0.0; }            // fragment cut: bootstrap with own value
+            const double delta = (double)r + g * next_v - v;
+            const double adv = delta + g * (double)a.lambda_ * next_adv;
+            a.adv[h][idx] = (float)adv;
+            a.tgt[h][idx] = (float)(adv + v);
+            nv[h] = v; nadv[h] = adv;
+        }
+        has_next = true;
+    }
+}
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float lcf_mix(float adv, float nei, float lcf) {
+    float phi = lcf * 3.14159274f * 0.5f;                                  // step_lcf * np.pi / 2 in float32
+    return cosf(phi) * adv + sinf(phi) * nei;
+}
+
+// out[0..2] = sum x, sum x^2, count over valid rows of the mixed advantage; out[3..4] = sum, sum^2 of global adv
+__global__ void lcf_mix_stats_kernel(const uint8_t* __restrict__ flags, const float* __restrict__ adv,
+                                     const float* __restrict__ nei, const float* __restrict__ lcf,
+                                     const float* __restrict__ gadv, size_t rows, double* __restrict__ out) {
+    double s = 0, s2 = 0, c = 0, g = 0, g2 = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (size_t)gridDim.x * blockDim.x) {
+        if (flags && !(flags[i] & FLAG_VALID)) continue;
+        float x = nei ? lcf_mix(adv[i], nei[i], lcf[i]) : adv[i];
+        s += x; s2 += (double)x * x; c += 1.0;
+        if (gadv) { float y = gadv[i]; g += y; g2 += (double)y * y; }
+    }
+    s = warp_sum_d(s); s2 = warp_sum_d(s2); c = warp_sum_d(c); g = warp_sum_d(g); g2 = warp_sum_d(g2);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&out[0], s); atomicAdd(&out[1], s2); atomicAdd(&out[2], c);
+        atomicAdd(&out[3], g); atomicAdd(&out[4], g2);
+    }
+}
+
+__global__ void lcf_mix_apply_kernel(const uint8_t* __restrict__ flags, const float* __restrict__ adv,
+                                     const float* __restrict__ nei, const float* __restrict__ lcf,
+                                     float* __restrict__ gadv, float* __restrict__ norm_adv, size_t rows, float mean,
+                                     float inv_std, float gmean, float ginv_std) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (size_t)gridDim.x * blockDim.x) {
+        bool valid = !flags || (flags[i] & FLAG_VALID);
+        float x = nei ? lcf_mix(adv[i], nei[i], lcf[i]) : adv[i];
+        norm_adv[i] = valid ? (x - mean) * inv_std : 0.0f;
+        if (gadv) gadv[i] = valid ? (gadv[i] - gmean) * ginv_std : 0.0f;
+    }
+}
+
+// one warp per (t, slot) row.  mode 0: none (copy), 1: mean field, 2: concat of the 4 nearest
+__global__ void cc_obs_fuse_kernel(const float* __restrict__ obs, const float* __restrict__ act,
+                                   const uint8_t* __restrict__ flags, const unsigned long long* __restrict__ mf_mask,
+                                   const int8_t* __restrict__ nei_list, float* __restrict__ cobs, size_t rows, int A,
+                                   int D, int AD, int C, int mode, int counterfactual) {
+    const int lane = threadIdx.x & 31;
+    const size_t row = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    float* out = cobs + row * C;
+    const float* own = obs + row * D;
+    const bool valid = flags[row] & FLAG_VALID;
+    for (int d = lane; d < C; d += 32) out[d] = (d < D && valid) ? own[d] : 0.0f;
+    if (!valid || mode == 0) return;
+    const size_t scene_row0 = row - (row % A);            // first slot of this (t, scene)
+    if (mode == 1) {
+        unsigned long long m = mf_mask[row];
+        int cnt = 0;
+        for (unsigned long long mm = m; mm; mm &= mm - 1) {
+            int j = __ffsll((long long)mm) - 1;
+            if (flags[scene_row0 + j] & FLAG_VALID) ++cnt;
+        }
+        if (cnt == 0) return;
+        const float inv = 1.0f / (float)cnt;
+        const int W = D + (counterfactual ? AD : 0);
+        for (int d = lane; d < W; d += 32) {
+            float s = 0.0f;
+            for (unsigned long long mm = m; mm; mm &= mm - 1) {
+                int j = __ffsll((long long)mm) - 1;
+                size_t r = scene_row0 + j;
+                if (!(flags[r] & FLAG_VALID)) continue;
+                s += (d < D) ? obs[r * D + d] : act[r * AD + (d - D)];
+            }
+            out[D + d] = s * inv;
+        }
+    } else {
+        const int W = D + (counterfactual ? AD : 0);
+        for (int k = 0; k < 4; ++k) {
+            int j = nei_list[row * 4 + k];
+            if (j < 0) continue;
+            size_t r = scene_row0 + j;
+            if (!(flags[r] & FLAG_VALID)) continue;
+            for (int d = lane; d < W; d += 32)
+                out[D + k * W + d] = (d < D) ? obs[r * D + d] : act[r * AD + (d - D)];
+        }
+    }
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ src, size_t ld_src, const int64_t* __restrict__ idx,
+                                   float* __restrict__ dst, size_t ld_dst, size_t rows, int width) {
+    const int lane = threadIdx.x & 31;
+    const size_t row = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float* s = src + (size_t)idx[row] * ld_src;
+    float* d = dst + row * ld_dst;
+    for (int k = lane; k < width; k += 32) d[k] = s[k];
+}
+
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, size_t n, float step_size, float inv_sqrt_bc2, float b1, float b2,
+                            float eps, float grad_scale) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float gi = g[i] * grad_scale;
+        float mi = b1 * m[i] + (1.0f - b1) * gi;
+        float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+        m[i] = mi; v[i] = vi;
+        float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
+        p[i] = p[i] - step_size * (mi / denom);
+    }
+}
+
+__global__ void dot_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t n, double* __restrict__ out) {
+    double s = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        s += (double)a[i] * (double)b[i];
+    s = warp_sum_d(s);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
+}
+
+}  // namespace b2c
+
+using namespace b2c;
+
+static int grid_for(size_t n, int block) {
+    size_t g = (n + block - 1) / block;
+    return (int)(g > 148 * 16 ? 148 * 16 : (g < 1 ? 1 : g));
+}
+
+extern "C" {
+
+int b2c_gae3(const b2c_gae_args* p, void* stream) {
+    if (!p || !p->flags || p->heads < 1 || p->heads > 3 || p->T < 1 || p->N < 1)
+        return b2c_set_error(B2C_ERR_ARG, "b2c_gae3: bad argument");
+    GaeArgs a;
+    a.flags = p->flags; a.T = p->T; a.N = p->N; a.heads = p->heads; a.gamma = p->gamma; a.lambda_ = p->lambda_;
+    a.g_div = p->global_reward_per_scene > 0 ? p->global_reward_per_scene : 1;
+    a.g_ld = p->global_reward_per_scene > 0 ? p->N / p->global_reward_per_scene : p->N;
+    for (int h = 0; h < 3; ++h) {
+        a.rew[h] = p->rewards[h]; a.val[h] = p->values[h]; a.adv[h] = p->advantages[h]; a.tgt[h] = p->targets[h];
+        if (h < p->heads && (!a.rew[h] || !a.val[h] || !a.adv[h] || !a.tgt[h]))
+            return b2c_set_error(B2C_ERR_ARG, "b2c_gae3: head %d has a null column", h);
+    }
+    gae3_kernel<<<(p->N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
+    B2C_CUDA(cudaGetLastError());
+    return B2C_OK;
+}
+
+int b2c_lcf_mix_stats(const uint8_t* flags, const float* adv, const float* nei_adv, const float* step_lcf,
+                      const float* global_adv, size_t rows, double* out5, void* stream) {
+    if (!adv || !out5 || (nei_adv && !step_lcf)) return b2c_set_error(B2C_ERR_ARG, "b2c_lcf_mix_stats: bad argument");
+    if (rows == 0) return B2C_OK;
+    lcf_mix_stats_kernel<<<grid_for(rows, 256), 256, 0, (cudaStream_t)stream>>>(flags, adv, nei_adv, step_lcf, global_adv,
+                                                                               rows, out5);
+    B2C_CUDA(cudaGetLastError());
+    return B2C_OK;
+}
+
+int b2c_lcf_mix_apply(const uint8_t* flags, const float* adv, const float* nei_adv, const float* step_lcf,
+                      float* global_adv, float* normalized_adv, size_t rows, float mean, float std, float gmean,
+                      float gstd, void* stream) {
+    if (!adv || !normalized_adv) return b2c_set_error(B2C_ERR_ARG, "b2c_lcf_mix_apply: bad argument");
+    if (rows == 0) return B2C_OK;
+    float s = std > 1e-4f ? std : 1e-4f, gs = gstd > 1e-4f ? gstd : 1e-4f;      // max(1e-4, std): rllib standardized
+    lcf_mix_apply_kernel<<<grid_for(rows, 256), 256, 0, (cudaStream_t)stream>>>(flags, adv, nei_adv, step_lcf, global_adv,
+                                                                               normalized_adv, rows, mean, 1.0f / s,
+                                                                               gmean, 1.0f / gs);
+    B2C_CUDA(cudaGetLastError());
+    return B2C_OK;
+}
+
+int b2c_cc_obs_fuse(const float* obs, const float* actions, const uint8_t* flags, const uint64_t* mf_mask,
+                    const int8_t* nei_list, float* cobs, size_t rows, int slots, int obs_dim, int act_dim, int cobs_dim,
+                    int mode, int counterfactual, void* stream) {
+    if (!obs || !flags || !cobs || slots < 1 || mode < 0 || mode > 2)
+        return b2c_set_error(B2C_ERR_ARG, "b2c_cc_obs_fuse: bad argument");
+    int n_other = mode == 0 ? 0 : (mode == 1 ? 1 : 4);
+    int want = obs_dim + n_other * (obs_dim + (counterfactual ? act_dim : 0));
+    if (cobs_dim != want) return b2c_set_error(B2C_ERR_ARG, "b2c_cc_obs_fuse: cobs_dim %d, expected %d (algo_ccppo.py:55-71)", cobs_dim, want);
+    if ((mode == 1 && !mf_mask) || (mode == 2 && !nei_list) || (mode && counterfactual && !actions))
+        return b2c_set_error(B2C_ERR_ARG, "b2c_cc_obs_fuse: missing neighbour columns");
+    if (rows == 0) return B2C_OK;
+    size_t blocks = (rows + 7) / 8;
+    cc_obs_fuse_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(obs, actions, flags, (const unsigned long long*)mf_mask,
+                                                                          nei_list, cobs, rows, slots, obs_dim, act_dim,
+                                                                          cobs_dim, mode, counterfactual);
+    B2C_CUDA(cudaGetLastError());
+    return B2C_OK;
+}
+
+int b2c_gather_rows(const float* src, size_t ld_src, const int64_t* idx, float* dst, size_t ld_dst, size_t rows, int width,
+                    void* stream) {
+    if (!src || !idx || !dst || width < 1) return b2c_set_error(B2C_ERR_ARG, "b2c_gather_rows: bad argument");
+    if (rows == 0) return B2C_OK;
+    size_t blocks = (rows + 7) / 8;
+    gather_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, ld_src, idx, dst, ld_dst, rows, width);
+    B2C_CUDA(cudaGetLastError());
+    return B2C_OK;
+}
+
+int b2c_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1,
+                  float beta2, float eps, int step, float grad_scale, void* stream) {
+    if (!param || !grad || !exp_avg || !exp_avg_sq || step < 1) return b2c_set_error(B2C_ERR_ARG, "b2c_adam_step: bad argument");
+    if (n == 0) return B2C_OK;
+    double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
+    adam_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, (float)(lr / bc1),
+                                                                   (float)(1.0 / sqrt(bc2)), beta1, beta2, eps, grad_scale);
+    B2C_CUDA(cudaGetLastError());
+    return B2C_OK;
+}
+
+int b2c_dot(const float* a, const float* b, size_t n, double* out, void* stream) {
+    if (!a || !b || !out) return b2c_set_error(B2C_ERR_ARG, "b2c_dot: null argument");
+    if (n == 0) return B2C_OK;
+    dot_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(a, b, n, out);
+    B2C_CUDA(cudaGetLastError());
+    return B2C_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,243 @@
+"""Policy / value networks of IPPO, CCPPO and CoPO on the CUDA kernels of libcopo_b200.so.
+
+Mirrors the reference's model interface (torch_copo/algo_ccppo.py:74-219 `CCModel`, algo_copo.py:96-182 `CoPOModel`):
+`forward(obs) -> logits`, `central_value_function(cobs)`, `get_nei_value`, `get_global_value`, `value_function()`
+raising, `compute_coordinated`, `lcf_mean / lcf_std / lcf_parameters`, and a `state_dict()` whose keys are RLlib's
+(`_hidden_layers.0._model.0.weight`, `_logits._model.0.bias`, `_value_branch_separate.1._model.0.weight`,
+`nei_value_network.2._model.0.weight`, ...), so the shipped `best_checkpoints/ccppo_*.npz` load directly and the TF-era
+`ippo_* / cl_* / copo_*` files load through `load_policy_npz` (copo/eval/get_policy_function.py:54-98 naming).
+
+All network parameters live in one flat float32 device buffer (one Adam launch, one gradient all-reduce); a second
+flat buffer holds the gradients.  There is no autograd in here: backward is the hand-written kernels.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import ops
+
+
+def centralized_critic_obs_dim(obs_dim, act_dim, counterfactual=True, num_neighbours=4, fuse_mode="mf"):
+    """algo_ccppo.py:55-71."""
+    if fuse_mode not in ("concat", "mf", "none"):
+        raise ValueError("Unknown fuse mode: %s" % fuse_mode)
+    n = {"concat": num_neighbours, "mf": 1, "none": 0}[fuse_mode] + 1
+    d = n * obs_dim
+    if counterfactual:
+        d += (n - 1) * act_dim
+    return d
+
+
+class _Net:
+    """One 3-layer tanh MLP: views into the model's flat parameter / gradient buffers."""
+
+    def __init__(self, names, in_dim, hiddens, out_dim):
+        self.names, self.in_dim, self.hiddens, self.out_dim = names, in_dim, tuple(hiddens), out_dim
+        dims = [in_dim] + list(hiddens) + [out_dim]
+        self.shapes = [(dims[k + 1], dims[k]) for k in range(len(dims) - 1)]
+        self.W, self.b, self.dW, self.db = [], [], [], []
+
+    def numel(self):
+        return sum(o * i + o for o, i in self.shapes)
+
+    def bind(self, flat, gflat, offset):
+        self.offset = offset
+        for o, i in self.shapes:
+            self.W.append(flat[offset:offset + o * i].view(o, i))
+            self.dW.append(gflat[offset:offset + o * i].view(o, i))
+            offset += o * i
+            self.b.append(flat[offset:offset + o])
+            self.db.append(gflat[offset:offset + o])
+            offset += o
+        self.end = offset
+        return offset
+
+    def init(self, gen):
+        n_layers = len(self.shapes)
+        for k, (o, i) in enumerate(self.shapes):
+            std = 1.0 if k < n_layers - 1 else 0.01                      # normc_initializer(1.0) / (0.01)
+            w = torch.randn(o, i, generator=gen)
+            w *= std / torch.sqrt(w.pow(2).sum(1, keepdim=True))
+            self.W[k].copy_(w)
+            self.b[k].zero_()
+
+    # inference: no activations kept
+    def forward(self, x):
+        h = x
+        for k in range(len(self.shapes)):
+            last = k == len(self.shapes) - 1
+            h = ops.linear_forward(h, self.W[k], self.b[k], 0 if last else 1)
+        return h
+
+    def forward_train(self, x):
+        acts = [x]
+        for k in range(len(self.shapes)):
+            last = k == len(self.shapes) - 1
+            acts.append(ops.linear_forward(acts[-1], self.W[k], self.b[k], 0 if last else 1))
+        return acts                                                     # [x, h1, h2, out]
+
+    def backward(self, acts, dout):
+        """Accumulates dW / db of every layer given d(loss)/d(out)."""
+        d = dout
+        for k in reversed(range(len(self.shapes))):
+            d = ops.linear_backward(d, acts[k], self.W[k], self.dW[k], self.db[k], h_prev_is_tanh=(k > 0),
+                                    need_dx=(k > 0))
+
+
+class CCModel:
+    POLICY = ("_hidden_layers.0._model.0", "_hidden_layers.1._model.0", "_logits._model.0")
+    VALUE = ("_value_branch_separate.0._model.0", "_value_branch_separate.1._model.0", "_value_branch._model.0")
+
+    def __init__(self, obs_dim, act_dim=2, hiddens=(256, 256), fuse_mode="none", counterfactual=True, num_neighbours=4,
+                 device=None, seed=0, critic_obs_dim=None):
+        self.obs_dim, self.act_dim, self.num_outputs = int(obs_dim), int(act_dim), 2 * int(act_dim)
+        self.custom = dict(fuse_mode=fuse_mode, counterfactual=counterfactual, num_neighbours=num_neighbours)
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.cobs_dim = critic_obs_dim if critic_obs_dim is not None else self.get_centralized_critic_obs_dim()
+        self.nets = {"policy": _Net(self.POLICY, self.obs_dim, hiddens, self.num_outputs),
+                     "value": _Net(self.VALUE, self.cobs_dim, hiddens, 1)}
+        self._extra_nets(hiddens)
+        self._allocate(seed)
+        self.tower_stats = {}
+
+    def _extra_nets(self, hiddens):
+        pass
+
+    def get_centralized_critic_obs_dim(self):
+        return centralized_critic_obs_dim(self.obs_dim, self.act_dim, self.custom["counterfactual"],
+                                          self.custom["num_neighbours"], self.custom["fuse_mode"])
+
+    def _allocate(self, seed):
+        n = sum(net.numel() for net in self.nets.values())
+        self.flat = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self.grad = torch.zeros(n, dtype=torch.float32, device=self.device)
+        off = 0
+        for net in self.nets.values():
+            off = net.bind(self.flat, self.grad, off)
+        gen = torch.Generator().manual_seed(seed)
+        for net in self.nets.values():
+            net.init(gen)
+
+    # ---- reference interface -------------------------------------------------------------------------------
+    def forward(self, obs, state=None, seq_lens=None):
+        if isinstance(obs, dict):
+            obs = obs.get("obs_flat", obs.get("obs"))
+        obs = obs.reshape(obs.shape[0], -1)
+        logits = self.nets["policy"].forward(obs)
+        return logits if state is None else (logits, state)
+
+    __call__ = forward
+
+    def value_function(self):
+        raise ValueError("Centralized Value Function should not be called directly! "
+                         "Call central_value_function(cobs) instead!")
+
+    def central_value_function(self, cobs):
+        return self.nets["value"].forward(cobs).reshape(-1)
+
+    def zero_grad(self):
+        self.grad.zero_()
+
+    def parameters(self):
+        return [self.flat]
+
+    def policy_slice(self):
+        p = self.nets["policy"]
+        return slice(p.offset, p.end)
+
+    def num_parameters(self):
+        return self.flat.numel()
+
+    # ---- checkpoints (RLlib state_dict names) -------------------------------------------------
+    def state_dict(self):
+        out = {}
+        for net in self.nets.values():
+            for name, W, b in zip(net.names, net.W, net.b):
+                out[name + ".weight"] = W.detach().clone()
+                out[name + ".bias"] = b.detach().clone()
+        return out
+
+    def load_state_dict(self, sd, strict=True):
+        for net in self.nets.values():
+            for name, W, b in zip(net.names, net.W, net.b):
+                if name + ".weight" not in sd:
+                    if strict:
+                        raise KeyError(name + ".weight")
+                    continue
+                W.copy_(torch.as_tensor(np.asarray(sd[name + ".weight"]), dtype=torch.float32))
+                b.copy_(torch.as_tensor(np.asarray(sd[name + ".bias"]), dtype=torch.float32))
+
+    def load_policy_npz(self, path_or_dict):
+        """Policy-only weights in either naming of best_checkpoints/*.npz (get_policy_function.py:54-98)."""
+        w = path_or_dict if isinstance(path_or_dict, dict) else dict(np.load(path_or_dict))
+        keys = list(w.keys())
+        net = self.nets["policy"]
+        if self.POLICY[0] + ".weight" in keys:
+            for name, W, b in zip(net.names, net.W, net.b):
+                W.copy_(torch.as_tensor(w[name + ".weight"]))
+                b.copy_(torch.as_tensor(w[name + ".bias"]))
+            return
+        suffix = "_1" if any(k.endswith("fc_1_1/kernel") for k in keys) else ""
+        for layer, W, b in zip(("fc_1", "fc_2", "fc_out"), net.W, net.b):
+            k = [x for x in keys if x.endswith("/%s%s/kernel" % (layer, suffix))][0]
+            W.copy_(torch.as_tensor(np.ascontiguousarray(w[k].T)))           # TF kernels are stored [in, out]
+            b.copy_(torch.as_tensor(w[k.replace("kernel", "bias")]))
+
+
+class CoPOModel(CCModel):
+    NEI = ("nei_value_network.0._model.0", "nei_value_network.1._model.0", "nei_value_network.2._model.0")
+    GLOBAL = ("global_value_network.0._model.0", "global_value_network.1._model.0", "global_value_network.2._model.0")
+
+    def __init__(self, obs_dim, act_dim=2, hiddens=(256, 256), fuse_mode="none", counterfactual=True, num_neighbours=4,
+                 initial_lcf_std=0.1, use_distributional_lcf=True, device=None, seed=0):
+        self.use_distributional_lcf = use_distributional_lcf
+        super().__init__(obs_dim, act_dim, hiddens, fuse_mode, counterfactual, num_neighbours, device, seed)
+        init = [0.0, math.log(initial_lcf_std)] if use_distributional_lcf else [0.0]
+        self.lcf_parameters = torch.tensor(init, dtype=torch.float32, device=self.device)     # algo_copo.py:120-124
+        self.lcf_grad = torch.zeros_like(self.lcf_parameters)
+
+    def _extra_nets(self, hiddens):
+        self.nets["nei"] = _Net(self.NEI, self.cobs_dim, hiddens, 1)
+        self.nets["global"] = _Net(self.GLOBAL, self.cobs_dim, hiddens, 1)
+
+    def get_nei_value(self, cobs):
+        return self.nets["nei"].forward(cobs).reshape(-1)
+
+    def get_global_value(self, cobs):
+        return self.nets["global"].forward(cobs).reshape(-1)
+
+    @property
+    def lcf_mean(self):
+        return torch.clamp(torch.tanh(self.lcf_parameters[0]), -1 + 1e-6, 1 - 1e-6)          # algo_copo.py:171-172
+
+    @property
+    def lcf_std(self):
+        if not self.use_distributional_lcf:
+            return None
+        return torch.exp(torch.clamp(self.lcf_parameters[1], -20, 2))                         # algo_copo.py:175-177
+
+    @property
+    def lcf_dist(self):
+        if not self.use_distributional_lcf:
+            return None
+        return torch.distributions.normal.Normal(self.lcf_mean, self.lcf_std)
+
+    def compute_coordinated(self, ego, neighbor, eps=None):
+        if self.use_distributional_lcf:
+            if eps is None:
+                eps = torch.randn_like(ego)
+            lcf_rad = (self.lcf_mean + self.lcf_std * eps) * np.pi / 2
+        else:
+            lcf_rad = self.lcf_mean * np.pi / 2
+        return torch.cos(lcf_rad) * ego + torch.sin(lcf_rad) * neighbor
+
+    def state_dict(self):
+        out = super().state_dict()
+        out["lcf_parameters"] = self.lcf_parameters.detach().clone()
+        return out
+
+    def load_state_dict(self, sd, strict=True):
+        super().load_state_dict(sd, strict)
+        if "lcf_parameters" in sd:
+            self.lcf_parameters.copy_(torch.as_tensor(np.asarray(sd["lcf_parameters"]), dtype=torch.float32))

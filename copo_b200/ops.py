@@ -1,0 +1,223 @@
+"""Torch-tensor front ends of the C-ABI compute entry points (include/copo_b200.h).  Every function enqueues
+hand-written CUDA kernels of libcopo_b200.so on the current torch stream; torch only owns the memory.  There is no
+CPU implementation: calling these without the library or without an sm_100 device raises."""
+import ctypes
+
+import torch
+
+from . import _lib
+
+c_int, c_float, c_size_t, c_u32 = ctypes.c_int, ctypes.c_float, ctypes.c_size_t, ctypes.c_uint32
+P = _lib.ptr
+
+
+def _f32(t):
+    assert t.is_cuda and t.dtype == torch.float32, (t.device, t.dtype)
+    return t
+
+
+def _rows2d(t):
+    """(pointer, rows, cols, row stride) of a float32 CUDA matrix whose last dim is contiguous."""
+    _f32(t)
+    assert t.dim() == 2 and t.stride(1) == 1, (t.shape, t.stride())
+    return ctypes.c_void_p(t.data_ptr()), t.shape[0], t.shape[1], t.stride(0)
+
+
+class PpoHeadArgs(ctypes.Structure):
+    _fields_ = ([(n, ctypes.c_void_p) for n in ("logits", "actions", "old_logp", "old_logits", "adv")] +
+                [("v_cur", ctypes.c_void_p * 3), ("v_old", ctypes.c_void_p * 3), ("v_tgt", ctypes.c_void_p * 3),
+                 ("dlogits", ctypes.c_void_p), ("dv", ctypes.c_void_p * 3), ("stats", ctypes.c_void_p),
+                 ("rows", ctypes.c_int32), ("n_heads", ctypes.c_int32), ("mode", ctypes.c_int32)] +
+                [(n, ctypes.c_float) for n in ("clip_param", "vf_clip_param", "vf_loss_coeff", "entropy_coeff",
+                                               "kl_coeff")])
+
+
+class GaeArgs(ctypes.Structure):
+    _fields_ = [("flags", ctypes.c_void_p), ("rewards", ctypes.c_void_p * 3), ("values", ctypes.c_void_p * 3),
+                ("advantages", ctypes.c_void_p * 3), ("targets", ctypes.c_void_p * 3), ("T", ctypes.c_int32),
+                ("N", ctypes.c_int32), ("heads", ctypes.c_int32), ("global_reward_per_scene", ctypes.c_int32),
+                ("gamma", ctypes.c_float), ("lambda_", ctypes.c_float)]
+
+
+def _lib_ready():
+    return _lib.require_device()
+
+
+def _dp(t):
+    return t.data_ptr() if t is not None else None
+
+
+# ---- linear layers -----------------------------------------------------------------------------------------------
+def linear_forward(x, W, b, act, out=None):
+    """act(x W^T + b); x [M, K], W [N, K] (torch Linear layout)."""
+    lib = _lib_ready()
+    px, M, K, ldx = _rows2d(x)
+    N = W.shape[0]
+    assert W.shape == (N, K) and W.is_contiguous()
+    y = out if out is not None else torch.empty((M, N), dtype=torch.float32, device=x.device)
+    py, _, _, ldy = _rows2d(y)
+    if N <= 8:
+        assert act == 0
+        _lib.check(lib.b2c_head_forward(px, c_int(ldx), P(_f32(W)), P(b), py, c_int(ldy), c_int(M), c_int(K), c_int(N),
+                                        _lib.stream_ptr()))
+    else:
+        _lib.check(lib.b2c_linear_forward(px, c_int(ldx), P(_f32(W)), P(b), py, c_int(ldy), c_int(M), c_int(K),
+                                          c_int(N), c_int(act), _lib.stream_ptr()))
+    return y
+
+
+def linear_backward(dy, x, W, dW, db, h_prev_is_tanh, need_dx=True, dx_out=None):
+    """Backward of y = x W^T + b given dy.  Accumulates dW / db; returns dz_prev = (dy W) * (1 - x^2) when x is a tanh
+    output (h_prev_is_tanh), else dy W; None when need_dx is False."""
+    lib = _lib_ready()
+    pdy, M, N, ldy = _rows2d(dy)
+    px, _, K, ldx = _rows2d(x)
+    assert W.shape == (N, K)
+    dx = None
+    if need_dx:
+        dx = dx_out if dx_out is not None else torch.empty((M, K), dtype=torch.float32, device=dy.device)
+    if N <= 8:
+        pdx = P(dx)
+        _lib.check(lib.b2c_head_backward(pdy, c_int(ldy), px, c_int(ldx), P(W), pdx, c_int(dx.stride(0) if need_dx else 0),
+                                         P(dW), P(db), c_int(M), c_int(K), c_int(N), c_int(1 if h_prev_is_tanh else 0),
+                                         _lib.stream_ptr()))
+        return dx
+    _lib.check(lib.b2c_linear_backward_weight(pdy, c_int(ldy), px, c_int(ldx), P(dW), P(db), c_int(M), c_int(K), c_int(N),
+                                              _lib.stream_ptr()))
+    if need_dx:
+        _lib.check(lib.b2c_linear_backward_input(pdy, c_int(ldy), P(W), px if h_prev_is_tanh else None, c_int(ldx), P(dx),
+                                                 c_int(dx.stride(0)), c_int(M), c_int(K), c_int(N), _lib.stream_ptr()))
+    return dx
+
+
+def gaussian_sample(logits, eps=None, seed=0, step=0, deterministic=False, want_eps=False):
+    lib = _lib_ready()
+    M = logits.shape[0]
+    assert logits.shape == (M, 4) and logits.is_contiguous()
+    actions = torch.empty((M, 2), dtype=torch.float32, device=logits.device)
+    logp = torch.empty((M,), dtype=torch.float32, device=logits.device)
+    eps_out = torch.empty((M, 2), dtype=torch.float32, device=logits.device) if want_eps else None
+    _lib.check(lib.b2c_gaussian_sample(P(_f32(logits)), P(eps), P(actions), P(logp), P(eps_out), c_int(M),
+                                       c_u32(seed & 0xFFFFFFFF), c_u32(step & 0xFFFFFFFF), c_int(int(deterministic)),
+                                       _lib.stream_ptr()))
+    return (actions, logp, eps_out) if want_eps else (actions, logp)
+
+
+def ppo_head(logits, actions, old_logp, old_logits, adv, heads, cfg, mode=0, stats=None):
+    """heads: list of (v_cur, v_old, v_tgt) triples.  Returns (dlogits, [dv...], stats[8] float64)."""
+    lib = _lib_ready()
+    M = logits.shape[0]
+    dev = logits.device
+    dlogits = torch.empty((M, 4), dtype=torch.float32, device=dev)
+    dvs = [torch.empty((M,), dtype=torch.float32, device=dev) for _ in heads]
+    if stats is None:
+        stats = torch.zeros(8, dtype=torch.float64, device=dev)
+    a = PpoHeadArgs()
+    a.logits, a.actions = _dp(logits), _dp(actions)
+    a.old_logp, a.old_logits, a.adv = _dp(old_logp), _dp(old_logits), _dp(adv)
+    for k, (vc, vo, vt) in enumerate(heads):
+        for t in (vc, vo, vt):
+            assert t.is_contiguous() and t.dtype == torch.float32 and t.numel() == M
+        a.v_cur[k], a.v_old[k], a.v_tgt[k], a.dv[k] = vc.data_ptr(), vo.data_ptr(), vt.data_ptr(), dvs[k].data_ptr()
+    a.dlogits, a.stats = dlogits.data_ptr(), stats.data_ptr()
+    a.rows, a.n_heads, a.mode = M, len(heads), mode
+    a.clip_param, a.vf_clip_param = cfg["clip_param"], cfg["vf_clip_param"]
+    a.vf_loss_coeff, a.entropy_coeff, a.kl_coeff = cfg["vf_loss_coeff"], cfg["entropy_coeff"], cfg["kl_coeff"]
+    _lib.check(lib.b2c_ppo_head(ctypes.byref(a), _lib.stream_ptr()))
+    return dlogits, dvs, stats
+
+
+def lcf_meta_terms(adv, nei_adv, eps, lcf_mean, lcf_std):
+    lib = _lib_ready()
+    out = torch.zeros(3, dtype=torch.float64, device=adv.device)
+    _lib.check(lib.b2c_lcf_meta_terms(P(_f32(adv)), P(_f32(nei_adv)), P(_f32(eps)), c_int(adv.numel()),
+                                      c_float(lcf_mean), c_float(lcf_std), P(out), _lib.stream_ptr()))
+    return out
+
+
+# ---- rollout bookkeeping ------------------------------------------------------------------------------------------
+def gae3(flags, rewards, values, gamma, lambda_, global_reward_per_scene=0):
+    """flags uint8 [T, N]; rewards / values: lists of 1 or 3 float32 [T, N] tensors (the global reward may be [T, S]
+    with global_reward_per_scene = slots per scene).  Returns (advantages, targets) lists."""
+    lib = _lib_ready()
+    T, N = flags.shape
+    heads = len(values)
+    adv = [torch.empty((T, N), dtype=torch.float32, device=flags.device) for _ in range(heads)]
+    tgt = [torch.empty((T, N), dtype=torch.float32, device=flags.device) for _ in range(heads)]
+    a = GaeArgs()
+    a.flags = flags.data_ptr()
+    for h in range(heads):
+        assert rewards[h].is_contiguous() and values[h].is_contiguous()
+        a.rewards[h], a.values[h] = rewards[h].data_ptr(), values[h].data_ptr()
+        a.advantages[h], a.targets[h] = adv[h].data_ptr(), tgt[h].data_ptr()
+    a.T, a.N, a.heads, a.global_reward_per_scene = T, N, heads, global_reward_per_scene
+    a.gamma, a.lambda_ = gamma, lambda_
+    _lib.check(lib.b2c_gae3(ctypes.byref(a), _lib.stream_ptr()))
+    return adv, tgt
+
+
+def lcf_mix_stats(flags, adv, nei_adv, step_lcf, global_adv, out=None):
+    lib = _lib_ready()
+    if out is None:
+        out = torch.zeros(5, dtype=torch.float64, device=adv.device)
+    _lib.check(lib.b2c_lcf_mix_stats(P(flags), P(adv), P(nei_adv), P(step_lcf), P(global_adv), c_size_t(adv.numel()),
+                                     P(out), _lib.stream_ptr()))
+    return out
+
+
+def lcf_mix_apply(flags, adv, nei_adv, step_lcf, global_adv, mean, std, gmean, gstd):
+    lib = _lib_ready()
+    norm = torch.empty_like(adv)
+    _lib.check(lib.b2c_lcf_mix_apply(P(flags), P(adv), P(nei_adv), P(step_lcf), P(global_adv), P(norm),
+                                     c_size_t(adv.numel()), c_float(mean), c_float(std), c_float(gmean), c_float(gstd),
+                                     _lib.stream_ptr()))
+    return norm
+
+
+def stats_to_mean_std(sum_, sumsq, n):
+    mean = sum_ / max(n, 1.0)
+    var = max(sumsq / max(n, 1.0) - mean * mean, 0.0)
+    return mean, var ** 0.5
+
+
+def cc_obs_fuse(obs, actions, flags, mf_mask, nei_list, slots, mode, counterfactual=True):
+    """obs [R, D] with R ordered [t][scene][slot]; mode 'none' | 'mf' | 'concat'."""
+    lib = _lib_ready()
+    R, D = obs.shape
+    AD = actions.shape[1] if actions is not None else 2
+    m = {"none": 0, "mf": 1, "concat": 2}[mode]
+    n_other = (0, 1, 4)[m]
+    C = D + n_other * (D + (AD if counterfactual else 0))
+    cobs = torch.empty((R, C), dtype=torch.float32, device=obs.device)
+    _lib.check(lib.b2c_cc_obs_fuse(P(obs), P(actions), P(flags), P(mf_mask), P(nei_list), P(cobs), c_size_t(R), c_int(slots),
+                                   c_int(D), c_int(AD), c_int(C), c_int(m), c_int(int(counterfactual)), _lib.stream_ptr()))
+    return cobs
+
+
+def gather_rows(src, idx, out=None):
+    lib = _lib_ready()
+    src2 = src if src.dim() == 2 else src.unsqueeze(1)
+    assert src2.stride(1) == 1 and idx.dtype == torch.int64 and idx.is_contiguous()
+    R, Wd = idx.numel(), src2.shape[1]
+    dst = out if out is not None else torch.empty((R, Wd), dtype=torch.float32, device=src.device)
+    _lib.check(lib.b2c_gather_rows(P(src2) if src2.is_contiguous() else ctypes.c_void_p(src2.data_ptr()),
+                                   c_size_t(src2.stride(0)), P(idx), ctypes.c_void_p(dst.data_ptr()),
+                                   c_size_t(dst.stride(0)), c_size_t(R), c_int(Wd), _lib.stream_ptr()))
+    return dst if src.dim() == 2 else dst.squeeze(1)
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, lr, step, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
+    lib = _lib_ready()
+    for t in (param, grad, exp_avg, exp_avg_sq):
+        assert t.is_contiguous() and t.dtype == torch.float32 and t.numel() == param.numel()
+    _lib.check(lib.b2c_adam_step(P(param), P(grad), P(exp_avg), P(exp_avg_sq), c_size_t(param.numel()), c_float(lr),
+                                 c_float(beta1), c_float(beta2), c_float(eps), c_int(step), c_float(grad_scale),
+                                 _lib.stream_ptr()))
+
+
+def dot(a, b, out=None):
+    lib = _lib_ready()
+    if out is None:
+        out = torch.zeros(1, dtype=torch.float64, device=a.device)
+    _lib.check(lib.b2c_dot(P(a), P(b), c_size_t(a.numel()), P(out), _lib.stream_ptr()))
+    return out

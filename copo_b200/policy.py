@@ -1,0 +1,365 @@
+"""IPPO / CCPPO / CoPO policies on the CUDA kernels: the reference's hook names with batched semantics.
+
+  IPPOPolicy.loss          torch_copo/algo_ippo.py:79-172
+  CCPPOPolicy.loss         torch_copo/algo_ccppo.py:376-472      postprocess: algo_ccppo.py:322-374
+  CoPOPolicy.loss          torch_copo/algo_copo.py:311-424       postprocess: algo_copo.py:473-502
+  CoPOPolicy.meta_update   torch_copo/algo_copo.py:228-309       assign_lcf / update_old_policy: :442-471
+
+`train_batch` is a dict of device tensors under RLlib's SampleBatch column names.  `loss()` runs forward AND backward
+through the hand-written kernels (gradients land in `model.grad`) and returns the scalar loss tensor; `learn_on_batch`
+adds the data-parallel gradient all-reduce and the Adam step.  `postprocess_rollout` is the batched form of
+`postprocess_trajectory`: it works on whole [T, N] rollout columns instead of one agent's SampleBatch.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import ops
+from .models import CCModel, CoPOModel
+
+# SampleBatch / Postprocessing column names (rllib) and CoPO's own (algo_copo.py:48-60)
+OBS, ACTIONS, ACTION_LOGP, ACTION_DIST_INPUTS = "obs", "actions", "action_logp", "action_dist_inputs"
+REWARDS, DONES, VF_PREDS, ADVANTAGES, VALUE_TARGETS = "rewards", "dones", "vf_preds", "advantages", "value_targets"
+CENTRALIZED_CRITIC_OBS = "centralized_critic_obs"
+NEI_REWARDS, NEI_VALUES, NEI_ADVANTAGE, NEI_TARGET = "nei_rewards", "nei_values", "nei_advantage", "nei_target"
+GLOBAL_REWARDS, GLOBAL_VALUES, GLOBAL_ADVANTAGES, GLOBAL_TARGET = ("global_rewards", "global_values",
+                                                                   "global_advantages", "global_target")
+
+
+class AlgoConfig(dict):
+    """Attribute- and item-indexable config (the reference reads both `config["lcf_lr"]` and `config.lr`)."""
+    __getattr__ = dict.__getitem__
+    __setattr__ = dict.__setitem__
+
+    def update_from_dict(self, d):
+        for k, v in d.items():
+            if isinstance(v, dict) and isinstance(self.get(k), dict):
+                self[k].update(v)
+            else:
+                self[k] = v
+        return self
+
+
+def ippo_config(**over):
+    """IPPOConfig (algo_ippo.py:17-42) on top of the rllib 2.2.0 PPO defaults."""
+    c = AlgoConfig(gamma=0.99, lambda_=0.95, kl_coeff=0.2, kl_target=0.01, vf_loss_coeff=1.0, entropy_coeff=0.0,
+                   clip_param=0.2, vf_clip_param=100.0, old_value_loss=True, use_gae=True, use_critic=True, lr=3e-4,
+                   sgd_minibatch_size=512, rollout_fragment_length=200, train_batch_size=2000, num_sgd_iter=5,
+                   fcnet_hiddens=(256, 256), env_config={}, seed=0)
+    c["lambda"] = c["lambda_"]
+    return c.update_from_dict(over)
+
+
+def ccppo_config(**over):
+    """CCPPOConfig (algo_ccppo.py:37-45)."""
+    c = ippo_config(counterfactual=True, num_neighbours=4, fuse_mode="mf", mf_nei_distance=10)
+    return c.update_from_dict(over)
+
+
+def copo_config(**over):
+    """CoPOConfig (algo_copo.py:63-92)."""
+    c = ccppo_config(initial_lcf_std=0.1, lcf_sgd_minibatch_size=None, lcf_num_iters=5, lcf_lr=1e-4,
+                     use_distributional_lcf=True, use_centralized_critic=False, fuse_mode="none")
+    c.update_from_dict(over)
+    assert c["use_distributional_lcf"]
+    c["env_config"].update(return_native_reward=True, lcf_dist="normal", lcf_normal_std=c["initial_lcf_std"])
+    return c
+
+
+class _Adam:
+    def __init__(self, param, lr):
+        self.param, self.lr, self.step = param, lr, 0
+        self.m, self.v = torch.zeros_like(param), torch.zeros_like(param)
+
+    def apply(self, grad, grad_scale=1.0):
+        self.step += 1
+        ops.adam_step(self.param, grad, self.m, self.v, self.lr, self.step, grad_scale=grad_scale)
+
+
+class IPPOPolicy:
+    algo = "ippo"
+    model_cls = CCModel
+
+    def __init__(self, obs_dim, act_dim=2, config=None, device=None, dist=None):
+        self.config = config if config is not None else self.default_config()
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.obs_dim, self.act_dim = obs_dim, act_dim
+        self.model = self._build_model(self.config.get("seed", 0))
+        self.kl_coeff = float(self.config["kl_coeff"])
+        self.entropy_coeff = float(self.config["entropy_coeff"])
+        self._optimizer = _Adam(self.model.flat, self.config["lr"])
+        self.dist = dist                                 # torch.distributed module when data parallel, else None
+        self.num_grad_updates = 0
+
+    @classmethod
+    def default_config(cls):
+        return ippo_config()
+
+    def _build_model(self, seed):
+        return CCModel(self.obs_dim, self.act_dim, self.config["fcnet_hiddens"], fuse_mode="none", device=self.device,
+                       seed=seed)
+
+    # ---- acting (a7) ---------------------------------------------------------------------------------------
+    def compute_actions(self, obs, eps=None, step=0, deterministic=False):
+        """obs [M, D] -> (actions [M, 2], logp [M], logits [M, 4]).  No squashing / clipping (the env clips)."""
+        logits = self.model.forward(obs)
+        actions, logp = ops.gaussian_sample(logits, eps=eps, seed=self.config.get("seed", 0), step=step,
+                                            deterministic=deterministic)
+        return actions, logp, logits
+
+    def extra_action_out(self, *a, **k):
+        return {}
+
+    # ---- loss (a16 / a17) ----------------------------------------------------------------------------------
+    def _heads(self, train_batch):
+        """[(net name, input column, VF_PREDS-like, target)]"""
+        return [("value", OBS, VF_PREDS, VALUE_TARGETS)]
+
+    def _adv_column(self):
+        return ADVANTAGES
+
+    def loss(self, model, dist_class, train_batch):
+        cfg = dict(clip_param=self.config["clip_param"], vf_clip_param=self.config["vf_clip_param"],
+                   vf_loss_coeff=self.config["vf_loss_coeff"], entropy_coeff=self.entropy_coeff,
+                   kl_coeff=self.kl_coeff)
+        B = train_batch[OBS].shape[0]
+        pol = model.nets["policy"]
+        acts_p = pol.forward_train(train_batch[OBS])
+        head_acts, heads = [], []
+        for net_name, in_col, old_col, tgt_col in self._heads(train_batch):
+            acts = model.nets[net_name].forward_train(train_batch[in_col])
+            head_acts.append((net_name, acts))
+            heads.append((acts[-1].reshape(-1), train_batch[old_col], train_batch[tgt_col]))
+        dlogits, dvs, st = ops.ppo_head(acts_p[-1], train_batch[ACTIONS], train_batch[ACTION_LOGP],
+                                        train_batch[ACTION_DIST_INPUTS], train_batch[self._adv_column()], heads, cfg)
+        pol.backward(acts_p, dlogits)
+        for (net_name, acts), dv in zip(head_acts, dvs):
+            model.nets[net_name].backward(acts, dv.unsqueeze(1))
+        m = st / B
+        total = m[0] + cfg["vf_loss_coeff"] * (m[1] + m[2] + m[3]) - cfg["entropy_coeff"] * m[4] + cfg["kl_coeff"] * m[5]
+        ts = model.tower_stats
+        ts["total_loss"], ts["mean_policy_loss"], ts["mean_vf_loss"] = total, m[0], m[1]
+        ts["mean_entropy"], ts["mean_kl_loss"] = m[4], m[5]
+        ts["vf_explained_var"] = torch.zeros((), device=self.device)
+        self._extra_tower_stats(model, m, train_batch)
+        return total
+
+    compute_loss = loss                                  # BASELINE.json's name for the same hook
+
+    def _extra_tower_stats(self, model, m, train_batch):
+        pass
+
+    def learn_on_batch(self, train_batch):
+        """zero grads -> loss fwd+bwd -> (all-reduce) -> Adam.  Returns the stats dict of this minibatch."""
+        self.model.zero_grad()
+        self.loss(self.model, None, train_batch)
+        scale = 1.0
+        if self.dist is not None and self.dist.is_initialized() and self.dist.get_world_size() > 1:
+            self.dist.all_reduce(self.model.grad)        # one NCCL all-reduce of the flat gradient
+            scale = 1.0 / self.dist.get_world_size()
+        self._optimizer.apply(self.model.grad, grad_scale=scale)
+        self.num_grad_updates += 1
+        return dict(self.model.tower_stats)
+
+    def extra_grad_info(self, train_batch=None):
+        ts = self.model.tower_stats
+        return {"total_loss": float(ts["total_loss"]), "policy_loss": float(ts["mean_policy_loss"]),
+                "vf_loss": float(ts["mean_vf_loss"]), "kl": float(ts["mean_kl_loss"]),
+                "entropy": float(ts["mean_entropy"]), "cur_kl_coeff": self.kl_coeff, "cur_lr": self.config["lr"],
+                "entropy_coeff": self.entropy_coeff, "vf_explained_var": 0.0}
+
+    def update_kl(self, sampled_kl):
+        """rllib KLCoeffMixin.update_kl (ppo_torch_policy, ray 2.2.0)."""
+        if sampled_kl > 2.0 * self.config["kl_target"]:
+            self.kl_coeff *= 1.5
+        elif sampled_kl < 0.5 * self.config["kl_target"]:
+            self.kl_coeff *= 0.5
+        return self.kl_coeff
+
+    # ---- postprocessing (a8, a11) --------------------------------------------------------------------------
+    def _critic_obs(self, ro):
+        return ro[OBS].reshape(-1, ro[OBS].shape[-1])
+
+    def postprocess_rollout(self, ro):
+        """ro: dict of [T, N, ...] rollout columns (obs, actions, rewards, flags, ...).  Adds vf_preds, advantages,
+        value_targets (GAE; IPPO bootstraps like CCPPO here: value of the last observed state)."""
+        T, N = ro["flags"].shape
+        cobs = self._critic_obs(ro)
+        ro[CENTRALIZED_CRITIC_OBS] = cobs.reshape(T, N, -1)
+        ro[VF_PREDS] = self.model.central_value_function(cobs).reshape(T, N)
+        adv, tgt = ops.gae3(ro["flags"], [ro[REWARDS]], [ro[VF_PREDS]], self.config["gamma"], self.config["lambda_"])
+        ro[ADVANTAGES], ro[VALUE_TARGETS] = adv[0], tgt[0]
+        return ro
+
+    def standardize_advantages(self, ro):
+        """Stock PPO training_step: standardize_fields(["advantages"]) over the whole train batch."""
+        st = ops.lcf_mix_stats(ro["flags"].reshape(-1), ro[ADVANTAGES].reshape(-1), None, None, None)
+        st = self._allreduce_stats(st)
+        s = st.tolist()
+        mean, std = ops.stats_to_mean_std(s[0], s[1], s[2])
+        ro[ADVANTAGES] = ops.lcf_mix_apply(ro["flags"].reshape(-1), ro[ADVANTAGES].reshape(-1), None, None, None, mean,
+                                           std, 0.0, 1.0).reshape(ro[ADVANTAGES].shape)
+        return ro
+
+    def _allreduce_stats(self, st):
+        if self.dist is not None and self.dist.is_initialized() and self.dist.get_world_size() > 1:
+            self.dist.all_reduce(st)
+        return st
+
+
+class CCPPOPolicy(IPPOPolicy):
+    algo = "ccppo"
+
+    @classmethod
+    def default_config(cls):
+        return ccppo_config()
+
+    def _build_model(self, seed):
+        c = self.config
+        return CCModel(self.obs_dim, self.act_dim, c["fcnet_hiddens"], c["fuse_mode"], c["counterfactual"],
+                       c["num_neighbours"], device=self.device, seed=seed)
+
+    def _heads(self, train_batch):
+        return [("value", CENTRALIZED_CRITIC_OBS, VF_PREDS, VALUE_TARGETS)]
+
+    def _critic_obs(self, ro):
+        T, N, D = ro[OBS].shape
+        mode = self.config["fuse_mode"]
+        if mode == "none":
+            return ro[OBS].reshape(T * N, D)
+        return ops.cc_obs_fuse(ro[OBS].reshape(T * N, D), ro[ACTIONS].reshape(T * N, -1), ro["flags"].reshape(-1),
+                               ro["mf_mask"].reshape(-1) if mode == "mf" else None,
+                               ro["nei_list"].reshape(T * N, 4) if mode == "concat" else None, ro["slots"], mode,
+                               self.config["counterfactual"])
+
+
+class CoPOPolicy(CCPPOPolicy):
+    algo = "copo"
+
+    def __init__(self, obs_dim, act_dim=2, config=None, device=None, dist=None):
+        super().__init__(obs_dim, act_dim, config, device, dist)
+        self.target_model = self._build_model(self.config.get("seed", 0))        # algo_copo.py:210-221
+        self.update_old_policy()
+        self._lcf_optimizer = _Adam(self.model.lcf_parameters, self.config["lcf_lr"])
+        self._raw_lcf_adv_mean, self._raw_lcf_adv_std = 0.0, 1.0
+
+    @classmethod
+    def default_config(cls):
+        return copo_config()
+
+    def _build_model(self, seed):
+        c = self.config
+        return CoPOModel(self.obs_dim, self.act_dim, c["fcnet_hiddens"], c["fuse_mode"], c["counterfactual"],
+                         c["num_neighbours"], c["initial_lcf_std"], c["use_distributional_lcf"], device=self.device,
+                         seed=seed)
+
+    def _heads(self, train_batch):
+        return [("value", CENTRALIZED_CRITIC_OBS, VF_PREDS, VALUE_TARGETS),
+                ("nei", CENTRALIZED_CRITIC_OBS, NEI_VALUES, NEI_TARGET),
+                ("global", CENTRALIZED_CRITIC_OBS, GLOBAL_VALUES, GLOBAL_TARGET)]
+
+    def _adv_column(self):
+        return "normalized_advantages"
+
+    def _extra_tower_stats(self, model, m, train_batch):
+        ts = model.tower_stats
+        ts["lcf"], ts["lcf_std"] = model.lcf_mean, model.lcf_std
+        ts["mean_nei_vf_loss"], ts["mean_global_vf_loss"] = m[2], m[3]
+        ts["normalized_advantages"] = train_batch["normalized_advantages"].mean()
+
+    def extra_grad_info(self, train_batch=None):
+        ret = super().extra_grad_info(train_batch)
+        ts = self.model.tower_stats
+        ret.update(lcf=float(ts["lcf"]), lcf_std=float(ts["lcf_std"]), mean_nei_vf_loss=float(ts["mean_nei_vf_loss"]),
+                   mean_global_vf_loss=float(ts["mean_global_vf_loss"]),
+                   normalized_advantages=float(ts["normalized_advantages"]))
+        return ret
+
+    # ---- postprocessing (a13, a12, a15) --------------------------------------------------------------------
+    def postprocess_rollout(self, ro):
+        T, N = ro["flags"].shape
+        cobs = self._critic_obs(ro)
+        ro[CENTRALIZED_CRITIC_OBS] = cobs.reshape(T, N, -1)
+        ro[VF_PREDS] = self.model.central_value_function(cobs).reshape(T, N)
+        ro[NEI_VALUES] = self.model.get_nei_value(cobs).reshape(T, N)
+        ro[GLOBAL_VALUES] = self.model.get_global_value(cobs).reshape(T, N)
+        per_scene = ro["slots"] if ro[GLOBAL_REWARDS].shape[1] != N else 0
+        adv, tgt = ops.gae3(ro["flags"], [ro[REWARDS], ro[NEI_REWARDS], ro[GLOBAL_REWARDS]],
+                            [ro[VF_PREDS], ro[NEI_VALUES], ro[GLOBAL_VALUES]], self.config["gamma"],
+                            self.config["lambda_"], global_reward_per_scene=per_scene)
+        ro[ADVANTAGES], ro[NEI_ADVANTAGE], ro[GLOBAL_ADVANTAGES] = adv
+        ro[VALUE_TARGETS], ro[NEI_TARGET], ro[GLOBAL_TARGET] = tgt
+        return ro
+
+    def standardize_advantages(self, ro):
+        """CoPOTrainer.training_step:539-551: LCF mix with the per-row step_lcf, whole-batch standardisation of the
+        mixed and of the global advantage; the raw mean / std are kept for the meta update."""
+        f = ro["flags"].reshape(-1)
+        a, n, l = ro[ADVANTAGES].reshape(-1), ro[NEI_ADVANTAGE].reshape(-1), ro["step_lcf"].reshape(-1)
+        g = ro[GLOBAL_ADVANTAGES].reshape(-1)
+        s = self._allreduce_stats(ops.lcf_mix_stats(f, a, n, l, g)).tolist()
+        mean, std = ops.stats_to_mean_std(s[0], s[1], s[2])
+        gmean, gstd = ops.stats_to_mean_std(s[3], s[4], s[2])
+        self._raw_lcf_adv_mean, self._raw_lcf_adv_std = mean, max(1e-4, std)
+        ro["normalized_advantages"] = ops.lcf_mix_apply(f, a, n, l, g, mean, std, gmean, gstd).reshape(
+            ro[ADVANTAGES].shape)
+        return ro
+
+    # ---- meta-gradient (a18) -------------------------------------------------------------------------------
+    def _policy_grad(self, model, batch, mode, adv):
+        cfg = dict(clip_param=self.config["clip_param"], vf_clip_param=0.0, vf_loss_coeff=0.0, entropy_coeff=0.0,
+                   kl_coeff=0.0)
+        pol = model.nets["policy"]
+        acts = pol.forward_train(batch[OBS])
+        model.grad[model.policy_slice()].zero_()
+        dlogits, _, st = ops.ppo_head(acts[-1], batch[ACTIONS], batch[ACTION_LOGP], None, adv, [], cfg, mode=mode)
+        pol.backward(acts, dlogits)
+        g = model.grad[model.policy_slice()]
+        if self.dist is not None and self.dist.is_initialized() and self.dist.get_world_size() > 1:
+            self.dist.all_reduce(g)                      # reduce the gradient vectors BEFORE the dot (bilinear)
+            g = g / self.dist.get_world_size()
+        return g.clone(), st
+
+    def meta_update(self, train_batch, eps=None):
+        B = train_batch[OBS].shape[0]
+        g_new, st_new = self._policy_grad(self.model, train_batch, 0, train_batch[GLOBAL_ADVANTAGES])
+        g_old, st_old = self._policy_grad(self.target_model, train_batch, 1, None)
+        grad_value = ops.dot(g_new, g_old)[0]
+        if eps is None:
+            eps = torch.randn(B, dtype=torch.float32, device=self.device)
+        mean_t, std_t = self.model.lcf_mean, self.model.lcf_std
+        mean, std = float(mean_t), float(std_t)
+        terms = self._allreduce_stats(ops.lcf_meta_terms(train_batch[ADVANTAGES], train_batch[NEI_ADVANTAGE], eps, mean,
+                                                         std))
+        world = self.dist.get_world_size() if (self.dist is not None and self.dist.is_initialized()) else 1
+        terms = terms / (B * world)
+        coordinated_mean = terms[0]
+        lcf_adv_loss = (coordinated_mean - self._raw_lcf_adv_mean) / self._raw_lcf_adv_std
+        p = self.model.lcf_parameters
+        th = torch.tanh(p[0])
+        dmean = torch.where(th.abs() < 1 - 1e-6, 1 - th * th, torch.zeros_like(th))
+        dstd = torch.where((p[1] > -20) & (p[1] < 2), std_t, torch.zeros_like(std_t))
+        dl = torch.stack([terms[1] * dmean, terms[2] * dstd]) / self._raw_lcf_adv_std
+        self.model.lcf_grad.copy_((grad_value * dl).to(torch.float32))
+        final = grad_value * lcf_adv_loss
+        self._lcf_optimizer.apply(self.model.lcf_grad)
+        return dict(new_policy_ego_loss=float(st_new[0]) / B, old_policy_logp_loss=float(st_old[6]) / B,
+                    lcf_lcf_adv_loss=float(lcf_adv_loss), lcf_final_loss=float(final), grad_value=float(grad_value),
+                    lcf=float(self.model.lcf_mean), lcf_deg=float(self.model.lcf_mean) * 90,
+                    lcf_param=float(self.model.lcf_parameters[0]), coordinated_adv=float(coordinated_mean),
+                    global_adv=float(train_batch[GLOBAL_ADVANTAGES].mean()), lcf_std=float(self.model.lcf_std),
+                    lcf_std_deg=float(self.model.lcf_std) * 90, lcf_std_param=float(self.model.lcf_parameters[1]))
+
+    def update_old_policy(self):
+        self.target_model.flat.copy_(self.model.flat)
+        self.target_model.lcf_parameters.copy_(self.model.lcf_parameters)
+
+    def assign_lcf(self, lcf_parameters, lcf_mean, lcf_std=None, my_name=None):
+        """algo_copo.py:446-471 (same assertions)."""
+        lcf_parameters = torch.as_tensor(lcf_parameters, dtype=torch.float32).to(self.device)
+        assert self.model.lcf_parameters.size() == lcf_parameters.size()
+        self.model.lcf_parameters.copy_(lcf_parameters)
+        assert abs(float(self.model.lcf_mean) - lcf_mean) < 1e-5
+        if lcf_std is not None:
+            assert abs(float(self.model.lcf_std) - lcf_std) < 1e-5

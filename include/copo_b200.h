@@ -92,6 +92,100 @@ int b2c_env_slots_padded(const b2c_env* env);
 int b2c_env_get_state(b2c_env* env, uint32_t* dst_host, void* stream);       /* synchronises the stream */
 int b2c_env_set_state(b2c_env* env, const uint32_t* src_host, void* stream); /* synchronises the stream */
 
+
+/* ---------------------------------------------------------------------------------------------------
+ * Policy / value networks: 3-layer tanh MLPs, weights in torch Linear layout W[out][in] (row-major), fp32.
+ * Replaces SlimFC stacks of CCModel / CoPOModel (algo_ccppo.py:74-219, algo_copo.py:96-182) and their autograd
+ * backward inside {IPPO,CCPPO,CoPO}Policy.loss (algo_ippo.py:79-172, algo_ccppo.py:376-472, algo_copo.py:311-424).
+ * ------------------------------------------------------------------------------------------------- */
+/* y[M][N] = act(x[M][K] W^T + b); act: 0 none, 1 tanh.  ldx / ldy are row strides in floats. */
+int b2c_linear_forward(const float* x, int ldx, const float* W, const float* b, float* y, int ldy, int M, int K, int N,
+                       int act, void* stream);
+/* dx[M][K] = (dy[M][N] W) * (1 - h_prev^2)   (h_prev = tanh output that fed this layer; NULL: no factor) */
+int b2c_linear_backward_input(const float* dy, int ldy, const float* W, const float* h_prev, int ldh, float* dx, int ldx,
+                              int M, int K, int N, void* stream);
+/* dW[N][K] += dy^T x, db[N] += column sums of dy (db may be NULL).  Accumulates: zero dW / db first. */
+int b2c_linear_backward_weight(const float* dy, int ldy, const float* x, int ldx, float* dW, float* db, int M, int K,
+                               int N, void* stream);
+/* narrow output layers (logits: N = 4, value: N = 1), N <= 8 */
+int b2c_head_forward(const float* h, int ldh, const float* W, const float* b, float* y, int ldy, int M, int K, int N,
+                     void* stream);
+/* dz[M][K] = (dy W) * (dtanh ? 1 - h^2 : 1), dW += dy^T h, db += colsum(dy); dz / dW / db may be NULL */
+int b2c_head_backward(const float* dy, int ldy, const float* h, int ldh, const float* W, float* dz, int ldz, float* dW,
+                      float* db, int M, int K, int N, int dtanh, void* stream);
+/* TorchDiagGaussian (rllib): logits = (mean[2] | log_std[2]); action = mean + exp(log_std) * eps, logp(action).
+ * eps_in NULL: standard normals from the counter-based generator keyed by (seed, step, row); eps_out optional. */
+int b2c_gaussian_sample(const float* logits, const float* eps_in, float* actions, float* logp, float* eps_out, int M,
+                        uint32_t seed, uint32_t step, int deterministic, void* stream);
+
+/* Per-row forward + backward of the PPO objective (mode 0) or of mean(logp) (mode 1, the theta_old term of
+ * CoPOPolicy.meta_update, algo_copo.py:265-272).  Gradients are those of
+ *   mean(-surr + vf_loss_coeff * sum_h vf_loss_h - entropy_coeff * H) + kl_coeff * mean(KL(old || new))
+ * with the clipped "old" value loss (algo_copo.py:360-367), including autograd's tie rule for min / max.
+ * stats[8] (+=): sum(-surr), sum vf_loss[0..2], sum entropy, sum KL, sum logp, rows. */
+typedef struct {
+    const float* logits;          /* [rows][4] current policy output */
+    const float* actions;         /* [rows][2] */
+    const float* old_logp;        /* [rows]    SampleBatch.ACTION_LOGP */
+    const float* old_logits;      /* [rows][4] SampleBatch.ACTION_DIST_INPUTS (NULL allowed when kl_coeff == 0) */
+    const float* adv;             /* [rows]    advantages / normalized_advantages / global_advantages */
+    const float* v_cur[3];        /* value heads (native, neighbourhood, global): current prediction */
+    const float* v_old[3];        /*   prediction stored at sampling time (VF_PREDS, NEI_VALUES, GLOBAL_VALUES) */
+    const float* v_tgt[3];        /*   targets (VALUE_TARGETS, NEI_TARGET, GLOBAL_TARGET) */
+    float* dlogits;               /* [rows][4] out */
+    float* dv[3];                 /* [rows]    out */
+    double* stats;                /* [8] accumulated, may be NULL */
+    int32_t rows, n_heads, mode;
+    float clip_param, vf_clip_param, vf_loss_coeff, entropy_coeff, kl_coeff;
+} b2c_ppo_head_args;
+int b2c_ppo_head(const b2c_ppo_head_args* args, void* stream);
+
+/* LCF side of the meta-gradient (algo_copo.py:280-287, compute_coordinated algo_copo.py:155-161), with
+ * phi = (lcf_mean + lcf_std * eps) * pi/2:  out3 += { sum(cos(phi) adv + sin(phi) nei),
+ * sum d, sum d * eps },  d = (-sin(phi) adv + cos(phi) nei) * pi/2. */
+int b2c_lcf_meta_terms(const float* adv, const float* nei_adv, const float* eps, int rows, float lcf_mean, float lcf_std,
+                       double* out3, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Rollout bookkeeping over time-major [T][N] columns (N = scenes x slots); flags are the B2C_FLAG_* bytes the
+ * env wrote for the step in which the row's action was applied.
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct {
+    const uint8_t* flags;         /* [T][N] */
+    const float* rewards[3];      /* native, neighbourhood (info["nei_rewards"]), global (info["global_rewards"]) */
+    const float* values[3];       /* VF_PREDS, NEI_VALUES, GLOBAL_VALUES */
+    float* advantages[3];         /* out */
+    float* targets[3];            /* out */
+    int32_t T, N, heads;          /* heads = 1 (IPPO / CCPPO) or 3 (CoPO) */
+    int32_t global_reward_per_scene;  /* 0: rewards[2] is [T][N]; A > 0: it is [T][N / A], one value per scene */
+    float gamma, lambda_;         /* the global head always uses gamma = 1 (algo_copo.py:498-500) */
+} b2c_gae_args;
+/* compute_advantages x3 (rllib postprocessing; algo_copo.py:189-204, 473-502): per (scene, slot) column, consecutive
+ * valid rows up to a done row are one trajectory; a trajectory cut by the fragment end bootstraps with the value
+ * of its own last row (algo_ccppo.py:362-365).  Scan in float64, results float32. */
+int b2c_gae3(const b2c_gae_args* args, void* stream);
+/* algo_copo.py:539-551.  out5 += { sum x, sum x^2, rows, sum g, sum g^2 } over valid rows, x = cos(lcf pi/2) adv +
+ * sin(lcf pi/2) nei_adv (nei_adv NULL: x = adv, the stock PPO standardisation), g = global_adv (may be NULL). */
+int b2c_lcf_mix_stats(const uint8_t* flags, const float* adv, const float* nei_adv, const float* step_lcf,
+                      const float* global_adv, size_t rows, double* out5, void* stream);
+/* normalized_adv = (x - mean) / max(1e-4, std); global_adv standardised in place with (gmean, gstd) */
+int b2c_lcf_mix_apply(const uint8_t* flags, const float* adv, const float* nei_adv, const float* step_lcf,
+                      float* global_adv, float* normalized_adv, size_t rows, float mean, float std, float gmean,
+                      float gstd, void* stream);
+/* centralized critic observation (algo_ccppo.py:225-355): mode 0 none, 1 mean field (mf_mask), 2 concat (nei_list);
+ * rows = T * N ordered [t][scene][slot]; a neighbour contributes when it has a row at the same t (its VALID flag). */
+int b2c_cc_obs_fuse(const float* obs, const float* actions, const uint8_t* flags, const uint64_t* mf_mask,
+                    const int8_t* nei_list, float* cobs, size_t rows, int slots, int obs_dim, int act_dim, int cobs_dim,
+                    int mode, int counterfactual, void* stream);
+/* dst[r][0..width) = src[idx[r]][0..width): minibatch assembly from a shuffled index list */
+int b2c_gather_rows(const float* src, size_t ld_src, const int64_t* idx, float* dst, size_t ld_dst, size_t rows, int width,
+                    void* stream);
+/* torch.optim.Adam step (no weight decay); grad_scale multiplies the gradient first (1/world_size after an all-reduce) */
+int b2c_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1,
+                  float beta2, float eps, int step, float grad_scale, void* stream);
+/* *out += <a, b> in float64 (algo_copo.py:274-278) */
+int b2c_dot(const float* a, const float* b, size_t n, double* out, void* stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif
