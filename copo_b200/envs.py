@@ -1,0 +1,286 @@
+"""RLlib-style dict API of the reference's environments over the batched CUDA scene step.
+
+The reference wraps MetaDrive's `MultiAgent{Intersection,Roundabout,Tollgate,Bottleneck,ParkingLot}Env`
+(`from metadrive.envs.marl_envs import ...`, torch_copo/train_copo.py:1-2) with `CCEnv` / `LCFEnv`
+(torch_copo/utils/env_wrappers.py:30-430) and `get_rllib_compatible_env` (:559-597).  These classes keep that surface:
+`reset() -> {agent: obs}`, `step({agent: action}) -> (obs, reward, done, info)` dicts with `done["__all__"]`, the
+`info` keys the wrappers and callbacks read, `default_config()`, `set_lcf_dist`, `set_force_lcf`,
+`close_and_reset_num_agents`, `observation_space` / `action_space` dict spaces, `vehicles`.  One instance is one scene
+of a `BatchedDrivingEnv` (S = 1); the arithmetic of a step is the CUDA kernel's, this file only re-keys its outputs by
+agent name ("agent{id}", fresh ids on respawn as in MetaDrive's agent manager).  Training at scale uses the tensor
+API (copo_b200/batched_env.py, copo_b200/trainer.py) instead.
+"""
+import numpy as np
+import torch
+
+from .batched_env import (BatchedDrivingEnv, DEFAULT_NUM_AGENTS, FLAG_ARRIVE, FLAG_CRASH, FLAG_DONE, FLAG_MAXSTEP,
+                          FLAG_OUT, FLAG_SPAWNED, FLAG_VALID)
+
+F_X, F_Y, F_H, F_V, F_STEER, F_THR, F_S, F_DONE_LEN, F_ROUTE, F_SEG, F_EPLEN, F_EPREW, F_LCF, F_STATUS, F_ID, F_YAW = range(16)
+VMAX = 22.22222137451172
+
+
+class Box:
+    """Minimal stand-in for gym.spaces.Box (gym is not a dependency of the hot path)."""
+
+    def __init__(self, low, high, shape, dtype=np.float32):
+        self.low = np.full(shape, low, dtype)
+        self.high = np.full(shape, high, dtype)
+        self.shape, self.dtype = tuple(shape), dtype
+
+    def contains(self, x):
+        x = np.asarray(x)
+        return x.shape == self.shape and bool(np.all(x >= self.low)) and bool(np.all(x <= self.high))
+
+    def sample(self):
+        return np.random.uniform(self.low, self.high).astype(self.dtype)
+
+
+class DictSpace:
+    def __init__(self, spaces):
+        self.spaces = dict(spaces)
+
+    def keys(self):
+        return self.spaces.keys()
+
+    def __getitem__(self, k):
+        return self.spaces[k]
+
+    def __contains__(self, k):
+        return k in self.spaces
+
+    def sample(self):
+        return {k: s.sample() for k, s in self.spaces.items()}
+
+
+class _Vehicle:
+    def __init__(self, x, y, speed):
+        self.position = np.array([x, y], dtype=np.float64)
+        self.speed = speed
+
+
+class MultiAgentDrivingEnv:
+    """One scene with the reference's multi-agent dict API (native MetaDrive-level view, no CoPO wrappers)."""
+    MAP = "intersection"
+    APPEND_LCF = False
+
+    @classmethod
+    def default_config(cls):
+        return dict(num_agents=DEFAULT_NUM_AGENTS[cls.MAP], horizon=1000, delay_done=25, allow_respawn=True,
+                    start_seed=0, neighbours_distance=40, crash_done=True, out_of_road_done=True)
+
+    def __init__(self, config=None):
+        self.config = self.default_config()
+        self.config.update(config or {})
+        self._build()
+
+    def _build(self):
+        c = self.config
+        self._sim = BatchedDrivingEnv(self.MAP, num_scenes=1, num_slots=int(c["num_agents"]),
+                                      num_agents=int(c["num_agents"]), delay_done=int(c["delay_done"]),
+                                      horizon=int(c["horizon"]), neighbours_distance=float(c["neighbours_distance"]),
+                                      allow_respawn=bool(c["allow_respawn"]), auto_reset=False,
+                                      append_lcf=self.APPEND_LCF, lcf_uniform=(c.get("lcf_dist") == "uniform"),
+                                      seed=int(c["start_seed"]), lcf_std=float(c.get("lcf_normal_std", 0.1)),
+                                      force_lcf=float(c.get("force_lcf", -100)))
+        self.A, self.D = self._sim.A, self._sim.D
+        self._slot_of, self.vehicles, self.vehicles_including_just_terminated = {}, {}, {}
+        self._agent_ids = set(["agent{}".format(i) for i in range(100)] + ["{}".format(i) for i in range(10000)])
+        self.episode_step = 0
+
+    # ---- spaces -----------------------------------------------------------------------------------------------
+    @property
+    def observation_space(self):
+        names = list(self.vehicles.keys()) or ["agent%d" % i for i in range(self.A)]
+        low = -1.0 if self.APPEND_LCF else 0.0                     # LCFObs space: Box(-1, 1) (env_wrappers.py:227-246)
+        return DictSpace({k: Box(low, 1.0, (self.D,)) for k in names})
+
+    @property
+    def action_space(self):
+        names = list(self.vehicles.keys()) or ["agent%d" % i for i in range(self.A)]
+        return DictSpace({k: Box(-1.0, 1.0, (2,)) for k in names})
+
+    def action_space_sample(self, agent_ids=None):
+        return {k: v for k, v in self.action_space.sample().items() if agent_ids is None or k in agent_ids}
+
+    # ---- stepping ---------------------------------------------------------------------------------------------
+    def _harvest(self, out, first):
+        st = self._sim.get_state()[0]
+        AP = (self.A + 3) // 4 * 4
+        fld = st[:16 * AP].reshape(16, AP)[:, :self.A]
+        ff = fld.view(np.float32)
+        flags = out["flags"][0].cpu().numpy()
+        obs, rew = out["obs"][0].cpu().numpy(), out["reward"][0].cpu().numpy()
+        ids = out["agent_id"][0].cpu().numpy()
+        nei_mask = out["nei_mask"][0].cpu().numpy().view(np.uint64)
+        o, r, d, info = {}, {}, {}, {}
+        name = lambda i: "agent%d" % int(ids[i])
+        part = [i for i in range(self.A) if flags[i] & (FLAG_VALID | FLAG_SPAWNED)]
+        self.vehicles_including_just_terminated = {name(i): _Vehicle(ff[F_X, i], ff[F_Y, i], ff[F_V, i]) for i in part}
+        self.vehicles = {name(i): self.vehicles_including_just_terminated[name(i)] for i in part
+                         if not (flags[i] & FLAG_DONE)}
+        self._slot_of = {name(i): i for i in part if not (flags[i] & FLAG_DONE)}
+        route_len = self._sim.tables.route_len
+        for i in part:
+            k = name(i)
+            o[k] = obs[i].copy()
+            if first:
+                continue
+            f = int(flags[i])
+            acted = bool(f & FLAG_VALID)
+            r[k] = float(rew[i]) if acted else 0.0
+            d[k] = bool(f & FLAG_DONE)
+            pos = np.array([ff[F_X, i], ff[F_Y, i]], np.float64)
+            others = [j for j in part if j != i and (int(nei_mask[i]) >> j) & 1]
+            dist = {j: float(np.linalg.norm(pos - np.array([ff[F_X, j], ff[F_Y, j]], np.float64))) for j in others}
+            order = sorted(others, key=lambda j: dist[j])
+            total = float(route_len[int(fld[F_ROUTE, i])])
+            cur = float(ff[F_DONE_LEN, i] + ff[F_S, i])
+            info[k] = dict(velocity=float(ff[F_V, i]) * 3.6, steering=float(ff[F_STEER, i]),
+                           acceleration=float(ff[F_THR, i]), step_reward=r[k], cost=1.0 if f & FLAG_CRASH else 0.0,
+                           episode_length=int(fld[F_EPLEN, i]), episode_reward=float(ff[F_EPREW, i]),
+                           arrive_dest=bool(f & FLAG_ARRIVE), crash=bool(f & FLAG_CRASH),
+                           crash_vehicle=bool(f & FLAG_CRASH), out_of_road=bool(f & FLAG_OUT),
+                           max_step=bool(f & FLAG_MAXSTEP), route_completion=cur / total, track_length=total,
+                           current_distance=cur, step_energy=0.0, episode_energy=0.0,
+                           raw_action=(float(ff[F_STEER, i]), float(ff[F_THR, i])),
+                           all_agents=[name(j) for j in part], neighbours=[name(j) for j in order],
+                           neighbours_distance=[dist[j] for j in order])
+        if not first:
+            d["__all__"] = bool(out["scene_done"][0]) or (self.episode_step >= self.config["horizon"])
+        self._last_out = out
+        self._slot_now = {name(i): i for i in part}
+        return o, r, d, info
+
+    def reset(self, force_seed=None):
+        self.episode_step = 0
+        out = self._sim.reset(new_episode=True)
+        return self._harvest(out, first=True)[0]
+
+    def step(self, actions):
+        act = torch.zeros((1, self.A, 2), dtype=torch.float32)
+        for k, a in actions.items():
+            if k in self._slot_of:
+                act[0, self._slot_of[k]] = torch.as_tensor(np.asarray(a, np.float32)[:2])
+        self.episode_step += 1
+        out = self._sim.step(act.to(self._sim.device))
+        return self._harvest(out, first=False)
+
+    def close(self):
+        self._sim.close()
+
+    def close_and_reset_num_agents(self, num_agents):
+        """ChangeNEnv (env_wrappers.py:444-460): population change = slot masking, no re-allocation."""
+        self.config["num_agents"] = num_agents
+        self._sim.set_num_agents(num_agents)
+
+
+def _named(map_name, cls_name):
+    return type(cls_name, (MultiAgentDrivingEnv,), {"MAP": map_name})
+
+
+MultiAgentIntersectionEnv = _named("intersection", "MultiAgentIntersectionEnv")
+MultiAgentRoundaboutEnv = _named("roundabout", "MultiAgentRoundaboutEnv")
+MultiAgentTollgateEnv = _named("tollgate", "MultiAgentTollgateEnv")
+MultiAgentBottleneckEnv = _named("bottleneck", "MultiAgentBottleneckEnv")
+MultiAgentParkingLotEnv = _named("parking_lot", "MultiAgentParkingLotEnv")
+
+
+def get_ccenv(env_class):
+    """CCEnv (env_wrappers.py:30-158, 433-441): `all_agents`, `neighbours`, `neighbours_distance` in every info."""
+    name = env_class.__name__
+    assert name.startswith("MultiAgent")
+
+    class TMP(env_class):
+        @classmethod
+        def default_config(cls):
+            c = super().default_config()
+            c["neighbours_distance"] = 40
+            return c
+
+    TMP.__name__ = TMP.__qualname__ = "CC" + name
+    return TMP
+
+
+def get_lcf_env(env_class):
+    """LCFEnv (env_wrappers.py:161-430, 463-471): LCF appended to the obs, nei / global / coordinated rewards."""
+    name = env_class.__name__
+    base = get_ccenv(env_class)
+
+    class TMP(base):
+        APPEND_LCF = True
+
+        @classmethod
+        def default_config(cls):
+            c = super().default_config()
+            c.update(neighbours_distance=40, lcf_mode="angle", lcf_dist="normal", lcf_normal_std=0.1,
+                     return_native_reward=True, force_lcf=-100, enable_copo=True)
+            return c
+
+        def __init__(self, config=None):
+            super().__init__(config)
+            assert self.config["lcf_mode"] in ["linear", "angle"]
+            assert self.config["lcf_dist"] in ["uniform", "normal"]
+            assert self.config["lcf_normal_std"] > 0.0
+            self.force_lcf = self.config["force_lcf"]
+            self.current_lcf_mean, self.current_lcf_std = 0.0, self.config["lcf_normal_std"]
+
+        @property
+        def enable_copo(self):
+            return self.config["enable_copo"]
+
+        def step(self, actions):
+            o, r, d, i = super().step(actions)
+            assert set(i.keys()) == set(o.keys())
+            out = self._last_out
+            nei_r, glob = out["nei_reward"][0].cpu().numpy(), float(out["global_reward"][0])
+            lcf = out["lcf"][0].cpu().numpy()
+            new_r = {}
+            for k, inf in i.items():
+                s = self._slot_now[k]
+                inf["nei_rewards"] = float(nei_r[s])
+                inf["global_rewards"] = glob
+                agent_lcf = float(lcf[s])
+                inf["lcf"], inf["lcf_deg"] = agent_lcf, agent_lcf * 90
+                if self.config["lcf_mode"] == "linear":
+                    cr = agent_lcf * r[k] + (1 - agent_lcf) * inf["nei_rewards"]
+                else:
+                    rad = agent_lcf * np.pi / 2
+                    cr = np.cos(rad) * r[k] + np.sin(rad) * inf["nei_rewards"]
+                inf["coordinated_rewards"], inf["native_rewards"] = cr, r[k]
+                new_r[k] = r[k] if self.config["return_native_reward"] else cr
+            return o, new_r, d, i
+
+        def set_lcf_dist(self, mean, std):
+            assert self.enable_copo
+            assert self.config["lcf_dist"] == "normal"
+            assert std > 0.0
+            assert -1.0 <= mean <= 1.0
+            self.current_lcf_mean, self.current_lcf_std = mean, std
+            self._sim.set_lcf_dist(mean, std)
+
+        def set_force_lcf(self, v):
+            assert self.enable_copo
+            self.force_lcf = v
+            self._sim.set_force_lcf(v)
+
+    TMP.__name__ = TMP.__qualname__ = "LCF" + name
+    return TMP
+
+
+def get_change_n_env(env_class):
+    return env_class
+
+
+_REGISTRY = {}
+
+
+def get_rllib_compatible_env(env_class, return_class=False):
+    """env_wrappers.py:559-597: returns the registered env name (or the class)."""
+    env_name = env_class.__name__
+    _REGISTRY[env_name] = env_class
+    return env_class if return_class else env_name
+
+
+def make_env(name, config=None):
+    return _REGISTRY[name](config)

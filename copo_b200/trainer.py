@@ -1,0 +1,251 @@
+"""IPPO / CCPPO / CoPO trainers over device-resident rollouts.
+
+Mirrors torch_copo/algo_{ippo,ccppo,copo}.py `*Trainer`: `get_default_config()`, `get_default_policy_class()`,
+`training_step()` (CoPO's: algo_copo.py:516-661) and `train()`.  One process drives one GPU; every rank holds
+`num_scenes` scenes (scene sharding, no data-path collective during the rollout).  Per iteration:
+
+  sample      T env steps: policy forward + Gaussian sample + fused scene step, the env writes straight into the
+              [T, N] rollout columns                                            (synchronous_parallel_sample, :518-525)
+  postprocess critic obs, value heads, GAE x3                                   (postprocess_trajectory, :473-502)
+  mix         LCF-mixed advantage, whole-batch standardisation (all-reduce of 5 sums)                 (:539-551)
+  sgd         num_sgd_iter epochs of shuffled minibatches, one gradient all-reduce + Adam each (train_one_step, :555)
+  meta        lcf_num_iters epochs of meta_update minibatches                                         (:582-589)
+  hand-over   theta_old <- theta, env.set_lcf_dist(mean, std), KL coefficient update                  (:596-632)
+"""
+import math
+import time
+
+import torch
+
+from . import ops
+from . import policy as P
+from .batched_env import (BatchedDrivingEnv, FLAG_ARRIVE, FLAG_CRASH, FLAG_DONE, FLAG_MAXSTEP, FLAG_OUT, FLAG_VALID,
+                          MAP_OF_ENV)
+
+SCALAR_COLUMNS = (P.ACTION_LOGP, P.ADVANTAGES, P.VALUE_TARGETS, P.VF_PREDS, "normalized_advantages", P.NEI_VALUES,
+                  P.NEI_TARGET, P.NEI_ADVANTAGE, P.GLOBAL_VALUES, P.GLOBAL_TARGET, P.GLOBAL_ADVANTAGES)
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist if (dist.is_available() and dist.is_initialized()) else None
+
+
+class IPPOTrainer:
+    policy_cls = P.IPPOPolicy
+
+    @classmethod
+    def get_default_config(cls):
+        c = cls.policy_cls.default_config()
+        c.update_from_dict(dict(env="MultiAgentIntersectionEnv", num_scenes=64, sgd_minibatch_size=512,
+                                rollout_fragment_length=200))
+        return c
+
+    def get_default_policy_class(self, config=None):
+        return self.policy_cls
+
+    def __init__(self, config=None, env=None, device=None):
+        cfg = self.get_default_config()
+        if config:
+            cfg.update_from_dict(config)
+        self.config = cfg
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        dist = _dist()
+        self.rank = dist.get_rank() if dist else 0
+        self.world = dist.get_world_size() if dist else 1
+        ec = dict(cfg.get("env_config", {}))
+        if env is None:
+            name = cfg["env"]
+            map_name = MAP_OF_ENV.get(name, name)
+            S = int(cfg["num_scenes"])
+            append_lcf = self.policy_cls.algo == "copo"
+            env = BatchedDrivingEnv(map_name, num_scenes=S, num_agents=ec.get("num_agents"),
+                                    num_slots=ec.get("num_agents"), seed=int(ec.get("start_seed", cfg.get("seed", 0))),
+                                    scene_offset=self.rank * S, append_lcf=append_lcf,
+                                    neighbours_distance=ec.get("neighbours_distance", 40.0),
+                                    mf_nei_distance=cfg.get("mf_nei_distance", 10.0),
+                                    lcf_std=ec.get("lcf_normal_std", 0.1), horizon=ec.get("horizon", 1000),
+                                    delay_done=ec.get("delay_done", 25), device=self.device)
+        self.env = env
+        self.policy = self.policy_cls(env.D, 2, cfg, device=self.device, dist=dist)
+        self._counters = {"num_env_steps_sampled": 0, "num_agent_steps_sampled": 0}
+        self._timers = {}
+        self._iteration = 0
+        self._step_counter = 0
+        self._alloc_rollout()
+        self.env.reset()
+        self.ro[P.OBS][0].copy_(self.env.out["obs"].reshape(self.N, -1))
+
+    def get_policy(self, policy_id="default"):
+        return self.policy
+
+    # ---- rollout storage: time-major columns the env and the policy write into directly -----------------------
+    def _alloc_rollout(self):
+        T = int(self.config["rollout_fragment_length"])
+        S, A, D = self.env.S, self.env.A, self.env.D
+        N, dev = S * A, self.device
+        self.T, self.N = T, N
+        z = lambda shape, dt=torch.float32: torch.zeros(shape, dtype=dt, device=dev)
+        self.ro = {P.OBS: z((T + 1, N, D)), P.ACTIONS: z((T, N, 2)), P.ACTION_LOGP: z((T, N)),
+                   P.ACTION_DIST_INPUTS: z((T, N, 4)), P.REWARDS: z((T, N)), "flags": z((T, N), torch.uint8),
+                   P.NEI_REWARDS: z((T, N)), P.GLOBAL_REWARDS: z((T, S)), "step_lcf": z((T, N)),
+                   "mf_mask": z((T, N), torch.int64), "nei_mask": z((T, N), torch.int64),
+                   "nei_list": z((T, N, 4), torch.int8), "agent_id": z((T, N), torch.int32),
+                   "scene_done": z((T, S), torch.uint8)}
+        self._step_out = []
+        for t in range(T):
+            r = self.ro
+            self._step_out.append(dict(
+                obs=r[P.OBS][t + 1].view(S, A, D), reward=r[P.REWARDS][t].view(S, A), flags=r["flags"][t].view(S, A),
+                nei_mask=r["nei_mask"][t].view(S, A), mf_mask=r["mf_mask"][t].view(S, A),
+                nei_reward=r[P.NEI_REWARDS][t].view(S, A), global_reward=r[P.GLOBAL_REWARDS][t],
+                nei_list=r["nei_list"][t].view(S, A, 4), agent_id=r["agent_id"][t].view(S, A),
+                lcf=r["step_lcf"][t].view(S, A), scene_done=r["scene_done"][t]))
+
+    def sample(self):
+        """One rollout fragment of T env steps for every scene of this rank."""
+        ro, pol = self.ro, self.policy
+        if self._iteration > 0:
+            ro[P.OBS][0].copy_(ro[P.OBS][self.T])        # the fragment continues where the last one stopped
+        for t in range(self.T):
+            logits = pol.model.forward(ro[P.OBS][t])
+            ro[P.ACTION_DIST_INPUTS][t].copy_(logits)
+            actions, logp = ops.gaussian_sample(logits, seed=self.config.get("seed", 0) + self.rank * 7919,
+                                                step=self._step_counter)
+            ro[P.ACTIONS][t].copy_(actions)
+            ro[P.ACTION_LOGP][t].copy_(logp)
+            self.env.step(ro[P.ACTIONS][t].view(self.env.S, self.env.A, 2), out=self._step_out[t])
+            self._step_counter += 1
+        view = {k: (v[:self.T] if k == P.OBS else v) for k, v in ro.items()}
+        view["slots"] = self.env.A
+        return view
+
+    # ---- minibatches -----------------------------------------------------------------------------------------
+    def _flatten(self, ro):
+        R = self.T * self.N
+        cols = [c for c in SCALAR_COLUMNS if c in ro]
+        scal = torch.stack([ro[c].reshape(R) for c in cols], dim=1).contiguous()
+        wide = {P.OBS: ro[P.OBS].reshape(R, -1), P.ACTIONS: ro[P.ACTIONS].reshape(R, 2),
+                P.ACTION_DIST_INPUTS: ro[P.ACTION_DIST_INPUTS].reshape(R, 4)}
+        cobs = ro[P.CENTRALIZED_CRITIC_OBS].reshape(R, -1)
+        if cobs.data_ptr() != wide[P.OBS].data_ptr():
+            wide[P.CENTRALIZED_CRITIC_OBS] = cobs
+        valid = torch.nonzero(ro["flags"].reshape(R) & FLAG_VALID).reshape(-1)
+        return cols, scal, wide, valid
+
+    def _num_minibatches(self, n_valid, mb):
+        k = max(1, math.ceil(n_valid / mb))
+        if self.world > 1:
+            t = torch.tensor([k], device=self.device)
+            _dist().all_reduce(t, op=_dist().ReduceOp.MAX)
+            k = int(t)
+        return k
+
+    def _minibatches(self, cols, scal, wide, valid, mb):
+        """Shuffled minibatches over the valid rows (rllib.utils.sgd.minibatches)."""
+        k = self._num_minibatches(valid.numel(), mb)
+        perm = valid[torch.randperm(valid.numel(), device=self.device)]
+        size = math.ceil(valid.numel() / k)
+        for j in range(k):
+            idx = perm[j * size:(j + 1) * size].contiguous()
+            if idx.numel() == 0:
+                idx = perm[:1].contiguous()
+            batch = {c: ops.gather_rows(w, idx) for c, w in wide.items()}
+            if P.CENTRALIZED_CRITIC_OBS not in batch:
+                batch[P.CENTRALIZED_CRITIC_OBS] = batch[P.OBS]
+            s = ops.gather_rows(scal, idx)
+            for n, c in enumerate(cols):
+                batch[c] = s[:, n].contiguous()
+            yield batch
+
+    # ---- one training iteration ------------------------------------------------------------------------------
+    def _learn(self, ro):
+        cols, scal, wide, valid = self._flatten(ro)
+        stats, n = {}, 0
+        for _ in range(int(self.config["num_sgd_iter"])):
+            for batch in self._minibatches(cols, scal, wide, valid, int(self.config["sgd_minibatch_size"])):
+                self.policy.learn_on_batch(batch)
+                for k, v in self.policy.extra_grad_info().items():
+                    stats[k] = stats.get(k, 0.0) + v
+                n += 1
+        return {k: v / max(n, 1) for k, v in stats.items()}, (cols, scal, wide, valid)
+
+    def _episode_metrics(self, ro):
+        f = ro["flags"]
+        done = (f & FLAG_DONE) > 0
+        n = max(int(done.sum()), 1)
+        rate = lambda bit: float(((f & bit) > 0)[done].sum()) / n
+        valid = (f & FLAG_VALID) > 0
+        return dict(success_rate=rate(FLAG_ARRIVE), crash_rate=rate(FLAG_CRASH), out_of_road_rate=rate(FLAG_OUT),
+                    max_step_rate=rate(FLAG_MAXSTEP), episodes=int(done.sum()),
+                    step_reward_mean=float(ro[P.REWARDS][valid].mean()) if bool(valid.any()) else 0.0,
+                    agent_steps=int(valid.sum()))
+
+    def training_step(self):
+        t0 = time.perf_counter()
+        ro = self.sample()
+        torch.cuda.synchronize(self.device)
+        t1 = time.perf_counter()
+        ro = self.policy.postprocess_rollout(ro)
+        ro = self.policy.standardize_advantages(ro)
+        learner_stats, flat = self._learn(ro)
+        torch.cuda.synchronize(self.device)
+        t2 = time.perf_counter()
+        results = {"default": {"learner_stats": learner_stats, "custom_metrics": {}}}
+        self._after_sgd(ro, flat, results)
+        self.policy.update_kl(learner_stats["kl"])
+        metrics = self._episode_metrics(ro)
+        self._counters["num_env_steps_sampled"] += self.T * self.env.S
+        self._counters["num_agent_steps_sampled"] += metrics["agent_steps"]
+        self._timers = {"sample_time_ms": (t1 - t0) * 1e3, "learn_time_ms": (t2 - t1) * 1e3,
+                        "sample_throughput": metrics["agent_steps"] / max(t1 - t0, 1e-9)}
+        results["default"]["custom_metrics"].update(metrics)
+        self._iteration += 1
+        return results
+
+    def _after_sgd(self, ro, flat, results):
+        pass
+
+    def train(self):
+        t0 = time.perf_counter()
+        res = self.training_step()
+        info = res["default"]
+        return {"training_iteration": self._iteration, "time_this_iter_s": time.perf_counter() - t0,
+                "timesteps_total": self._counters["num_env_steps_sampled"] * self.world,
+                "agent_timesteps_total": self._counters["num_agent_steps_sampled"] * self.world,
+                "info": {"learner": {"default": info}}, "timers": dict(self._timers),
+                "custom_metrics": info["custom_metrics"],
+                "success": info["custom_metrics"].get("success_rate", 0.0)}
+
+    def stop(self):
+        self.env.close()
+
+
+class CCPPOTrainer(IPPOTrainer):
+    policy_cls = P.CCPPOPolicy
+
+
+class CoPOTrainer(CCPPOTrainer):
+    policy_cls = P.CoPOPolicy
+
+    def _after_sgd(self, ro, flat, results):
+        """LCF meta update + hand-over (algo_copo.py:579-624)."""
+        cols, scal, wide, valid = flat
+        pol = self.policy
+        mb = int(self.config["lcf_sgd_minibatch_size"] or self.config["sgd_minibatch_size"])
+        rec, ret = {}, {}
+        for _ in range(int(self.config["lcf_num_iters"])):
+            for batch in self._minibatches(cols, scal, wide, valid, mb):
+                ret = pol.meta_update(batch)
+                for k, v in ret.items():
+                    rec.setdefault(k, []).append(v)
+        avg = {k: sum(v) / len(v) for k, v in rec.items() if k not in ("lcf", "lcf_std")}
+        last = {k: v for k, v in ret.items() if k in ("lcf", "lcf_std")}
+        lcf_mean, lcf_std = float(pol.model.lcf_mean), float(pol.model.lcf_std)
+        pol.assign_lcf(pol.model.lcf_parameters.clone(), lcf_mean, lcf_std)
+        pol.update_old_policy()
+        self.env.set_lcf_dist(mean=lcf_mean, std=lcf_std)
+        fetches = {"raw_lcf_adv_mean_value": pol._raw_lcf_adv_mean, "raw_lcf_adv_std_value": pol._raw_lcf_adv_std}
+        fetches.update(avg)
+        fetches.update(last)
+        results["default"]["custom_metrics"]["meta_update"] = fetches

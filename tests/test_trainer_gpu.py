@@ -1,0 +1,94 @@
+"""End-to-end checks of the host API on the GPU: the dict-API environments (reference's env interface) against the
+oracle, and full training iterations of the three trainers on a small scene batch."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_dict_env_follows_reference_interface():
+    from copo_b200 import envs
+    from copo_b200.maps import build_map
+    from oracle import sim as osim
+    cls = envs.get_lcf_env(envs.MultiAgentIntersectionEnv)
+    assert cls.__name__ == "LCFMultiAgentIntersectionEnv" and cls.default_config()["neighbours_distance"] == 40
+    name = envs.get_rllib_compatible_env(cls)
+    env = envs.make_env(name, {"num_agents": 12, "start_seed": 5})
+    A = 12
+    cfg = osim.SimConfig(seed=5, auto_reset=False)
+    cfg.num_agents = A
+    ref = osim.OracleSim(build_map("intersection"), 1, A, cfg)
+    ref.episode[:] = 0
+    o = env.reset()
+    r0 = ref.reset(new_episode=True)
+    assert len(o) == A and all(v.shape == (92,) and v.dtype == np.float32 for v in o.values())
+    assert set(o.keys()) == set(env.observation_space.keys()) == set("agent%d" % i for i in range(A))
+    rng = np.random.default_rng(0)
+    seen_done = 0
+    for t in range(150):
+        acts = {k: np.array([rng.uniform(-0.3, 0.3), rng.uniform(0, 1)], np.float32) for k in env.vehicles}
+        arr = np.zeros((1, A, 2), np.float32)
+        for k, a in acts.items():
+            arr[0, env._slot_of[k]] = a
+        o, r, d, i = env.step(acts)
+        w = ref.step(arr)
+        assert set(o.keys()) == set(i.keys()) == set(r.keys()) and "__all__" in d
+        for k in o:
+            s = env._slot_now[k]
+            assert k == "agent%d" % w["agent_id"][0, s]
+            assert np.array_equal(o[k], w["obs"][0, s])
+            inf = i[k]
+            if w["flags"][0, s] & osim.F_VALID:
+                assert r[k] == float(w["reward"][0, s]) and d[k] == bool(w["flags"][0, s] & osim.F_DONE)
+            assert inf["nei_rewards"] == float(w["nei_reward"][0, s])
+            assert inf["global_rewards"] == float(w["global_reward"][0])
+            assert inf["lcf"] == float(w["lcf"][0, s]) and 0.0 <= o[k][-1] <= 1.0
+            mask = 0
+            for n in inf["neighbours"]:
+                mask |= 1 << env._slot_now[n]
+            assert mask == int(w["nei_mask"][0, s])
+            assert inf["neighbours_distance"] == sorted(inf["neighbours_distance"])
+            want = math.cos(inf["lcf"] * math.pi / 2) * r[k] + math.sin(inf["lcf"] * math.pi / 2) * inf["nei_rewards"]
+            assert abs(inf["coordinated_rewards"] - want) < 1e-9
+            for key in ("velocity", "steering", "acceleration", "step_reward", "cost", "episode_length",
+                        "episode_reward", "arrive_dest", "crash", "out_of_road", "route_completion", "all_agents"):
+                assert key in inf
+            seen_done += int(d[k])
+    assert seen_done > 0
+    env.set_lcf_dist(0.3, 0.05)
+    with pytest.raises(AssertionError):
+        env.set_lcf_dist(0.3, 0.0)
+    env.close()
+
+
+@pytest.mark.parametrize("algo", ["copo", "ccppo", "ippo"])
+def test_training_iterations(algo):
+    from copo_b200 import trainer as T
+    cls = {"copo": T.CoPOTrainer, "ccppo": T.CCPPOTrainer, "ippo": T.IPPOTrainer}[algo]
+    tr = cls(dict(env="MultiAgentRoundaboutEnv" if algo == "ccppo" else "MultiAgentIntersectionEnv", num_scenes=16,
+                  rollout_fragment_length=24, sgd_minibatch_size=2048, num_sgd_iter=2, lcf_num_iters=2,
+                  env_config={"num_agents": 20}, seed=1))
+    assert tr.policy.model.obs_dim == (92 if algo == "copo" else 91)
+    if algo == "ccppo":
+        assert tr.policy.model.cobs_dim == 184
+    p0 = tr.policy.model.flat.clone()
+    for it in range(2):
+        res = tr.train()
+        st = res["info"]["learner"]["default"]["learner_stats"]
+        for k in ("total_loss", "policy_loss", "vf_loss", "kl", "entropy", "cur_kl_coeff"):
+            assert math.isfinite(st[k]), (k, st[k])
+        cm = res["custom_metrics"]
+        assert 0 <= cm["success_rate"] <= 1 and cm["agent_steps"] > 0
+    assert res["training_iteration"] == 2 and res["timesteps_total"] == 2 * 24 * 16
+    assert not torch.equal(p0, tr.policy.model.flat) and torch.isfinite(tr.policy.model.flat).all()
+    if algo == "copo":
+        mu = res["custom_metrics"]["meta_update"]
+        for k in ("grad_value", "lcf", "lcf_std", "lcf_final_loss", "raw_lcf_adv_mean_value"):
+            assert math.isfinite(mu[k])
+        assert torch.equal(tr.policy.target_model.flat, tr.policy.model.flat)          # theta_old handed over
+        assert abs(tr.env.lcf_mean - float(tr.policy.model.lcf_mean)) < 1e-6           # envs draw from the new LCF
+        assert float(tr.policy.model.lcf_parameters[0]) != 0.0
+    tr.stop()
