@@ -1,0 +1,391 @@
+// mlp_tc.cu - tcgen05 tensor-core path for the 256-wide layers of the policy / value MLPs (K5 of SURVEY.md 2.2).
+//
+//   y[M x 256] = epilogue( A[M x K] * W[256 x K]^T )            M = scenes x slots x steps (10^5 .. 10^7 rows)
+//
+// fp32 accuracy on bf16 tensor cores: every fp32 operand x is split into hi = bf16(x), lo = bf16(x - hi) and the
+// product is taken as hi*hi + lo*hi + hi*lo with fp32 accumulation in TMEM ("bf16x3", ~2^-16 relative per product)
+// - value predictions feed GAE, which must match the fp32 reference to 1e-4 (SURVEY.md 7 "hard parts").  The three
+// passes are one GEMM over a 3x longer reduction dimension:
+//   A' = [A_hi | A_lo | A_hi]   (stored once as [hi | lo]; the TMA producer maps reduction blocks onto it)
+//   W' = [W_hi | W_hi | W_lo]   (prepared per weight update; weights are tiny)
+//
+// Kernel: persistent, one CTA per SM, 128 x 256 output tile, 64-wide reduction blocks.
+//   warp 0     TMA producer: cp.async.bulk.tensor (SWIZZLE_128B) of the A and W' blocks into a 4-stage ring
+//   warp 1     MMA issuer: one thread issues tcgen05.mma.cta_group::1.kind::f16 (M128 N256 K16), accumulators in
+//              TMEM (2 x 256 columns, double buffered so the epilogue of tile i overlaps the MMAs of tile i+1)
+//   warp 2     TMEM allocation
+//   warps 4-7  epilogue: tcgen05.ld 32 lanes x 32 columns, bias + tanh (or * (1 - h^2) for the input gradient),
+//              writes fp32 and / or the [hi | lo] bf16 operand of the next layer
+//
+// Replaces: SlimFC hidden layers of CCModel / CoPOModel forward (torch_copo/algo_ccppo.py:108-170, 201-219;
+// algo_copo.py:138-153) and their input-gradient GEMM in backward.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "b2c_internal.h"
+
+namespace b2c {
+namespace tc {
+
+constexpr int BLOCK_M = 128, BLOCK_N = 256, BLOCK_K = 64, UMMA_K = 16, STAGES = 4;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;      // 16 KB
+constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;      // 32 KB
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int TMEM_COLS = 512;
+constexpr int NUM_THREADS = 256;
+// instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D = f32, A = B = bf16, both K-major,
+// N = 256 (bits 17..22 = N >> 3), M = 128 (bits 24..28 = M >> 4)
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((BLOCK_N >> 3) << 17) | ((BLOCK_M >> 4) << 24);
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+// SWIZZLE_128B, K-major shared-memory matrix descriptor (cute SmemDescriptor): start >> 4, LBO = 1 (unused for
+// swizzled K-major), SBO = 1024 B (8 rows x 128 B) >> 4, version 1 (Blackwell), layout type 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ float fast_tanh(float x) {
+    // 1 - 2 / (exp(2x) + 1); |error| ~ 2e-7 absolute, saturates cleanly for large |x|
+    float e = __expf(2.0f * x);
+    return 1.0f - __fdividef(2.0f, e + 1.0f);
+}
+__device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
+    return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+struct LinearArgs {
+    const float* bias;        // [256] or null
+    const float* dtanh_src;   // [M][ld_src] or null: multiply the result by (1 - h^2)
+    float* out_f32;           // [M][ld_out] or null
+    uint16_t* out_split;      // [M][512] bf16 (hi | lo) or null
+    int M, kp_blocks;         // kp_blocks = Kp / 64; the reduction loop runs 3 * kp_blocks blocks
+    int ld_out, ld_src, act;  // act: 0 none, 1 tanh
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                 const __grid_constant__ LinearArgs args) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tmem_full = empty + STAGES;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_tiles = (args.M + BLOCK_M - 1) / BLOCK_M;
+    const int num_kb = 3 * args.kp_blocks;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1u);
+                    uint8_t* sa = smem + stage * STAGE_BYTES;
+                    uint8_t* sb = sa + A_STAGE_BYTES;
+                    mbar_expect_tx(&full[stage], STAGE_BYTES);
+                    // reduction block kb of A' = [hi | lo | hi] lives at column block (segment 1 ? lo : hi)
+                    int seg = kb / args.kp_blocks, blk = kb - seg * args.kp_blocks;
+                    int a_col = ((seg == 1) ? args.kp_blocks : 0) * BLOCK_K + blk * BLOCK_K;
+                    tma_load_2d(sa, &map_a, a_col, tile * BLOCK_M, &full[stage]);
+                    tma_load_2d(sb, &map_w, kb * BLOCK_K, 0, &full[stage]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                    const uint32_t sb = sa + A_STAGE_BYTES;
+                    const uint64_t da = make_desc(sa), db = make_desc(sb);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        // advance the start address by 32 B (16 bf16) inside the 128 B swizzle row
+                        umma_bf16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC, (kb | k) ? 1u : 0u);
+                    }
+                    umma_commit(&empty[stage]);                  // frees the smem slot when these MMAs retire
+                    if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: warp w reads TMEM lanes 32*(w%4) .. +31, one output row per thread =====
+        const int q = warp & 3;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const int row = tile * BLOCK_M + q * 32 + lane;
+            const bool live = row < args.M;
+            const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld32(taddr0 + (uint32_t)(c * 32), r);
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float x = __uint_as_float(r[j]);
+                    if (args.bias) x += __ldg(args.bias + c * 32 + j);
+                    if (args.act == 1) x = fast_tanh(x);
+                    v[j] = x;
+                }
+                if (live) {
+                    if (args.dtanh_src) {
+                        const float4* hs = reinterpret_cast<const float4*>(args.dtanh_src + (size_t)row * args.ld_src + c * 32);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float4 h = hs[j];
+                            v[4 * j] *= (1.0f - h.x * h.x); v[4 * j + 1] *= (1.0f - h.y * h.y);
+                            v[4 * j + 2] *= (1.0f - h.z * h.z); v[4 * j + 3] *= (1.0f - h.w * h.w);
+                        }
+                    }
+                    if (args.out_f32) {
+                        float4* o = reinterpret_cast<float4*>(args.out_f32 + (size_t)row * args.ld_out + c * 32);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    }
+                    if (args.out_split) {
+                        uint32_t hi[16], lo[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * j]), h1 = __float2bfloat16_rn(v[2 * j + 1]);
+                            __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * j] - __bfloat162float(h0));
+                            __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * j + 1] - __bfloat162float(h1));
+                            hi[j] = pack_bf16(h0, h1); lo[j] = pack_bf16(l0, l1);
+                        }
+                        uint4* oh = reinterpret_cast<uint4*>(args.out_split + (size_t)row * 512 + c * 32);
+                        uint4* ol = reinterpret_cast<uint4*>(args.out_split + (size_t)row * 512 + 256 + c * 32);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            oh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                            ol[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+// x fp32 [M][K] -> [M][2*Kp] bf16: hi in columns [0, Kp), lo in [Kp, 2Kp), zero padding beyond K
+__global__ void split_rows_kernel(const float* __restrict__ x, int ldx, uint16_t* __restrict__ out, int M, int K, int Kp) {
+    const size_t total = (size_t)M * Kp;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        size_t m = i / Kp; int k = (int)(i - m * Kp);
+        float v = (k < K) ? x[m * ldx + k] : 0.0f;
+        __nv_bfloat16 h = __float2bfloat16_rn(v);
+        __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+        out[m * 2 * Kp + k] = __bfloat16_as_ushort(h);
+        out[m * 2 * Kp + Kp + k] = __bfloat16_as_ushort(l);
+    }
+}
+// W fp32 [N][K] (or its transpose) -> [rows][3*Kp] bf16: [hi | hi | lo]
+__global__ void prep_weight_kernel(const float* __restrict__ W, uint16_t* __restrict__ out, int N, int K, int Kp, int rows,
+                                   int transpose) {
+    // transpose = 0: out row n, reduction index k reads W[n][k]   (forward, rows = N, reduction K)
+    // transpose = 1: out row k, reduction index n reads W[n][k]   (input gradient, rows = K, reduction N)
+    const int red = transpose ? N : K;
+    const size_t total = (size_t)rows * Kp;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        int r = (int)(i / Kp), c = (int)(i - (size_t)r * Kp);
+        float v = 0.0f;
+        if (c < red) v = transpose ? W[(size_t)c * K + r] : W[(size_t)r * K + c];
+        __nv_bfloat16 h = __float2bfloat16_rn(v);
+        __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+        uint16_t* o = out + (size_t)r * 3 * Kp;
+        o[c] = __bfloat16_as_ushort(h);
+        o[Kp + c] = __bfloat16_as_ushort(h);
+        o[2 * Kp + c] = __bfloat16_as_ushort(l);
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// bf16 row-major [rows][cols] matrix, box = 64 columns x box_rows rows, 128-byte swizzle
+static int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return b2c_set_error(B2C_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {cols * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return b2c_set_error(B2C_ERR_CUDA, "cuTensorMapEncodeTiled failed with code %d", (int)r);
+    return B2C_OK;
+}
+
+}  // namespace tc
+}  // namespace b2c
+
+using namespace b2c::tc;
+
+extern "C" {
+
+int b2c_tc_padded_k(int K) { return (K + BLOCK_K - 1) / BLOCK_K * BLOCK_K; }
+
+int b2c_tc_split_rows(const float* x, int ldx, uint16_t* out, int M, int K, int Kp, void* stream) {
+    if (!x || !out || K < 1 || Kp < K || Kp % BLOCK_K) return b2c_set_error(B2C_ERR_ARG, "b2c_tc_split_rows: bad argument");
+    if (M == 0) return B2C_OK;
+    size_t total = (size_t)M * Kp;
+    int grid = (int)((total + 255) / 256 > 148 * 32 ? 148 * 32 : (total + 255) / 256);
+    split_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, out, M, K, Kp);
+    B2C_CUDA(cudaGetLastError());
+    return B2C_OK;
+}
+
+int b2c_tc_prep_weight(const float* W, uint16_t* out, int N, int K, int Kp, int transpose, void* stream) {
+    int red = transpose ? N : K, rows = transpose ? K : N;
+    if (!W || !out || Kp < red || Kp % BLOCK_K) return b2c_set_error(B2C_ERR_ARG, "b2c_tc_prep_weight: bad argument");
+    size_t total = (size_t)rows * Kp;
+    prep_weight_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(W, out, N, K, Kp, rows, transpose);
+    B2C_CUDA(cudaGetLastError());
+    return B2C_OK;
+}
+
+int b2c_tc_linear(const uint16_t* a_split, const uint16_t* w_prep, const float* bias, const float* dtanh_src, int ld_src,
+                  float* out_f32, int ld_out, uint16_t* out_split, int M, int Kp, int act, void* stream) {
+    if (!a_split || !w_prep || (!out_f32 && !out_split) || Kp < BLOCK_K || Kp % BLOCK_K || M < 0)
+        return b2c_set_error(B2C_ERR_ARG, "b2c_tc_linear: bad argument");
+    if (((uintptr_t)a_split | (uintptr_t)w_prep | (uintptr_t)out_f32 | (uintptr_t)out_split | (uintptr_t)dtanh_src) & 15)
+        return b2c_set_error(B2C_ERR_ARG, "b2c_tc_linear: pointers must be 16-byte aligned");
+    if ((out_f32 && (ld_out & 3)) || (dtanh_src && (ld_src & 3)))
+        return b2c_set_error(B2C_ERR_ARG, "b2c_tc_linear: row strides must be multiples of 4 floats");
+    if (M == 0) return B2C_OK;
+    static int attr_set = 0;
+    static int num_sms = 0;
+    if (!attr_set) {
+        B2C_CUDA(cudaFuncSetAttribute(tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        int dev = 0;
+        B2C_CUDA(cudaGetDevice(&dev));
+        B2C_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+        attr_set = 1;
+    }
+    CUtensorMap map_a, map_w;
+    int rc = make_map(&map_a, a_split, (uint64_t)M, (uint64_t)2 * Kp, BLOCK_M);
+    if (rc) return rc;
+    rc = make_map(&map_w, w_prep, (uint64_t)BLOCK_N, (uint64_t)3 * Kp, BLOCK_N);
+    if (rc) return rc;
+    LinearArgs a;
+    a.bias = bias; a.dtanh_src = dtanh_src; a.out_f32 = out_f32; a.out_split = out_split; a.M = M;
+    a.kp_blocks = Kp / BLOCK_K; a.ld_out = ld_out; a.ld_src = ld_src; a.act = act;
+    int tiles = (M + BLOCK_M - 1) / BLOCK_M;
+    int grid = tiles < num_sms ? tiles : num_sms;
+    tc_linear_kernel<<<grid, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(map_a, map_w, a);
+    B2C_CUDA(cudaGetLastError());
+    return B2C_OK;
+}
+
+}  // extern "C"

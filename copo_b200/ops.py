@@ -221,3 +221,52 @@ def dot(a, b, out=None):
         out = torch.zeros(1, dtype=torch.float64, device=a.device)
     _lib.check(lib.b2c_dot(P(a), P(b), c_size_t(a.numel()), P(out), _lib.stream_ptr()))
     return out
+
+
+# ---- tcgen05 path (bf16x3) --------------------------------------------------------------------------------------
+def tc_padded_k(K):
+    return (K + 63) // 64 * 64
+
+
+def tc_split_rows(x, out=None):
+    """fp32 [M, K] -> bf16 [M, 2*Kp] (hi | lo)."""
+    lib = _lib_ready()
+    px, M, K, ldx = _rows2d(x)
+    Kp = tc_padded_k(K)
+    if out is None:
+        out = torch.empty((M, 2 * Kp), dtype=torch.bfloat16, device=x.device)
+    _lib.check(lib.b2c_tc_split_rows(px, c_int(ldx), P(out), c_int(M), c_int(K), c_int(Kp), _lib.stream_ptr()))
+    return out
+
+
+def tc_prep_weight(W, transpose=False):
+    """fp32 W [N, K] -> bf16 [rows, 3*Kp] = [hi | hi | lo] of W (or of W^T when transpose)."""
+    lib = _lib_ready()
+    N, K = W.shape
+    rows, red = (K, N) if transpose else (N, K)
+    Kp = tc_padded_k(red)
+    out = torch.empty((rows, 3 * Kp), dtype=torch.bfloat16, device=W.device)
+    _lib.check(lib.b2c_tc_prep_weight(P(_f32(W)), P(out), c_int(N), c_int(K), c_int(Kp), c_int(int(transpose)),
+                                      _lib.stream_ptr()))
+    return out
+
+
+def tc_linear(a_split, w_prep, bias=None, act=0, want_f32=True, want_split=False, dtanh_src=None, out_f32=None,
+              out_split=None):
+    """256-wide layer on the tensor cores.  Returns (fp32 [M, 256] or None, bf16 split [M, 512] or None)."""
+    lib = _lib_ready()
+    M, two_kp = a_split.shape
+    Kp = two_kp // 2
+    assert a_split.dtype == torch.bfloat16 and a_split.is_contiguous()
+    assert w_prep.shape == (256, 3 * Kp) and w_prep.is_contiguous(), (w_prep.shape, Kp)
+    dev = a_split.device
+    if want_f32 and out_f32 is None:
+        out_f32 = torch.empty((M, 256), dtype=torch.float32, device=dev)
+    if want_split and out_split is None:
+        out_split = torch.empty((M, 512), dtype=torch.bfloat16, device=dev)
+    ld_src = dtanh_src.stride(0) if dtanh_src is not None else 0
+    _lib.check(lib.b2c_tc_linear(P(a_split), P(w_prep), P(bias), ctypes.c_void_p(dtanh_src.data_ptr()) if dtanh_src is not None else None,
+                                 c_int(ld_src), ctypes.c_void_p(out_f32.data_ptr()) if out_f32 is not None else None,
+                                 c_int(out_f32.stride(0) if out_f32 is not None else 0), P(out_split), c_int(M), c_int(Kp),
+                                 c_int(act), _lib.stream_ptr()))
+    return out_f32, out_split

@@ -186,6 +186,21 @@ int b2c_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
 /* *out += <a, b> in float64 (algo_copo.py:274-278) */
 int b2c_dot(const float* a, const float* b, size_t n, double* out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * tcgen05 tensor-core path for the 256-wide layers ("bf16x3": fp32 operands split into bf16 hi + lo, products
+ * hi*hi + lo*hi + hi*lo accumulated in fp32 in TMEM).  Same layers as b2c_linear_forward / _backward_input.
+ *   a_split  [M][2*Kp] bf16: hi in columns [0, Kp), lo in [Kp, 2Kp), Kp = b2c_tc_padded_k(K), zero padded
+ *   w_prep   [256][3*Kp] bf16: [hi | hi | lo] of W (forward) or of W^T (input gradient)
+ * ------------------------------------------------------------------------------------------------- */
+int b2c_tc_padded_k(int K);
+int b2c_tc_split_rows(const float* x, int ldx, uint16_t* out, int M, int K, int Kp, void* stream);
+/* transpose = 0: W[N][K] -> rows N, reduction K.  transpose = 1: rows K, reduction N (dx = dy W). */
+int b2c_tc_prep_weight(const float* W, uint16_t* out, int N, int K, int Kp, int transpose, void* stream);
+/* out = epilogue(a W'^T): + bias, tanh (act = 1), * (1 - dtanh_src^2); writes fp32 [M][ld_out] and / or the
+ * [hi | lo] bf16 operand of the next layer [M][512].  Output width is 256. */
+int b2c_tc_linear(const uint16_t* a_split, const uint16_t* w_prep, const float* bias, const float* dtanh_src, int ld_src,
+                  float* out_f32, int ld_out, uint16_t* out_split, int M, int Kp, int act, void* stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -1,0 +1,67 @@
+"""tcgen05 path of the 256-wide layers against float64 references: split-bf16 ("bf16x3") accuracy must be far inside
+the 1e-4 budget of the value predictions; covers ragged M (tile tails), every padded K the nets use, the input-gradient
+form and the chained [hi | lo] operand hand-over between layers."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(x, W, b, act):
+    y = x.double() @ W.double().T + (b.double() if b is not None else 0)
+    return torch.tanh(y) if act else y
+
+
+@pytest.mark.parametrize("M,K", [(128, 64), (1000, 92), (4096 + 37, 256), (300, 157), (129, 184), (77, 463), (1, 92),
+                                 (40000, 92)])
+def test_tc_linear_forward(M, K):
+    from copo_b200 import ops
+    g = torch.Generator().manual_seed(M * 7 + K)
+    x = torch.rand(M, K, generator=g)
+    W = torch.randn(256, K, generator=g) / K ** 0.5
+    b = 0.1 * torch.randn(256, generator=g)
+    a = ops.tc_split_rows(x.cuda())
+    Kp = ops.tc_padded_k(K)
+    assert a.shape == (M, 2 * Kp)
+    # the split itself: hi + lo reproduces x to ~2^-17 relative
+    rec = a[:, :K].float() + a[:, Kp:Kp + K].float()
+    assert float((rec.cpu() - x).abs().max()) < 2e-5
+    assert float(a[:, K:Kp].float().abs().max()) == 0.0 if Kp > K else True
+    w = ops.tc_prep_weight(W.cuda())
+    for act in (0, 1):
+        y, ys = ops.tc_linear(a, w, b.cuda(), act=act, want_f32=True, want_split=True)
+        want = _ref(x, W, b, act)
+        err = float((y.cpu().double() - want).abs().max())
+        assert err < 3e-5, (act, err)
+        rec = ys[:, :256].float() + ys[:, 256:].float()
+        assert float((rec - y).abs().max()) < 2e-5
+
+
+def test_tc_matches_fp32_kernels_and_chains():
+    """Three-layer policy forward through the tensor-core path vs the exact fp32 kernels."""
+    from copo_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    M = 5000
+    x = torch.rand(M, 92, generator=g).cuda()
+    W1, W2 = (torch.randn(256, 92, generator=g) / 92 ** 0.5).cuda(), (torch.randn(256, 256, generator=g) / 16).cuda()
+    b1, b2 = (0.1 * torch.randn(256, generator=g)).cuda(), (0.1 * torch.randn(256, generator=g)).cuda()
+    h1 = ops.linear_forward(x, W1, b1, 1)
+    h2 = ops.linear_forward(h1, W2, b2, 1)
+    _, s1 = ops.tc_linear(ops.tc_split_rows(x), ops.tc_prep_weight(W1), b1, act=1, want_f32=False, want_split=True)
+    t2, _ = ops.tc_linear(s1, ops.tc_prep_weight(W2), b2, act=1)
+    assert float((t2 - h2).abs().max()) < 5e-5
+
+
+def test_tc_input_gradient():
+    from copo_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    M = 3000
+    dy = torch.randn(M, 256, generator=g)
+    W = torch.randn(256, 256, generator=g) / 16
+    h = torch.tanh(torch.randn(M, 256, generator=g))
+    want = (dy.double() @ W.double()) * (1 - h.double() ** 2)
+    a = ops.tc_split_rows(dy.cuda())
+    wt = ops.tc_prep_weight(W.cuda(), transpose=True)
+    dx, _ = ops.tc_linear(a, wt, None, act=0, dtanh_src=h.cuda())
+    assert float((dx.cpu().double() - want).abs().max()) < 1e-4 * float(want.abs().max())
