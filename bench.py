@@ -82,15 +82,32 @@ def _oracle_worker(args):
     cfg = osim.SimConfig(seed=seed)
     cfg.num_agents = SLOTS
     sim = osim.OracleSim(build_map(MAP), scenes, SLOTS, cfg, scene_offset=seed * 1000)
-    sim.reset()
+    out = sim.reset()
     rng = np.random.default_rng(seed)
-    acts = [rng.uniform(-1, 1, (scenes, SLOTS, 2)).astype(np.float32) for _ in range(4)]   # recoder.py:385
+    # the same rollout step as the GPU arm: policy MLP forward (92-256-256-4, normc init) + Gaussian sample + env step
+    D = out["obs"].shape[-1]
+    layers = []
+    for (i, o, std) in ((D, 256, 1.0), (256, 256, 1.0), (256, 4, 0.01)):
+        w = rng.normal(size=(o, i)).astype(np.float32)
+        w *= std / np.sqrt((w ** 2).sum(1, keepdims=True))
+        layers.append((np.ascontiguousarray(w.T), np.zeros(o, np.float32)))
+
+    def act(obs):
+        x = obs.reshape(-1, D)
+        for n, (W, b) in enumerate(layers):
+            x = x @ W + b
+            if n < 2:
+                x = np.tanh(x)
+        mean, log_std = x[:, :2], x[:, 2:]
+        a = mean + np.exp(log_std) * rng.standard_normal(mean.shape).astype(np.float32)
+        return a.reshape(scenes, SLOTS, 2).astype(np.float32)
+
     for t in range(warmup):
-        sim.step(acts[t % 4])
+        out = sim.step(act(out["obs"]))
     n0 = int(sim.agent_steps.sum())
     t0 = time.perf_counter()
     for t in range(steps):
-        sim.step(acts[t % 4])
+        out = sim.step(act(out["obs"]))
     dt = time.perf_counter() - t0
     return int(sim.agent_steps.sum()) - n0, dt
 
@@ -122,14 +139,15 @@ def run_reference(args):
     steps = max(1, min(args.steps, 200))
     warmup = max(1, min(args.warmup, 20))
     value, slowest, wall, total = cpu_oracle_throughput(procs, scenes, steps, warmup)
-    sample = "%d processes x %d scenes x %d agents x %d steps of the numpy oracle (U(-1,1)^2 actions)" % (
+    sample = "%d processes x %d scenes x %d agents x %d rollout steps of the numpy oracle (policy forward + env step)" % (
         procs, scenes, SLOTS, steps)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": slowest / steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "CoPO Intersection 40 agents: env step + neighbour/LCF bookkeeping, CPU restatement "
-                               "(oracle/sim.py; MetaDrive itself is not installable here)", "map": MAP,
+        "config": {"workload": "CoPO Intersection 40 agents, one rollout step: policy MLP forward + Gaussian sample + "
+                               "env step with neighbour/LCF bookkeeping, CPU restatement (oracle/; MetaDrive + RLlib "
+                               "are not installable here)", "map": MAP,
                    "agents_per_scene": SLOTS, "scenes": procs * scenes},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -145,6 +163,8 @@ def run_gpu(args):
     import numpy as np
     import torch
     import torch.distributed as dist
+    from copo_b200 import _lib, ops
+    from copo_b200 import policy as P
     from copo_b200.batched_env import BatchedDrivingEnv
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -155,14 +175,35 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     S, A = args.scenes, SLOTS
+    N = S * A
     env = BatchedDrivingEnv(MAP, num_scenes=S, num_slots=A, num_agents=A, seed=args.seed, scene_offset=rank * S,
                             device=dev)
     D = env.D
+    pol = P.CoPOPolicy(D, 2, P.copo_config(seed=args.seed), device=dev, dist=dist if world > 1 else None)
+    # rollout ring: the env writes observations / rewards / flags of step t straight into slot t % RING
+    RING = 4
+    obs = torch.zeros((RING + 1, N, D), device=dev)
+    outs = []
+    for r in range(RING):
+        o = env.alloc_outputs()
+        o["obs"] = obs[r + 1].view(S, A, D)
+        outs.append(o)
+    logits = torch.zeros((RING, N, 4), device=dev)
     env.reset()
-    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    acts = [torch.rand((S, A, 2), device=dev, generator=gen) * 2 - 1 for _ in range(8)]     # recoder.py:385
+    obs[0].copy_(env.out["obs"].reshape(N, D))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream()
+    state = {"t": 0}
+
+    def rollout_step():
+        """policy forward (tcgen05 bf16_split) -> Gaussian sample -> fused scene step; everything stays in HBM"""
+        t = state["t"]
+        r = t % RING
+        src = obs[r] if r or t == 0 else obs[RING]
+        lg = pol.model.forward(src)
+        actions, logp = ops.gaussian_sample(lg, seed=args.seed + rank * 7919, step=t)
+        env.step(actions.view(S, A, 2), out=outs[r])
+        state["t"] = t + 1
 
     def barrier():
         torch.cuda.synchronize()
@@ -170,31 +211,54 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for t in range(args.warmup):
-        env.step(acts[t % 8])
+    for _ in range(max(args.warmup, RING)):
+        rollout_step()
     barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
     n0 = env.agent_steps()
+    l0 = _lib.LAUNCHES
     barrier()
-    launches = 0
     for t in range(args.steps):
         flush.fill_(t & 0xff)                        # L2 flush, outside the timed events
         ev[t][0].record(stream)
-        env.step(acts[t % 8])
-        launches += 1
+        rollout_step()
         ev[t][1].record(stream)
     barrier()
+    launches = _lib.LAUNCHES - l0
     clk = clocks.stop() if rank == 0 else None
     n1 = env.agent_steps()
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = float(sum(step_ms))
     agent_steps = n1 - n0
 
+    # ---- per-kernel timing of the two heavy kernels (same inputs, L2 flushed before each) ---------------------
+    def time_kernel(fn, reps=20):
+        ms = []
+        for _ in range(reps):
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            fn()
+            b.record(stream)
+            torch.cuda.synchronize()
+            ms.append(a.elapsed_time(b))
+        return float(np.median(ms))
+
+    act_buf = torch.rand((S, A, 2), device=dev) * 2 - 1
+    env_ms = time_kernel(lambda: env.step(act_buf, out=outs[0]))
+    net = pol.model.nets["policy"]
+    w1, w2, _ = net.tc_weights(pol.model.weights_version)
+    a1 = ops.tc_split_rows(obs[0])
+    _, s1 = ops.tc_linear(a1, w1, net.b[0], act=1, want_f32=False, want_split=True)
+    h2 = torch.empty((N, 256), device=dev)
+    l2_ms = time_kernel(lambda: ops.tc_linear(s1, w2, net.b[1], act=1, out_f32=h2))
+    l1_ms = time_kernel(lambda: ops.tc_linear(a1, w1, net.b[0], act=1, want_f32=False, out_split=s1, want_split=True))
+
     # ---- end to end through the host-buffer API ------------------------------------------------------------
-    host_acts = [a.cpu().pin_memory() for a in acts[:4]]
+    host_acts = [(torch.rand((S, A, 2)) * 2 - 1).pin_memory() for _ in range(4)]
     for t in range(3):
         env.step_host(host_acts[t % 4])
     e2e_steps = max(3, min(args.steps, 50))
@@ -218,6 +282,11 @@ def run_gpu(args):
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         total_ms, e2e_ms = float(mx[0]), float(mx[1])
         agent_steps, e2e_agent_steps = float(sm[2]), float(sm[3])
+
+    train = None
+    if args.train_iters > 0:
+        train = time_training(args, dev, world, rank)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -225,43 +294,83 @@ def run_gpu(args):
 
     value = agent_steps / (total_ms * 1e-3)
     e2e_value = e2e_agent_steps / (e2e_ms * 1e-3)
-    peak, peak_src = _peaks()
-    algo_bytes = S * A * (4 * D + 153)               # SURVEY.md 8d / DESIGN.md: per agent slot 4*D + 153 bytes
-    kernel_ms = float(np.mean(step_ms))              # one launch per step: the step time IS the kernel time
-    achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
+    hbm_peak, peak_src = _peaks()
+    tc_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"] if os.path.exists(
+        os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1590.0
+    algo_bytes = N * (4 * D + 153)                   # SURVEY.md 8d / DESIGN.md: per agent slot 4*D + 153 bytes
+    env_gbs = algo_bytes / (env_ms * 1e-3) / 1e9
+    l2_flops = 2.0 * N * 256 * 256                   # algorithmic fp32-equivalent flops of the 256x256 layer
+    l2_tf = l2_flops / (l2_ms * 1e-3) / 1e12
     traffic = None
     tp = os.path.join(ROOT, "profiles", "env_step_traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-
+    env_roof = {"bound": "hbm", "achieved": env_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": env_gbs / hbm_peak,
+                "traffic": traffic, "peak_source": peak_src, "kernel": "env_step_kernel",
+                "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": env_ms,
+                "note": "issue-bound (72-laser lidar + neighbour search): see profiles/ for the instruction mix"}
+    mlp_roof = {"bound": "tensor", "achieved": l2_tf, "peak": tc_peak, "unit": "TFLOP/s", "frac": l2_tf / tc_peak,
+                "traffic": None, "peak_source": peak_src, "kernel": "tc_linear_kernel (256x256 layer, bf16_split)",
+                "algorithmic_flops_per_launch": l2_flops, "kernel_ms": l2_ms, "tensor_flops_issued": 3 * l2_flops,
+                "note": "achieved counts fp32-equivalent flops; the kernel issues 3x as many bf16 flops (split operands)"}
+    dominant_is_env = env_ms >= (l1_ms + l2_ms)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         v, slowest, wall, total = cpu_oracle_throughput(1, 16, 150, 3)
         cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": "numpy oracle, 16 scenes x 40 agents x 150 steps on one core (%.1f s)" % slowest}
+               "sample": "numpy oracle, 16 scenes x 40 agents x 150 rollout steps (policy forward + env step) on one "
+                         "core (%.1f s)" % slowest}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "CoPO Intersection 40 agents x %d scenes per GPU: fused scene step (dynamics, "
+        "config": {"workload": "CoPO Intersection 40 agents x %d scenes per GPU, one rollout step: policy MLP forward "
+                               "(92-256-256-4, tcgen05 bf16_split) + Gaussian sample + fused scene step (dynamics, "
                                "crash/out/arrive, respawn, neighbours + nei/global reward, 72-laser lidar obs + LCF)"
                                % S, "map": MAP, "agents_per_scene": A, "scenes_per_gpu": S, "obs_dim": D,
-                   "actions": "iid U(-1,1)^2 (reference FPS harness, eval/recoder.py:385)",
+                   "actions": "sampled from the randomly initialised policy (normc init, seed %d)" % args.seed,
                    "l2": "flushed between steps with a 256 MiB write, outside the timed events",
-                   "slots_per_step": S * A * world, "counted": "agents that received an action (valid slots)"},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src, "kernel": "env_step_kernel",
-                     "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": kernel_ms},
+                   "slots_per_step": N * world, "counted": "agents that received an action (valid slots)"},
+        "roofline": env_roof if dominant_is_env else mlp_roof,
+        "roofline_other": mlp_roof if dominant_is_env else env_roof,
+        "kernel_ms": {"env_step": env_ms, "tc_linear_layer1": l1_ms, "tc_linear_layer2": l2_ms},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": env.h2d_bytes_per_step * world,
-                "d2h_bytes_per_step": env.d2h_bytes_per_step * world, "steps": e2e_steps},
+                "d2h_bytes_per_step": env.d2h_bytes_per_step * world, "steps": e2e_steps,
+                "api": "BatchedDrivingEnv.step_host: pinned host actions in, every env output back to pinned host"},
         "gpu_launches": launches,
         "clocks": clk,
+        "train": train,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def time_training(args, dev, world, rank):
+    """Whole CoPO training iterations (rollout + postprocess + SGD epochs + meta update) on a reduced fragment."""
+    import torch
+    from copo_b200 import trainer as T
+    tr = T.CoPOTrainer(dict(env="MultiAgentIntersectionEnv", num_scenes=args.train_scenes,
+                            rollout_fragment_length=args.train_fragment, sgd_minibatch_size=65536, num_sgd_iter=5,
+                            lcf_num_iters=5, env_config={"num_agents": SLOTS}, seed=args.seed), device=dev)
+    tr.train()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    steps = 0
+    for _ in range(args.train_iters):
+        res = tr.train()
+        steps += res["custom_metrics"]["agent_steps"]
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    out = {"agent_env_steps_per_s_per_gpu": steps / dt, "iterations": args.train_iters, "seconds": dt,
+           "scenes_per_gpu": args.train_scenes, "fragment": args.train_fragment, "sgd_minibatch_size": 65536,
+           "num_sgd_iter": 5, "lcf_num_iters": 5, "sample_ms": tr._timers["sample_time_ms"],
+           "learn_ms": tr._timers["learn_time_ms"],
+           "what": "full CoPOTrainer.training_step iterations, wall clock, this rank"}
+    tr.stop()
+    return out
 
 
 def main():
@@ -273,6 +382,9 @@ def main():
     ap.add_argument("--scenes", type=int, default=SCENES_PER_GPU, help="scenes per GPU")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--train-iters", type=int, default=1, help="timed full training iterations (0: skip)")
+    ap.add_argument("--train-scenes", type=int, default=1024)
+    ap.add_argument("--train-fragment", type=int, default=16)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

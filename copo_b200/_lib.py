@@ -48,7 +48,12 @@ def load():
     return _lib
 
 
+LAUNCHES = 0      # C-ABI compute calls issued by this process (each enqueues at least one of the library's kernels)
+
+
 def check(rc):
+    global LAUNCHES
+    LAUNCHES += 1
     if rc != 0:
         raise B2CError("libcopo_b200 error %d: %s" % (rc, load().b2c_last_error().decode()))
 

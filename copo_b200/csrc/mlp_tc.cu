@@ -3,19 +3,19 @@
 //   y[M x 256] = epilogue( A[M x K] * W[256 x K]^T )            M = scenes x slots x steps (10^5 .. 10^7 rows)
 //
 // fp32 accuracy on bf16 tensor cores: every fp32 operand x is split into hi = bf16(x), lo = bf16(x - hi) and the
-// product is taken as hi*hi + lo*hi + hi*lo with fp32 accumulation in TMEM ("bf16x3", ~2^-16 relative per product)
-// - value predictions feed GAE, which must match the fp32 reference to 1e-4 (SURVEY.md 7 "hard parts").  The three
-// passes are one GEMM over a 3x longer reduction dimension:
-//   A' = [A_hi | A_lo | A_hi]   (stored once as [hi | lo]; the TMA producer maps reduction blocks onto it)
-//   W' = [W_hi | W_hi | W_lo]   (prepared per weight update; weights are tiny)
+// product is taken as hi*hi + lo*hi + hi*lo + lo*lo with fp32 accumulation in TMEM ("split bf16") - value
+// predictions feed GAE, which must match the fp32 reference to 1e-4 (SURVEY.md 7 "hard parts").  Activations are
+// stored as [M][hi(Kp) | lo(Kp)], weights as [256][hi(Kp) | lo(Kp)]; one pipeline stage holds the hi and lo blocks
+// of both operands for one 64-wide reduction block, and the MMA thread issues the four products from it, so every
+// operand byte crosses L2 -> shared memory once per output tile.
 //
-// Kernel: persistent, one CTA per SM, 128 x 256 output tile, 64-wide reduction blocks.
-//   warp 0     TMA producer: cp.async.bulk.tensor (SWIZZLE_128B) of the A and W' blocks into a 4-stage ring
-//   warp 1     MMA issuer: one thread issues tcgen05.mma.cta_group::1.kind::f16 (M128 N256 K16), accumulators in
-//              TMEM (2 x 256 columns, double buffered so the epilogue of tile i overlaps the MMAs of tile i+1)
-//   warp 2     TMEM allocation
-//   warps 4-7  epilogue: tcgen05.ld 32 lanes x 32 columns, bias + tanh (or * (1 - h^2) for the input gradient),
-//              writes fp32 and / or the [hi | lo] bf16 operand of the next layer
+// Kernel: persistent, one CTA per SM, 128 x 256 output tile.
+//   warp 0      TMA producer: cp.async.bulk.tensor (SWIZZLE_128B) of A_hi, A_lo, W_hi, W_lo blocks, 2-stage ring
+//   warp 1      MMA issuer: one thread issues tcgen05.mma.cta_group::1.kind::f16 (M128 N256 K16), accumulators in
+//               TMEM (2 x 256 columns, double buffered so the epilogue of tile i overlaps the MMAs of tile i+1)
+//   warp 2      TMEM allocation
+//   warps 4-11  epilogue: tcgen05.ld 32 lanes x 32 columns, bias (from shared memory) + tanh (or * (1 - h^2) for
+//               the input gradient), writes fp32 and / or the [hi | lo] bf16 operand of the next layer
 //
 // Replaces: SlimFC hidden layers of CCModel / CoPOModel forward (torch_copo/algo_ccppo.py:108-170, 201-219;
 // algo_copo.py:138-153) and their input-gradient GEMM in backward.
@@ -28,13 +28,14 @@
 namespace b2c {
 namespace tc {
 
-constexpr int BLOCK_M = 128, BLOCK_N = 256, BLOCK_K = 64, UMMA_K = 16, STAGES = 4;
-constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;      // 16 KB
-constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;      // 32 KB
-constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int BLOCK_M = 128, BLOCK_N = 256, BLOCK_K = 64, UMMA_K = 16, STAGES = 2;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;      // 16 KB per half (hi or lo)
+constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;      // 32 KB per half
+constexpr int STAGE_BYTES = 2 * A_STAGE_BYTES + 2 * B_STAGE_BYTES;     // A_hi, A_lo, W_hi, W_lo: 96 KB
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 1024 /*bias*/;
 constexpr int TMEM_COLS = 512;
-constexpr int NUM_THREADS = 256;
+constexpr int EPI_WARPS = 8;
+constexpr int NUM_THREADS = 128 + EPI_WARPS * 32;
 // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D = f32, A = B = bf16, both K-major,
 // N = 256 (bits 17..22 = N >> 3), M = 128 (bits 24..28 = M >> 4)
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((BLOCK_N >> 3) << 17) | ((BLOCK_M >> 4) << 24);
@@ -97,9 +98,23 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 }
 
 __device__ __forceinline__ float fast_tanh(float x) {
-    // 1 - 2 / (exp(2x) + 1); |error| ~ 2e-7 absolute, saturates cleanly for large |x|
-    float e = __expf(2.0f * x);
-    return 1.0f - __fdividef(2.0f, e + 1.0f);
+    // odd rational minimax (13/6) on [-9, 9]: relative error < 4e-7 down to the smallest arguments (an exp-based
+    // form loses relative accuracy near 0, which the value heads then amplify); checked in tests/test_tc_gpu.py
+    x = fminf(fmaxf(x, -9.0f), 9.0f);
+    const float x2 = x * x;
+    float p = -2.76076847742355e-16f;
+    p = fmaf(p, x2, 2.00018790482477e-13f);
+    p = fmaf(p, x2, -8.60467152213735e-11f);
+    p = fmaf(p, x2, 5.12229709037114e-08f);
+    p = fmaf(p, x2, 1.48572235717979e-05f);
+    p = fmaf(p, x2, 6.37261928875436e-04f);
+    p = fmaf(p, x2, 4.89352455891786e-03f);
+    p *= x;
+    float q = 1.19825839466702e-06f;
+    q = fmaf(q, x2, 1.18534705686654e-04f);
+    q = fmaf(q, x2, 2.26843463243900e-03f);
+    q = fmaf(q, x2, 4.89352518554385e-03f);
+    return __fdividef(p, q);
 }
 __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
     return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
@@ -110,7 +125,7 @@ struct LinearArgs {
     const float* dtanh_src;   // [M][ld_src] or null: multiply the result by (1 - h^2)
     float* out_f32;           // [M][ld_out] or null
     uint16_t* out_split;      // [M][512] bf16 (hi | lo) or null
-    int M, kp_blocks;         // kp_blocks = Kp / 64; the reduction loop runs 3 * kp_blocks blocks
+    int M, kp_blocks;         // kp_blocks = Kp / 64 reduction blocks, four products each
     int ld_out, ld_src, act;  // act: 0 none, 1 tanh
 };
 
@@ -124,10 +139,12 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     uint64_t* tmem_full = empty + STAGES;
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    float* s_bias = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_tiles = (args.M + BLOCK_M - 1) / BLOCK_M;
-    const int num_kb = 3 * args.kp_blocks;
+    const int num_kb = args.kp_blocks;
+    const int kp = args.kp_blocks * BLOCK_K;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -135,7 +152,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -143,6 +160,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                      "n"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    for (int i = threadIdx.x; i < BLOCK_N; i += NUM_THREADS) s_bias[i] = args.bias ? args.bias[i] : 0.0f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -155,14 +173,12 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1u);
-                    uint8_t* sa = smem + stage * STAGE_BYTES;
-                    uint8_t* sb = sa + A_STAGE_BYTES;
+                    uint8_t* st = smem + stage * STAGE_BYTES;
                     mbar_expect_tx(&full[stage], STAGE_BYTES);
-                    // reduction block kb of A' = [hi | lo | hi] lives at column block (segment 1 ? lo : hi)
-                    int seg = kb / args.kp_blocks, blk = kb - seg * args.kp_blocks;
-                    int a_col = ((seg == 1) ? args.kp_blocks : 0) * BLOCK_K + blk * BLOCK_K;
-                    tma_load_2d(sa, &map_a, a_col, tile * BLOCK_M, &full[stage]);
-                    tma_load_2d(sb, &map_w, kb * BLOCK_K, 0, &full[stage]);
+                    tma_load_2d(st, &map_a, kb * BLOCK_K, tile * BLOCK_M, &full[stage]);                       // A_hi
+                    tma_load_2d(st + A_STAGE_BYTES, &map_a, kp + kb * BLOCK_K, tile * BLOCK_M, &full[stage]);  // A_lo
+                    tma_load_2d(st + 2 * A_STAGE_BYTES, &map_w, kb * BLOCK_K, 0, &full[stage]);                // W_hi
+                    tma_load_2d(st + 2 * A_STAGE_BYTES + B_STAGE_BYTES, &map_w, kp + kb * BLOCK_K, 0, &full[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -180,12 +196,17 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-                    const uint32_t sb = sa + A_STAGE_BYTES;
-                    const uint64_t da = make_desc(sa), db = make_desc(sb);
+                    const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + A_STAGE_BYTES);
+                    const uint64_t w_hi = make_desc(sa + 2 * A_STAGE_BYTES);
+                    const uint64_t w_lo = make_desc(sa + 2 * A_STAGE_BYTES + B_STAGE_BYTES);
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                         // advance the start address by 32 B (16 bf16) inside the 128 B swizzle row
-                        umma_bf16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC, (kb | k) ? 1u : 0u);
+                        const uint64_t o = (uint64_t)(k * 2);
+                        umma_bf16(tmem_d, a_hi + o, w_hi + o, IDESC, (kb | k) ? 1u : 0u);
+                        umma_bf16(tmem_d, a_lo + o, w_hi + o, IDESC, 1u);
+                        umma_bf16(tmem_d, a_hi + o, w_lo + o, IDESC, 1u);
+                        umma_bf16(tmem_d, a_lo + o, w_lo + o, IDESC, 1u);
                     }
                     umma_commit(&empty[stage]);                  // frees the smem slot when these MMAs retire
                     if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);
@@ -195,8 +216,9 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             }
         }
     } else if (warp >= 4) {
-        // ===== epilogue: warp w reads TMEM lanes 32*(w%4) .. +31, one output row per thread =====
+        // ===== epilogue: warp w reads TMEM lanes 32*(w%4) .. +31 (one output row per thread), columns by half =====
         const int q = warp & 3;
+        const int half = (warp - 4) >> 2;                        // 0: columns 0..127, 1: columns 128..255
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             mbar_wait(&tmem_full[acc], acc_phase);
@@ -205,16 +227,21 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const bool live = row < args.M;
             const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
 #pragma unroll 1
-            for (int c = 0; c < BLOCK_N / 32; ++c) {
+            for (int cc = 0; cc < BLOCK_N / 64; ++cc) {
+                const int c = half * (BLOCK_N / 64) + cc;        // 32-column chunk index
                 uint32_t r[32];
                 tmem_ld32(taddr0 + (uint32_t)(c * 32), r);
                 float v[32];
+                const float4* b4 = reinterpret_cast<const float4*>(s_bias + c * 32);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float x = __uint_as_float(r[j]);
-                    if (args.bias) x += __ldg(args.bias + c * 32 + j);
-                    if (args.act == 1) x = fast_tanh(x);
-                    v[j] = x;
+                for (int j = 0; j < 8; ++j) {
+                    float4 bb = b4[j];
+                    v[4 * j] = __uint_as_float(r[4 * j]) + bb.x; v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + bb.y;
+                    v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bb.z; v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bb.w;
+                }
+                if (args.act == 1) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = fast_tanh(v[j]);
                 }
                 if (live) {
                     if (args.dtanh_src) {
@@ -235,10 +262,12 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         uint32_t hi[16], lo[16];
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * j]), h1 = __float2bfloat16_rn(v[2 * j + 1]);
-                            __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * j] - __bfloat162float(h0));
-                            __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * j + 1] - __bfloat162float(h1));
-                            hi[j] = pack_bf16(h0, h1); lo[j] = pack_bf16(l0, l1);
+                            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                            uint32_t hb = *reinterpret_cast<uint32_t*>(&h2);
+                            float r0 = v[2 * j] - __uint_as_float(hb << 16);
+                            float r1 = v[2 * j + 1] - __uint_as_float(hb & 0xffff0000u);
+                            __nv_bfloat162 l2 = __floats2bfloat162_rn(r0, r1);
+                            hi[j] = hb; lo[j] = *reinterpret_cast<uint32_t*>(&l2);
                         }
                         uint4* oh = reinterpret_cast<uint4*>(args.out_split + (size_t)row * 512 + c * 32);
                         uint4* ol = reinterpret_cast<uint4*>(args.out_split + (size_t)row * 512 + 256 + c * 32);
@@ -276,7 +305,7 @@ __global__ void split_rows_kernel(const float* __restrict__ x, int ldx, uint16_t
         out[m * 2 * Kp + Kp + k] = __bfloat16_as_ushort(l);
     }
 }
-// W fp32 [N][K] (or its transpose) -> [rows][3*Kp] bf16: [hi | hi | lo]
+// W fp32 [N][K] (or its transpose) -> [rows][2*Kp] bf16: [hi | lo]
 __global__ void prep_weight_kernel(const float* __restrict__ W, uint16_t* __restrict__ out, int N, int K, int Kp, int rows,
                                    int transpose) {
     // transpose = 0: out row n, reduction index k reads W[n][k]   (forward, rows = N, reduction K)
@@ -289,10 +318,9 @@ __global__ void prep_weight_kernel(const float* __restrict__ W, uint16_t* __rest
         if (c < red) v = transpose ? W[(size_t)c * K + r] : W[(size_t)r * K + c];
         __nv_bfloat16 h = __float2bfloat16_rn(v);
         __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
-        uint16_t* o = out + (size_t)r * 3 * Kp;
+        uint16_t* o = out + (size_t)r * 2 * Kp;
         o[c] = __bfloat16_as_ushort(h);
-        o[Kp + c] = __bfloat16_as_ushort(h);
-        o[2 * Kp + c] = __bfloat16_as_ushort(l);
+        o[Kp + c] = __bfloat16_as_ushort(l);
     }
 }
 
@@ -376,7 +404,7 @@ int b2c_tc_linear(const uint16_t* a_split, const uint16_t* w_prep, const float* 
     CUtensorMap map_a, map_w;
     int rc = make_map(&map_a, a_split, (uint64_t)M, (uint64_t)2 * Kp, BLOCK_M);
     if (rc) return rc;
-    rc = make_map(&map_w, w_prep, (uint64_t)BLOCK_N, (uint64_t)3 * Kp, BLOCK_N);
+    rc = make_map(&map_w, w_prep, (uint64_t)BLOCK_N, (uint64_t)2 * Kp, BLOCK_N);
     if (rc) return rc;
     LinearArgs a;
     a.bias = bias; a.dtanh_src = dtanh_src; a.out_f32 = out_f32; a.out_split = out_split; a.M = M;

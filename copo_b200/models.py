@@ -62,23 +62,52 @@ class _Net:
             self.W[k].copy_(w)
             self.b[k].zero_()
 
+    # ---- tensor-core operands: [hi | lo] bf16 copies of the 256-wide layers, rebuilt when weights change ----
+    def tc_ok(self):
+        return len(self.shapes) == 3 and self.hiddens == (256, 256)
+
+    def tc_weights(self, version):
+        if getattr(self, "_tc_version", None) != version:
+            self._tc_w = [ops.tc_prep_weight(self.W[0]), ops.tc_prep_weight(self.W[1]),
+                          ops.tc_prep_weight(self.W[1], transpose=True)]
+            self._tc_version = version
+        return self._tc_w
+
     # inference: no activations kept
-    def forward(self, x):
+    def forward(self, x, tc_version=None):
+        if tc_version is not None and self.tc_ok():
+            w1, w2, _ = self.tc_weights(tc_version)
+            _, s1 = ops.tc_linear(ops.tc_split_rows(x), w1, self.b[0], act=1, want_f32=False, want_split=True)
+            h2, _ = ops.tc_linear(s1, w2, self.b[1], act=1)
+            return ops.linear_forward(h2, self.W[2], self.b[2], 0)
         h = x
         for k in range(len(self.shapes)):
             last = k == len(self.shapes) - 1
             h = ops.linear_forward(h, self.W[k], self.b[k], 0 if last else 1)
         return h
 
-    def forward_train(self, x):
+    def forward_train(self, x, tc_version=None):
+        if tc_version is not None and self.tc_ok():
+            w1, w2, _ = self.tc_weights(tc_version)
+            h1, s1 = ops.tc_linear(ops.tc_split_rows(x), w1, self.b[0], act=1, want_f32=True, want_split=True)
+            h2, _ = ops.tc_linear(s1, w2, self.b[1], act=1)
+            return [x, h1, h2, ops.linear_forward(h2, self.W[2], self.b[2], 0)]
         acts = [x]
         for k in range(len(self.shapes)):
             last = k == len(self.shapes) - 1
             acts.append(ops.linear_forward(acts[-1], self.W[k], self.b[k], 0 if last else 1))
         return acts                                                     # [x, h1, h2, out]
 
-    def backward(self, acts, dout):
+    def backward(self, acts, dout, tc_version=None):
         """Accumulates dW / db of every layer given d(loss)/d(out)."""
+        if tc_version is not None and self.tc_ok():
+            x, h1, h2, _ = acts
+            dz2 = ops.linear_backward(dout, h2, self.W[2], self.dW[2], self.db[2], h_prev_is_tanh=True)
+            # input gradient of layer 2 on the tensor cores, weight gradients on the fp32 path
+            dz1, _ = ops.tc_linear(ops.tc_split_rows(dz2), self.tc_weights(tc_version)[2], None, act=0, dtanh_src=h1)
+            ops.linear_backward(dz2, h1, self.W[1], self.dW[1], self.db[1], h_prev_is_tanh=True, need_dx=False)
+            ops.linear_backward(dz1, x, self.W[0], self.dW[0], self.db[0], h_prev_is_tanh=False, need_dx=False)
+            return
         d = dout
         for k in reversed(range(len(self.shapes))):
             d = ops.linear_backward(d, acts[k], self.W[k], self.dW[k], self.db[k], h_prev_is_tanh=(k > 0),
@@ -90,7 +119,7 @@ class CCModel:
     VALUE = ("_value_branch_separate.0._model.0", "_value_branch_separate.1._model.0", "_value_branch._model.0")
 
     def __init__(self, obs_dim, act_dim=2, hiddens=(256, 256), fuse_mode="none", counterfactual=True, num_neighbours=4,
-                 device=None, seed=0, critic_obs_dim=None):
+                 device=None, seed=0, critic_obs_dim=None, precision="bf16_split"):
         self.obs_dim, self.act_dim, self.num_outputs = int(obs_dim), int(act_dim), 2 * int(act_dim)
         self.custom = dict(fuse_mode=fuse_mode, counterfactual=counterfactual, num_neighbours=num_neighbours)
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
@@ -100,6 +129,16 @@ class CCModel:
         self._extra_nets(hiddens)
         self._allocate(seed)
         self.tower_stats = {}
+        # "bf16_split": 256-wide layers on tcgen05 tensor cores with split-bf16 operands (fp32-grade accuracy);
+        # "fp32": CUDA-core kernels, exact fp32 (used by the tight parity tests)
+        self.precision = precision
+        self.weights_version = 0
+
+    def _tc(self):
+        return self.weights_version if self.precision == "bf16_split" else None
+
+    def mark_weights_changed(self):
+        self.weights_version += 1
 
     def _extra_nets(self, hiddens):
         pass
@@ -124,7 +163,7 @@ class CCModel:
         if isinstance(obs, dict):
             obs = obs.get("obs_flat", obs.get("obs"))
         obs = obs.reshape(obs.shape[0], -1)
-        logits = self.nets["policy"].forward(obs)
+        logits = self.nets["policy"].forward(obs, self._tc())
         return logits if state is None else (logits, state)
 
     __call__ = forward
@@ -134,7 +173,7 @@ class CCModel:
                          "Call central_value_function(cobs) instead!")
 
     def central_value_function(self, cobs):
-        return self.nets["value"].forward(cobs).reshape(-1)
+        return self.nets["value"].forward(cobs, self._tc()).reshape(-1)
 
     def zero_grad(self):
         self.grad.zero_()
@@ -159,6 +198,7 @@ class CCModel:
         return out
 
     def load_state_dict(self, sd, strict=True):
+        self.mark_weights_changed()
         for net in self.nets.values():
             for name, W, b in zip(net.names, net.W, net.b):
                 if name + ".weight" not in sd:
@@ -171,6 +211,7 @@ class CCModel:
     def load_policy_npz(self, path_or_dict):
         """Policy-only weights in either naming of best_checkpoints/*.npz (get_policy_function.py:54-98)."""
         w = path_or_dict if isinstance(path_or_dict, dict) else dict(np.load(path_or_dict))
+        self.mark_weights_changed()
         keys = list(w.keys())
         net = self.nets["policy"]
         if self.POLICY[0] + ".weight" in keys:
@@ -190,9 +231,10 @@ class CoPOModel(CCModel):
     GLOBAL = ("global_value_network.0._model.0", "global_value_network.1._model.0", "global_value_network.2._model.0")
 
     def __init__(self, obs_dim, act_dim=2, hiddens=(256, 256), fuse_mode="none", counterfactual=True, num_neighbours=4,
-                 initial_lcf_std=0.1, use_distributional_lcf=True, device=None, seed=0):
+                 initial_lcf_std=0.1, use_distributional_lcf=True, device=None, seed=0, precision="bf16_split"):
         self.use_distributional_lcf = use_distributional_lcf
-        super().__init__(obs_dim, act_dim, hiddens, fuse_mode, counterfactual, num_neighbours, device, seed)
+        super().__init__(obs_dim, act_dim, hiddens, fuse_mode, counterfactual, num_neighbours, device, seed,
+                         precision=precision)
         init = [0.0, math.log(initial_lcf_std)] if use_distributional_lcf else [0.0]
         self.lcf_parameters = torch.tensor(init, dtype=torch.float32, device=self.device)     # algo_copo.py:120-124
         self.lcf_grad = torch.zeros_like(self.lcf_parameters)
@@ -202,10 +244,10 @@ class CoPOModel(CCModel):
         self.nets["global"] = _Net(self.GLOBAL, self.cobs_dim, hiddens, 1)
 
     def get_nei_value(self, cobs):
-        return self.nets["nei"].forward(cobs).reshape(-1)
+        return self.nets["nei"].forward(cobs, self._tc()).reshape(-1)
 
     def get_global_value(self, cobs):
-        return self.nets["global"].forward(cobs).reshape(-1)
+        return self.nets["global"].forward(cobs, self._tc()).reshape(-1)
 
     @property
     def lcf_mean(self):

@@ -223,7 +223,7 @@ def dot(a, b, out=None):
     return out
 
 
-# ---- tcgen05 path (bf16x3) --------------------------------------------------------------------------------------
+# ---- tcgen05 path (split bf16) --------------------------------------------------------------------------------------
 def tc_padded_k(K):
     return (K + 63) // 64 * 64
 
@@ -240,12 +240,12 @@ def tc_split_rows(x, out=None):
 
 
 def tc_prep_weight(W, transpose=False):
-    """fp32 W [N, K] -> bf16 [rows, 3*Kp] = [hi | hi | lo] of W (or of W^T when transpose)."""
+    """fp32 W [N, K] -> bf16 [rows, 2*Kp] = [hi | lo] of W (or of W^T when transpose)."""
     lib = _lib_ready()
     N, K = W.shape
     rows, red = (K, N) if transpose else (N, K)
     Kp = tc_padded_k(red)
-    out = torch.empty((rows, 3 * Kp), dtype=torch.bfloat16, device=W.device)
+    out = torch.empty((rows, 2 * Kp), dtype=torch.bfloat16, device=W.device)
     _lib.check(lib.b2c_tc_prep_weight(P(_f32(W)), P(out), c_int(N), c_int(K), c_int(Kp), c_int(int(transpose)),
                                       _lib.stream_ptr()))
     return out
@@ -258,7 +258,7 @@ def tc_linear(a_split, w_prep, bias=None, act=0, want_f32=True, want_split=False
     M, two_kp = a_split.shape
     Kp = two_kp // 2
     assert a_split.dtype == torch.bfloat16 and a_split.is_contiguous()
-    assert w_prep.shape == (256, 3 * Kp) and w_prep.is_contiguous(), (w_prep.shape, Kp)
+    assert w_prep.shape == (256, 2 * Kp) and w_prep.is_contiguous(), (w_prep.shape, Kp)
     dev = a_split.device
     if want_f32 and out_f32 is None:
         out_f32 = torch.empty((M, 256), dtype=torch.float32, device=dev)

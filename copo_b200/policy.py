@@ -16,6 +16,7 @@ import numpy as np
 import torch
 
 from . import ops
+from . import parallel
 from .models import CCModel, CoPOModel
 
 # SampleBatch / Postprocessing column names (rllib) and CoPO's own (algo_copo.py:48-60)
@@ -46,7 +47,7 @@ def ippo_config(**over):
     c = AlgoConfig(gamma=0.99, lambda_=0.95, kl_coeff=0.2, kl_target=0.01, vf_loss_coeff=1.0, entropy_coeff=0.0,
                    clip_param=0.2, vf_clip_param=100.0, old_value_loss=True, use_gae=True, use_critic=True, lr=3e-4,
                    sgd_minibatch_size=512, rollout_fragment_length=200, train_batch_size=2000, num_sgd_iter=5,
-                   fcnet_hiddens=(256, 256), env_config={}, seed=0)
+                   fcnet_hiddens=(256, 256), env_config={}, seed=0, precision="bf16_split")
     c["lambda"] = c["lambda_"]
     return c.update_from_dict(over)
 
@@ -98,7 +99,7 @@ class IPPOPolicy:
 
     def _build_model(self, seed):
         return CCModel(self.obs_dim, self.act_dim, self.config["fcnet_hiddens"], fuse_mode="none", device=self.device,
-                       seed=seed)
+                       seed=seed, precision=self.config.get("precision", "bf16_split"))
 
     # ---- acting (a7) ---------------------------------------------------------------------------------------
     def compute_actions(self, obs, eps=None, step=0, deterministic=False):
@@ -125,17 +126,18 @@ class IPPOPolicy:
                    kl_coeff=self.kl_coeff)
         B = train_batch[OBS].shape[0]
         pol = model.nets["policy"]
-        acts_p = pol.forward_train(train_batch[OBS])
+        tc = model._tc()
+        acts_p = pol.forward_train(train_batch[OBS], tc)
         head_acts, heads = [], []
         for net_name, in_col, old_col, tgt_col in self._heads(train_batch):
-            acts = model.nets[net_name].forward_train(train_batch[in_col])
+            acts = model.nets[net_name].forward_train(train_batch[in_col], tc)
             head_acts.append((net_name, acts))
             heads.append((acts[-1].reshape(-1), train_batch[old_col], train_batch[tgt_col]))
         dlogits, dvs, st = ops.ppo_head(acts_p[-1], train_batch[ACTIONS], train_batch[ACTION_LOGP],
                                         train_batch[ACTION_DIST_INPUTS], train_batch[self._adv_column()], heads, cfg)
-        pol.backward(acts_p, dlogits)
+        pol.backward(acts_p, dlogits, tc)
         for (net_name, acts), dv in zip(head_acts, dvs):
-            model.nets[net_name].backward(acts, dv.unsqueeze(1))
+            model.nets[net_name].backward(acts, dv.unsqueeze(1), tc)
         m = st / B
         total = m[0] + cfg["vf_loss_coeff"] * (m[1] + m[2] + m[3]) - cfg["entropy_coeff"] * m[4] + cfg["kl_coeff"] * m[5]
         ts = model.tower_stats
@@ -155,10 +157,11 @@ class IPPOPolicy:
         self.model.zero_grad()
         self.loss(self.model, None, train_batch)
         scale = 1.0
-        if self.dist is not None and self.dist.is_initialized() and self.dist.get_world_size() > 1:
-            self.dist.all_reduce(self.model.grad)        # one NCCL all-reduce of the flat gradient
-            scale = 1.0 / self.dist.get_world_size()
+        if parallel.active(self.dist):
+            parallel.allreduce_sum_(self.model.grad, self.dist)      # one NCCL all-reduce of the flat gradient
+            scale = 1.0 / self.dist.get_world_size()                 # the mean is folded into the Adam kernel
         self._optimizer.apply(self.model.grad, grad_scale=scale)
+        self.model.mark_weights_changed()
         self.num_grad_updates += 1
         return dict(self.model.tower_stats)
 
@@ -203,9 +206,7 @@ class IPPOPolicy:
         return ro
 
     def _allreduce_stats(self, st):
-        if self.dist is not None and self.dist.is_initialized() and self.dist.get_world_size() > 1:
-            self.dist.all_reduce(st)
-        return st
+        return parallel.allreduce_sum_(st, self.dist)
 
 
 class CCPPOPolicy(IPPOPolicy):
@@ -218,7 +219,7 @@ class CCPPOPolicy(IPPOPolicy):
     def _build_model(self, seed):
         c = self.config
         return CCModel(self.obs_dim, self.act_dim, c["fcnet_hiddens"], c["fuse_mode"], c["counterfactual"],
-                       c["num_neighbours"], device=self.device, seed=seed)
+                       c["num_neighbours"], device=self.device, seed=seed, precision=c.get("precision", "bf16_split"))
 
     def _heads(self, train_batch):
         return [("value", CENTRALIZED_CRITIC_OBS, VF_PREDS, VALUE_TARGETS)]
@@ -252,7 +253,7 @@ class CoPOPolicy(CCPPOPolicy):
         c = self.config
         return CoPOModel(self.obs_dim, self.act_dim, c["fcnet_hiddens"], c["fuse_mode"], c["counterfactual"],
                          c["num_neighbours"], c["initial_lcf_std"], c["use_distributional_lcf"], device=self.device,
-                         seed=seed)
+                         seed=seed, precision=c.get("precision", "bf16_split"))
 
     def _heads(self, train_batch):
         return [("value", CENTRALIZED_CRITIC_OBS, VF_PREDS, VALUE_TARGETS),
@@ -311,15 +312,13 @@ class CoPOPolicy(CCPPOPolicy):
         cfg = dict(clip_param=self.config["clip_param"], vf_clip_param=0.0, vf_loss_coeff=0.0, entropy_coeff=0.0,
                    kl_coeff=0.0)
         pol = model.nets["policy"]
-        acts = pol.forward_train(batch[OBS])
+        acts = pol.forward_train(batch[OBS], model._tc())
         model.grad[model.policy_slice()].zero_()
         dlogits, _, st = ops.ppo_head(acts[-1], batch[ACTIONS], batch[ACTION_LOGP], None, adv, [], cfg, mode=mode)
-        pol.backward(acts, dlogits)
-        g = model.grad[model.policy_slice()]
-        if self.dist is not None and self.dist.is_initialized() and self.dist.get_world_size() > 1:
-            self.dist.all_reduce(g)                      # reduce the gradient vectors BEFORE the dot (bilinear)
-            g = g / self.dist.get_world_size()
-        return g.clone(), st
+        pol.backward(acts, dlogits, model._tc())
+        g = model.grad[model.policy_slice()].clone()
+        parallel.allreduce_mean_(g, self.dist)           # reduce the gradient vectors BEFORE the dot (bilinear)
+        return g, st
 
     def meta_update(self, train_batch, eps=None):
         B = train_batch[OBS].shape[0]
@@ -332,7 +331,7 @@ class CoPOPolicy(CCPPOPolicy):
         mean, std = float(mean_t), float(std_t)
         terms = self._allreduce_stats(ops.lcf_meta_terms(train_batch[ADVANTAGES], train_batch[NEI_ADVANTAGE], eps, mean,
                                                          std))
-        world = self.dist.get_world_size() if (self.dist is not None and self.dist.is_initialized()) else 1
+        world = self.dist.get_world_size() if parallel.active(self.dist) else 1
         terms = terms / (B * world)
         coordinated_mean = terms[0]
         lcf_adv_loss = (coordinated_mean - self._raw_lcf_adv_mean) / self._raw_lcf_adv_std
@@ -353,6 +352,7 @@ class CoPOPolicy(CCPPOPolicy):
 
     def update_old_policy(self):
         self.target_model.flat.copy_(self.model.flat)
+        self.target_model.mark_weights_changed()
         self.target_model.lcf_parameters.copy_(self.model.lcf_parameters)
 
     def assign_lcf(self, lcf_parameters, lcf_mean, lcf_std=None, my_name=None):

@@ -18,6 +18,7 @@ import time
 import torch
 
 from . import ops
+from . import parallel
 from . import policy as P
 from .batched_env import (BatchedDrivingEnv, FLAG_ARRIVE, FLAG_CRASH, FLAG_DONE, FLAG_MAXSTEP, FLAG_OUT, FLAG_VALID,
                           MAP_OF_ENV)
@@ -61,7 +62,7 @@ class IPPOTrainer:
             append_lcf = self.policy_cls.algo == "copo"
             env = BatchedDrivingEnv(map_name, num_scenes=S, num_agents=ec.get("num_agents"),
                                     num_slots=ec.get("num_agents"), seed=int(ec.get("start_seed", cfg.get("seed", 0))),
-                                    scene_offset=self.rank * S, append_lcf=append_lcf,
+                                    scene_offset=parallel.scene_offset(self.rank, S), append_lcf=append_lcf,
                                     neighbours_distance=ec.get("neighbours_distance", 40.0),
                                     mf_nei_distance=cfg.get("mf_nei_distance", 10.0),
                                     lcf_std=ec.get("lcf_normal_std", 0.1), horizon=ec.get("horizon", 1000),
@@ -134,22 +135,14 @@ class IPPOTrainer:
         return cols, scal, wide, valid
 
     def _num_minibatches(self, n_valid, mb):
-        k = max(1, math.ceil(n_valid / mb))
-        if self.world > 1:
-            t = torch.tensor([k], device=self.device)
-            _dist().all_reduce(t, op=_dist().ReduceOp.MAX)
-            k = int(t)
-        return k
+        return parallel.num_minibatches(n_valid, mb, _dist(), self.device)
 
     def _minibatches(self, cols, scal, wide, valid, mb):
         """Shuffled minibatches over the valid rows (rllib.utils.sgd.minibatches)."""
         k = self._num_minibatches(valid.numel(), mb)
         perm = valid[torch.randperm(valid.numel(), device=self.device)]
-        size = math.ceil(valid.numel() / k)
-        for j in range(k):
-            idx = perm[j * size:(j + 1) * size].contiguous()
-            if idx.numel() == 0:
-                idx = perm[:1].contiguous()
+        for lo, hi in parallel.minibatch_bounds(valid.numel(), k):
+            idx = perm[lo:hi].contiguous()
             batch = {c: ops.gather_rows(w, idx) for c, w in wide.items()}
             if P.CENTRALIZED_CRITIC_OBS not in batch:
                 batch[P.CENTRALIZED_CRITIC_OBS] = batch[P.OBS]

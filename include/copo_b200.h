@@ -187,10 +187,11 @@ int b2c_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
 int b2c_dot(const float* a, const float* b, size_t n, double* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
- * tcgen05 tensor-core path for the 256-wide layers ("bf16x3": fp32 operands split into bf16 hi + lo, products
- * hi*hi + lo*hi + hi*lo accumulated in fp32 in TMEM).  Same layers as b2c_linear_forward / _backward_input.
+ * tcgen05 tensor-core path for the 256-wide layers ("split bf16": fp32 operands split into bf16 hi + lo, the four
+ * products hi*hi + lo*hi + hi*lo + lo*lo accumulated in fp32 in TMEM).  Same layers as b2c_linear_forward /
+ * b2c_linear_backward_input.
  *   a_split  [M][2*Kp] bf16: hi in columns [0, Kp), lo in [Kp, 2Kp), Kp = b2c_tc_padded_k(K), zero padded
- *   w_prep   [256][3*Kp] bf16: [hi | hi | lo] of W (forward) or of W^T (input gradient)
+ *   w_prep   [256][2*Kp] bf16: [hi | lo] of W (forward) or of W^T (input gradient)
  * ------------------------------------------------------------------------------------------------- */
 int b2c_tc_padded_k(int K);
 int b2c_tc_split_rows(const float* x, int ldx, uint16_t* out, int M, int K, int Kp, void* stream);

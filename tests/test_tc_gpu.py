@@ -1,4 +1,4 @@
-"""tcgen05 path of the 256-wide layers against float64 references: split-bf16 ("bf16x3") accuracy must be far inside
+"""tcgen05 path of the 256-wide layers against float64 references: split-bf16 accuracy must be far inside
 the 1e-4 budget of the value predictions; covers ragged M (tile tails), every padded K the nets use, the input-gradient
 form and the chained [hi | lo] operand hand-over between layers."""
 import numpy as np
@@ -65,3 +65,19 @@ def test_tc_input_gradient():
     wt = ops.tc_prep_weight(W.cuda(), transpose=True)
     dx, _ = ops.tc_linear(a, wt, None, act=0, dtanh_src=h.cuda())
     assert float((dx.cpu().double() - want).abs().max()) < 1e-4 * float(want.abs().max())
+
+
+def test_tc_tanh_is_accurate_near_zero():
+    """The epilogue's tanh keeps relative accuracy for tiny pre-activations (identity weights, scaled inputs); what is
+    left is the 2^-17 relative rounding of the [hi | lo] operand split."""
+    from copo_b200 import ops
+    M = 512
+    x = torch.zeros(M, 256)
+    vals = torch.logspace(-6, 1, M)
+    for j in range(256):
+        x[:, j] = vals * (1 if j % 2 == 0 else -1)
+    W = torch.eye(256)
+    y, _ = ops.tc_linear(ops.tc_split_rows(x.cuda()), ops.tc_prep_weight(W.cuda()), None, act=1)
+    want = torch.tanh(x.double())
+    rel = ((y.cpu().double() - want).abs() / want.abs()).max()
+    assert float(rel) < 2e-5, float(rel)
