@@ -173,6 +173,7 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("B2C_NCCL_DEBUG", "WARN")    # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     S, A = args.scenes, SLOTS
     N = S * A

@@ -198,11 +198,21 @@ int b2c_linear_backward_weight(const float* dy, int ldy, const float* x, int ldx
     sgemm_kernel<true, false, EPI_ATOMIC><<<grid, NTHREADS, 0, s>>>(dy, ldy, x, ldx, dW, K, N, K, M, nullptr, nullptr, 0, chunk);
     B2C_CUDA(cudaGetLastError());
     if (db) {
-        int rows = 4096;
+        int rows = 128;                                  // many short CTAs: the sum is bandwidth-bound
         dim3 g2((N + 127) / 128, (M + rows - 1) / rows);
         colsum_kernel<<<g2, 128, 0, s>>>(dy, ldy, db, M, N, rows);
         B2C_CUDA(cudaGetLastError());
     }
+    return B2C_OK;
+}
+
+int b2c_colsum(const float* dy, int ldy, float* db, int M, int N, void* stream) {
+    if (!dy || !db || M < 0 || N < 1) return b2c_set_error(B2C_ERR_ARG, "b2c_colsum: bad argument");
+    if (M == 0) return B2C_OK;
+    int rows = 128;
+    dim3 g2((N + 127) / 128, (M + rows - 1) / rows);
+    colsum_kernel<<<g2, 128, 0, (cudaStream_t)stream>>>(dy, ldy, db, M, N, rows);
+    B2C_CUDA(cudaGetLastError());
     return B2C_OK;
 }
 

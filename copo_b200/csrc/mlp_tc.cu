@@ -324,6 +324,165 @@ __global__ void prep_weight_kernel(const float* __restrict__ W, uint16_t* __rest
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Weight gradient on the tensor cores:  dW[256 x K] += dz^T[256 x M] * x[M x K]   (reduction over the batch rows)
+//
+// Both operands are "MN-major" for this product (the reduction index m is the slow one in memory), so the same
+// [hi | lo] row tensors the forward pass made are read again, now through 64-column x 32-row TMA boxes: a box is
+// exactly one SWIZZLE_128B MN-major atom stack (32 reduction rows of 128 B).  Each CTA owns a contiguous slice of
+// rows, accumulates its 256 x Kp partial in TMEM (2 halves of 128 output rows x Kp columns) over the whole slice and
+// writes it to a workspace; a second kernel adds the partials into dW in a fixed order (deterministic).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int WG_ROWS = 32;                                // reduction rows per stage
+constexpr int WG_BOX_BYTES = WG_ROWS * 128;                // one 64-column box: 4 KB
+constexpr int WG_OPERAND_BYTES = 4 * WG_BOX_BYTES;         // up to 256 columns per operand half: 16 KB
+constexpr int WG_STAGE_BYTES = 4 * WG_OPERAND_BYTES;       // dz_hi, dz_lo, x_hi, x_lo: 64 KB
+constexpr int WG_STAGES = 3;
+constexpr int WG_SMEM_BYTES = WG_STAGES * WG_STAGE_BYTES + 1024 + 256;
+
+// MN-major SWIZZLE_128B descriptor: LBO = byte distance between 64-element atoms along M/N (one box), SBO = byte
+// distance between 8-row groups along the reduction (1024 B)
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)(WG_BOX_BYTES >> 4) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+struct WgradArgs {
+    float* partial;        // [gridDim.x][256][kp]
+    int M, kp, rows_per_cta;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_constant__ CUtensorMap map_x,
+                const __grid_constant__ WgradArgs args) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES);
+    uint64_t* empty = full + WG_STAGES;
+    uint64_t* done = empty + WG_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kp = args.kp, n_xbox = kp / 64;
+    const int row0 = blockIdx.x * args.rows_per_cta;
+    int rows = args.M - row0;
+    rows = rows > args.rows_per_cta ? args.rows_per_cta : rows;
+    const int num_kb = rows > 0 ? (rows + WG_ROWS - 1) / WG_ROWS : 0;
+    // instruction descriptor: D f32, A = B = bf16, A and B MN-major (bits 15, 16), N = kp, M = 128
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                           ((uint32_t)(kp >> 3) << 17) | ((128u >> 4) << 24);
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_dz) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < WG_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t stage_tx = (uint32_t)(2 * WG_OPERAND_BYTES + 2 * n_xbox * WG_BOX_BYTES);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&empty[stage], phase ^ 1u);
+                uint8_t* st = smem + stage * WG_STAGE_BYTES;
+                mbar_expect_tx(&full[stage], stage_tx);
+                const int r = row0 + kb * WG_ROWS;
+                for (int b = 0; b < 4; ++b) {
+                    tma_load_2d(st + b * WG_BOX_BYTES, &map_dz, b * 64, r, &full[stage]);                          // dz_hi
+                    tma_load_2d(st + WG_OPERAND_BYTES + b * WG_BOX_BYTES, &map_dz, 256 + b * 64, r, &full[stage]);  // dz_lo
+                }
+                for (int b = 0; b < n_xbox; ++b) {
+                    tma_load_2d(st + 2 * WG_OPERAND_BYTES + b * WG_BOX_BYTES, &map_x, b * 64, r, &full[stage]);     // x_hi
+                    tma_load_2d(st + 3 * WG_OPERAND_BYTES + b * WG_BOX_BYTES, &map_x, kp + b * 64, r, &full[stage]);
+                }
+                if (++stage == WG_STAGES) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + stage * WG_STAGE_BYTES);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {                    // output rows 128 h .. 128 h + 127 (two 64-wide atoms)
+                    const uint64_t dz_hi = make_desc_mn(sa + h * 2 * WG_BOX_BYTES);
+                    const uint64_t dz_lo = make_desc_mn(sa + WG_OPERAND_BYTES + h * 2 * WG_BOX_BYTES);
+                    const uint64_t x_hi = make_desc_mn(sa + 2 * WG_OPERAND_BYTES);
+                    const uint64_t x_lo = make_desc_mn(sa + 3 * WG_OPERAND_BYTES);
+                    const uint32_t tmem_d = tmem_base + (uint32_t)(h * 256);
+#pragma unroll
+                    for (int k = 0; k < WG_ROWS / UMMA_K; ++k) {
+                        const uint64_t o = (uint64_t)((k * UMMA_K * 128) >> 4);      // 16 reduction rows = 2048 B
+                        umma_bf16(tmem_d, dz_hi + o, x_hi + o, idesc, (kb | k) ? 1u : 0u);
+                        umma_bf16(tmem_d, dz_lo + o, x_hi + o, idesc, 1u);
+                        umma_bf16(tmem_d, dz_hi + o, x_lo + o, idesc, 1u);
+                        umma_bf16(tmem_d, dz_lo + o, x_lo + o, idesc, 1u);
+                    }
+                }
+                umma_commit(&empty[stage]);
+                if (kb == num_kb - 1) umma_commit(done);
+                if (++stage == WG_STAGES) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp >= 4) {
+        const int q = warp & 3, h = (warp - 4) >> 2;
+        const int out_row = h * 128 + q * 32 + lane;
+        float* dst = args.partial + ((size_t)blockIdx.x * 256 + out_row) * kp;
+        if (num_kb > 0) {
+            mbar_wait(done, 0);
+            tc_fence_after();
+            const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 256);
+            for (int c = 0; c < kp / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld32(taddr0 + (uint32_t)(c * 32), r);
+                float4* o = reinterpret_cast<float4*>(dst + c * 32);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    o[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                       __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+            }
+        } else {
+            for (int c = 0; c < kp / 4; ++c) reinterpret_cast<float4*>(dst)[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+// dW[n][k] += sum_c partial[c][n][k]  (k < K), fixed summation order
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dW, int parts, int kp, int K) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 256 * K) return;
+    int n = idx / K, k = idx - n * K;
+    float s = 0.0f;
+    for (int c = 0; c < parts; ++c) s += partial[((size_t)c * 256 + n) * kp + k];
+    dW[idx] += s;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -341,6 +500,7 @@ static EncodeTiledFn encode_fn() {
 }
 
 // bf16 row-major [rows][cols] matrix, box = 64 columns x box_rows rows, 128-byte swizzle
+// (K-major operand tiles use tall boxes; the MN-major tiles of the weight gradient use 32-row boxes)
 static int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return b2c_set_error(B2C_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
@@ -412,6 +572,42 @@ int b2c_tc_linear(const uint16_t* a_split, const uint16_t* w_prep, const float* 
     int tiles = (M + BLOCK_M - 1) / BLOCK_M;
     int grid = tiles < num_sms ? tiles : num_sms;
     tc_linear_kernel<<<grid, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(map_a, map_w, a);
+    B2C_CUDA(cudaGetLastError());
+    return B2C_OK;
+}
+
+int b2c_tc_wgrad_parts(void) {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+        return -1;
+    return sms;
+}
+
+int b2c_tc_wgrad(const uint16_t* dz_split, const uint16_t* x_split, float* workspace, float* dW, int M, int K, int Kp,
+                 void* stream) {
+    if (!dz_split || !x_split || !workspace || !dW || Kp < BLOCK_K || Kp > 256 || Kp % BLOCK_K || K > Kp || M < 0)
+        return b2c_set_error(B2C_ERR_ARG, "b2c_tc_wgrad: bad argument (Kp must be 64..256)");
+    if (M == 0) return B2C_OK;
+    static int attr_set = 0;
+    static int num_sms = 0;
+    if (!attr_set) {
+        B2C_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES));
+        num_sms = b2c_tc_wgrad_parts();
+        attr_set = 1;
+    }
+    CUtensorMap map_dz, map_x;
+    int rc = make_map(&map_dz, dz_split, (uint64_t)M, 512, WG_ROWS);
+    if (rc) return rc;
+    rc = make_map(&map_x, x_split, (uint64_t)M, (uint64_t)2 * Kp, WG_ROWS);
+    if (rc) return rc;
+    WgradArgs a;
+    a.partial = workspace; a.M = M; a.kp = Kp;
+    int per = (M + num_sms - 1) / num_sms;
+    a.rows_per_cta = (per + WG_ROWS - 1) / WG_ROWS * WG_ROWS;
+    cudaStream_t s = (cudaStream_t)stream;
+    tc_wgrad_kernel<<<num_sms, NUM_THREADS, WG_SMEM_BYTES, s>>>(map_dz, map_x, a);
+    B2C_CUDA(cudaGetLastError());
+    wgrad_reduce_kernel<<<(256 * K + 255) / 256, 256, 0, s>>>(workspace, dW, num_sms, Kp, K);
     B2C_CUDA(cudaGetLastError());
     return B2C_OK;
 }

@@ -89,9 +89,11 @@ class _Net:
     def forward_train(self, x, tc_version=None):
         if tc_version is not None and self.tc_ok():
             w1, w2, _ = self.tc_weights(tc_version)
-            h1, s1 = ops.tc_linear(ops.tc_split_rows(x), w1, self.b[0], act=1, want_f32=True, want_split=True)
+            s0 = ops.tc_split_rows(x)
+            h1, s1 = ops.tc_linear(s0, w1, self.b[0], act=1, want_f32=True, want_split=True)
             h2, _ = ops.tc_linear(s1, w2, self.b[1], act=1)
-            return [x, h1, h2, ops.linear_forward(h2, self.W[2], self.b[2], 0)]
+            # the [hi | lo] operands are kept: the weight gradients read them again
+            return [x, h1, h2, ops.linear_forward(h2, self.W[2], self.b[2], 0), s0, s1]
         acts = [x]
         for k in range(len(self.shapes)):
             last = k == len(self.shapes) - 1
@@ -101,12 +103,18 @@ class _Net:
     def backward(self, acts, dout, tc_version=None):
         """Accumulates dW / db of every layer given d(loss)/d(out)."""
         if tc_version is not None and self.tc_ok():
-            x, h1, h2, _ = acts
+            x, h1, h2, _, s0, s1 = acts
             dz2 = ops.linear_backward(dout, h2, self.W[2], self.dW[2], self.db[2], h_prev_is_tanh=True)
-            # input gradient of layer 2 on the tensor cores, weight gradients on the fp32 path
-            dz1, _ = ops.tc_linear(ops.tc_split_rows(dz2), self.tc_weights(tc_version)[2], None, act=0, dtanh_src=h1)
-            ops.linear_backward(dz2, h1, self.W[1], self.dW[1], self.db[1], h_prev_is_tanh=True, need_dx=False)
-            ops.linear_backward(dz1, x, self.W[0], self.dW[0], self.db[0], h_prev_is_tanh=False, need_dx=False)
+            # layer 2: input gradient and weight gradient on the tensor cores from the same [hi | lo] operand
+            dz2s = ops.tc_split_rows(dz2)
+            dz1, dz1s = ops.tc_linear(dz2s, self.tc_weights(tc_version)[2], None, act=0, dtanh_src=h1, want_split=True)
+            ops.tc_wgrad(dz2s, s1, self.dW[1])
+            ops.colsum(dz2, self.db[1])
+            if s0.shape[1] <= 512:
+                ops.tc_wgrad(dz1s, s0, self.dW[0])
+                ops.colsum(dz1, self.db[0])
+            else:                                    # very wide critic inputs (concat fusion): fp32 path
+                ops.linear_backward(dz1, x, self.W[0], self.dW[0], self.db[0], h_prev_is_tanh=False, need_dx=False)
             return
         d = dout
         for k in reversed(range(len(self.shapes))):

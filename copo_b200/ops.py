@@ -270,3 +270,29 @@ def tc_linear(a_split, w_prep, bias=None, act=0, want_f32=True, want_split=False
                                  c_int(out_f32.stride(0) if out_f32 is not None else 0), P(out_split), c_int(M), c_int(Kp),
                                  c_int(act), _lib.stream_ptr()))
     return out_f32, out_split
+
+
+_WGRAD_WS = {}
+
+
+def tc_wgrad(dz_split, x_split, dW):
+    """dW[256, K] += dz^T x on the tensor cores from the [hi | lo] operands (dz_split [M, 512], x_split [M, 2*Kp])."""
+    lib = _lib_ready()
+    M = dz_split.shape[0]
+    Kp = x_split.shape[1] // 2
+    K = dW.shape[1]
+    assert dz_split.shape == (M, 512) and x_split.shape[0] == M and dW.shape[0] == 256 and dW.is_contiguous()
+    key = (dz_split.device, Kp)
+    if key not in _WGRAD_WS:
+        parts = lib.b2c_tc_wgrad_parts()
+        _WGRAD_WS[key] = torch.empty(parts * 256 * Kp, dtype=torch.float32, device=dz_split.device)
+    _lib.check(lib.b2c_tc_wgrad(P(dz_split), P(x_split), P(_WGRAD_WS[key]), P(dW), c_int(M), c_int(K), c_int(Kp),
+                                _lib.stream_ptr()))
+    return dW
+
+
+def colsum(dy, db):
+    lib = _lib_ready()
+    pdy, M, N, ldy = _rows2d(dy)
+    _lib.check(lib.b2c_colsum(pdy, c_int(ldy), P(db), c_int(M), c_int(N), _lib.stream_ptr()))
+    return db

@@ -132,8 +132,8 @@ class IPPOPolicy:
         for net_name, in_col, old_col, tgt_col in self._heads(train_batch):
             acts = model.nets[net_name].forward_train(train_batch[in_col], tc)
             head_acts.append((net_name, acts))
-            heads.append((acts[-1].reshape(-1), train_batch[old_col], train_batch[tgt_col]))
-        dlogits, dvs, st = ops.ppo_head(acts_p[-1], train_batch[ACTIONS], train_batch[ACTION_LOGP],
+            heads.append((acts[3].reshape(-1), train_batch[old_col], train_batch[tgt_col]))
+        dlogits, dvs, st = ops.ppo_head(acts_p[3], train_batch[ACTIONS], train_batch[ACTION_LOGP],
                                         train_batch[ACTION_DIST_INPUTS], train_batch[self._adv_column()], heads, cfg)
         pol.backward(acts_p, dlogits, tc)
         for (net_name, acts), dv in zip(head_acts, dvs):
@@ -314,7 +314,7 @@ class CoPOPolicy(CCPPOPolicy):
         pol = model.nets["policy"]
         acts = pol.forward_train(batch[OBS], model._tc())
         model.grad[model.policy_slice()].zero_()
-        dlogits, _, st = ops.ppo_head(acts[-1], batch[ACTIONS], batch[ACTION_LOGP], None, adv, [], cfg, mode=mode)
+        dlogits, _, st = ops.ppo_head(acts[3], batch[ACTIONS], batch[ACTION_LOGP], None, adv, [], cfg, mode=mode)
         pol.backward(acts, dlogits, model._tc())
         g = model.grad[model.policy_slice()].clone()
         parallel.allreduce_mean_(g, self.dist)           # reduce the gradient vectors BEFORE the dot (bilinear)
@@ -329,10 +329,11 @@ class CoPOPolicy(CCPPOPolicy):
             eps = torch.randn(B, dtype=torch.float32, device=self.device)
         mean_t, std_t = self.model.lcf_mean, self.model.lcf_std
         mean, std = float(mean_t), float(std_t)
-        terms = self._allreduce_stats(ops.lcf_meta_terms(train_batch[ADVANTAGES], train_batch[NEI_ADVANTAGE], eps, mean,
-                                                         std))
-        world = self.dist.get_world_size() if parallel.active(self.dist) else 1
-        terms = terms / (B * world)
+        terms = ops.lcf_meta_terms(train_batch[ADVANTAGES], train_batch[NEI_ADVANTAGE], eps, mean, std)
+        # ranks can hold minibatches of different sizes: reduce the sums together with the row count
+        terms = self._allreduce_stats(torch.cat([terms, torch.tensor([float(B)], dtype=torch.float64,
+                                                                      device=self.device)]))
+        terms = terms[:3] / terms[3]
         coordinated_mean = terms[0]
         lcf_adv_loss = (coordinated_mean - self._raw_lcf_adv_mean) / self._raw_lcf_adv_std
         p = self.model.lcf_parameters

@@ -107,6 +107,8 @@ int b2c_linear_backward_input(const float* dy, int ldy, const float* W, const fl
 /* dW[N][K] += dy^T x, db[N] += column sums of dy (db may be NULL).  Accumulates: zero dW / db first. */
 int b2c_linear_backward_weight(const float* dy, int ldy, const float* x, int ldx, float* dW, float* db, int M, int K,
                                int N, void* stream);
+/* db[N] += column sums of dy[M][N] (bias gradient on its own) */
+int b2c_colsum(const float* dy, int ldy, float* db, int M, int N, void* stream);
 /* narrow output layers (logits: N = 4, value: N = 1), N <= 8 */
 int b2c_head_forward(const float* h, int ldh, const float* W, const float* b, float* y, int ldy, int M, int K, int N,
                      void* stream);
@@ -199,6 +201,12 @@ int b2c_tc_split_rows(const float* x, int ldx, uint16_t* out, int M, int K, int 
 int b2c_tc_prep_weight(const float* W, uint16_t* out, int N, int K, int Kp, int transpose, void* stream);
 /* out = epilogue(a W'^T): + bias, tanh (act = 1), * (1 - dtanh_src^2); writes fp32 [M][ld_out] and / or the
  * [hi | lo] bf16 operand of the next layer [M][512].  Output width is 256. */
+/* Weight gradient of a 256-wide layer on the tensor cores: dW[256][K] += dz^T x from the [hi | lo] operands
+ * (dz_split [M][512], x_split [M][2*Kp], Kp <= 256).  workspace: b2c_tc_wgrad_parts() * 256 * Kp floats; the
+ * per-CTA partial sums are added in a fixed order (deterministic). */
+int b2c_tc_wgrad_parts(void);
+int b2c_tc_wgrad(const uint16_t* dz_split, const uint16_t* x_split, float* workspace, float* dW, int M, int K, int Kp,
+                 void* stream);
 int b2c_tc_linear(const uint16_t* a_split, const uint16_t* w_prep, const float* bias, const float* dtanh_src, int ld_src,
                   float* out_f32, int ld_out, uint16_t* out_split, int M, int Kp, int act, void* stream);
 

@@ -81,3 +81,20 @@ def test_tc_tanh_is_accurate_near_zero():
     want = torch.tanh(x.double())
     rel = ((y.cpu().double() - want).abs() / want.abs()).max()
     assert float(rel) < 2e-5, float(rel)
+
+
+@pytest.mark.parametrize("M,K", [(4096, 256), (1000, 92), (148 * 32 * 3 + 17, 157), (65536, 256), (31, 64)])
+def test_tc_weight_gradient(M, K):
+    from copo_b200 import ops
+    g = torch.Generator().manual_seed(M + K)
+    dz = torch.randn(M, 256, generator=g) * 0.1
+    x = torch.tanh(torch.randn(M, K, generator=g))
+    want = dz.double().T @ x.double()
+    dW = torch.full((256, K), 0.5, device="cuda")          # accumulates on top of what is there
+    ops.tc_wgrad(ops.tc_split_rows(dz.cuda()), ops.tc_split_rows(x.cuda()), dW)
+    got = dW.cpu().double() - 0.5
+    scale = float(want.abs().max())
+    assert float((got - want).abs().max()) < 1e-4 * scale + 1e-5, float((got - want).abs().max()) / scale
+    dW2 = torch.full((256, K), 0.5, device="cuda")
+    ops.tc_wgrad(ops.tc_split_rows(dz.cuda()), ops.tc_split_rows(x.cuda()), dW2)
+    assert torch.equal(dW, dW2)                            # fixed summation order: bitwise reproducible
