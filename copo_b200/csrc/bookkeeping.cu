@@ -80,10 +80,16 @@ __global__ void lcf_mix_stats_kernel(const uint8_t* __restrict__ flags, const fl
         s += x; s2 += (double)x * x; c += 1.0;
         if (gadv) { float y = gadv[i]; g += y; g2 += (double)y * y; }
     }
+    // warp -> CTA -> one atomic per CTA and statistic (float64 atomics to five addresses are the serial part)
+    __shared__ double red[5][8];
     s = warp_sum_d(s); s2 = warp_sum_d(s2); c = warp_sum_d(c); g = warp_sum_d(g); g2 = warp_sum_d(g2);
-    if ((threadIdx.x & 31) == 0) {
-        atomicAdd(&out[0], s); atomicAdd(&out[1], s2); atomicAdd(&out[2], c);
-        atomicAdd(&out[3], g); atomicAdd(&out[4], g2);
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { red[0][w] = s; red[1][w] = s2; red[2][w] = c; red[3][w] = g; red[4][w] = g2; }
+    __syncthreads();
+    if (threadIdx.x < 5) {
+        double t = 0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += red[threadIdx.x][k];
+        atomicAdd(&out[threadIdx.x], t);
     }
 }
 
