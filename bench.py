@@ -189,8 +189,10 @@ def run_gpu(args):
         o = env.alloc_outputs()
         o["obs"] = obs[r + 1].view(S, A, D)
         outs.append(o)
-    logits = torch.zeros((RING, N, 4), device=dev)
-    env.reset()
+    split = [env.alloc_obs_split() for _ in range(2)]      # the policy's [hi | lo] operand, written by the env
+    first = dict(env.out)
+    first["obs_split"] = split[0]
+    env.reset(out=first)
     obs[0].copy_(env.out["obs"].reshape(N, D))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream()
@@ -201,8 +203,9 @@ def run_gpu(args):
         t = state["t"]
         r = t % RING
         src = obs[r] if r or t == 0 else obs[RING]
-        lg = pol.model.forward(src)
+        lg = pol.model.forward(src, obs_split=split[t % 2].view(N, -1))
         actions, logp = ops.gaussian_sample(lg, seed=args.seed + rank * 7919, step=t)
+        outs[r]["obs_split"] = split[(t + 1) % 2]
         env.step(actions.view(S, A, 2), out=outs[r])
         state["t"] = t + 1
 
@@ -249,6 +252,7 @@ def run_gpu(args):
         return float(np.median(ms))
 
     act_buf = torch.rand((S, A, 2), device=dev) * 2 - 1
+    outs[0]['obs_split'] = split[0]
     env_ms = time_kernel(lambda: env.step(act_buf, out=outs[0]))
     net = pol.model.nets["policy"]
     w1, w2, _ = net.tc_weights(pol.model.weights_version)
@@ -298,7 +302,8 @@ def run_gpu(args):
     hbm_peak, peak_src = _peaks()
     tc_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"] if os.path.exists(
         os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1590.0
-    algo_bytes = N * (4 * D + 153)                   # SURVEY.md 8d / DESIGN.md: per agent slot 4*D + 153 bytes
+    # SURVEY.md 8d / DESIGN.md: per agent slot 4*D + 153 bytes, + the bf16 [hi | lo] policy operand (2 * Kp * 2 B)
+    algo_bytes = N * (4 * D + 153 + 2 * env.split_width)
     env_gbs = algo_bytes / (env_ms * 1e-3) / 1e9
     l2_flops = 2.0 * N * 256 * 256                   # algorithmic fp32-equivalent flops of the 256x256 layer
     l2_tf = l2_flops / (l2_ms * 1e-3) / 1e12

@@ -27,7 +27,7 @@ class EnvConfig(ctypes.Structure):
 
 
 ENV_IO_FIELDS = ("obs", "reward", "flags", "nei_mask", "mf_mask", "nei_reward", "global_reward", "nei_list",
-                 "agent_id", "lcf", "scene_done")
+                 "agent_id", "lcf", "scene_done", "obs_split")
 
 
 class EnvIO(ctypes.Structure):

@@ -51,6 +51,7 @@ class BatchedDrivingEnv:
                                                int(blob.size), ctypes.byref(self._h)))
         self.D = int(self.lib.b2c_env_obs_dim(self._h))
         self.tile_words = int(self.lib.b2c_env_state_words(self._h))
+        self.split_width = int(self.lib.b2c_env_obs_split_width(self._h))
         self.num_agents = int(num_agents)
         self.lcf_mean, self.lcf_std, self.force_lcf = float(lcf_mean), float(lcf_std), float(force_lcf)
         self.out = self.alloc_outputs()
@@ -64,6 +65,10 @@ class BatchedDrivingEnv:
                     nei_reward=z((S, A), torch.float32), global_reward=z((S,), torch.float32),
                     nei_list=z((S, A, 4), torch.int8), agent_id=z((S, A), torch.int32), lcf=z((S, A), torch.float32),
                     scene_done=z((S,), torch.uint8))
+
+    def alloc_obs_split(self):
+        """[S, A, 2*Kp] bf16 buffer for the optional `obs_split` output (the policy's tensor-core operand)."""
+        return torch.zeros((self.S, self.A, self.split_width), dtype=torch.bfloat16, device=self.device)
 
     def _io(self, out):
         return _lib.EnvIO(*[_lib.ptr(out.get(k)) for k in _lib.ENV_IO_FIELDS])

@@ -10,6 +10,7 @@
 // Replaces: MetaDrive env.step (reference call site env_wrappers.py:95), CCEnv._update_distance_map /
 // _find_in_range (env_wrappers.py:125-158), LCFEnv.step reward bookkeeping (env_wrappers.py:313-357) and
 // LCFEnv._add_lcf (env_wrappers.py:393-418).  Build with -fmad=false (bit-exact spec, oracle/sim.py).
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -33,6 +34,8 @@ struct EnvIO {
     int32_t* agent_id;
     float* lcf;
     uint8_t* scene_done;
+    uint32_t* obs_split;   // [S][A][kp] bf16 pairs: the policy's tensor-core operand ([hi | lo], mlp_tc.cu), or null
+    int kp;                // padded observation width (multiple of 64)
     int map_words;
     int tile_words;
     int obs_bulk;   // 1 when the obs tiles can leave through a bulk store (16-byte aligned base)
@@ -74,12 +77,13 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 
 static constexpr int ENV_MAX_THREADS = 256;
 static constexpr int ENV_MAX_GROUP = 16;      // scene tag in a queue entry is 4 bits
+static constexpr int GEOM_WORDS = 10;         // nx1 nx2 ny1 ny2 cc ss | k0 cnt excl lid_off
 
 // Shared-memory plan of one CTA working on `G` scenes at a time (offsets in bytes, every region 16-byte aligned).
 struct SmemPlan {
-    int map, st, obs, f, i, need, masks, queue, total;
+    int map, st, obs, f, i, need, masks, queue, geom, total;
 };
-__host__ __device__ inline SmemPlan smem_plan(int G, int A, int D, int map_words, int tile_words) {
+__host__ __device__ inline SmemPlan smem_plan(int G, int A, int D, int map_words, int tile_words, int n_warps) {
     SmemPlan p;
     int o = 16;                                          // mbarrier
     p.map = o;   o += map_words * 4;
@@ -90,6 +94,7 @@ __host__ __device__ inline SmemPlan smem_plan(int G, int A, int D, int map_words
     p.need = o;  o += ((2 * G + 4 + 3) & ~3) * 4;        // need[G], scene_done[G], queue fill
     p.masks = o; o += G * 2 * 8;                         // per scene: participant / present slot masks
     p.queue = o; o += ((G * A * A + 7) & ~7) * 2;
+    p.geom = o;  (void)n_warps;
     p.total = o;
     return p;
 }
@@ -99,7 +104,7 @@ env_step_kernel(const __grid_constant__ EnvConfig cfg, const __grid_constant__ E
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int A = cfg.A, AP = cfg.AP, D = cfg.D, G = io.group;
     const int tid = threadIdx.x, NT = blockDim.x;
-    const SmemPlan pl = smem_plan(G, A, D, io.map_words, io.tile_words);
+    const SmemPlan pl = smem_plan(G, A, D, io.map_words, io.tile_words, (int)(blockDim.x >> 5));
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     uint32_t* s_map = reinterpret_cast<uint32_t*>(smem_raw + pl.map);
     uint32_t* s_st = reinterpret_cast<uint32_t*>(smem_raw + pl.st);
@@ -294,6 +299,22 @@ env_step_kernel(const __grid_constant__ EnvConfig cfg, const __grid_constant__ E
         if (!obs_bulk) {
             for (int idx = tid; idx < ng * A * D; idx += NT) g_obs[idx] = s_obs[idx];
         }
+        if (io.obs_split) {
+            // the same observations as the [hi | lo] bf16 operand of the policy's first layer (two columns per item)
+            const int half = io.kp >> 1;
+            uint32_t* g_sp = io.obs_split + (size_t)scene0 * A * io.kp;
+            for (int idx = tid; idx < ng * A * half; idx += NT) {
+                int row = idx / half, c2 = idx - row * half;
+                int k = 2 * c2;
+                float v0 = (k < D) ? s_obs[row * D + k] : 0.0f;
+                float v1 = (k + 1 < D) ? s_obs[row * D + k + 1] : 0.0f;
+                __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+                __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0));
+                __nv_bfloat16 l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
+                g_sp[(size_t)row * io.kp + c2] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                g_sp[(size_t)row * io.kp + half + c2] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            }
+        }
     }
     if (tid == 0) bulk_wait_read0();
 }
@@ -355,12 +376,12 @@ int b2c_env_create(const b2c_env_config* c, const uint32_t* map_blob, int map_wo
     if (fit > k.S) fit = k.S;
     if (fit < 1) { delete e; return b2c_set_error(B2C_ERR_ARG, "num_slots does not fit one CTA"); }
     e->group = fit;
-    while (e->group > 1 && smem_plan(e->group, k.A, k.D, map_words, e->tile_words).total > 56 * 1024) e->group -= 1;
+    while (e->group > 1 && smem_plan(e->group, k.A, k.D, map_words, e->tile_words, e->threads / 32).total > 56 * 1024) e->group -= 1;
     if (const char* g = getenv("B2C_ENV_GROUP")) {
         int gg = atoi(g);
         if (gg >= 1 && gg <= fit) e->group = gg;
     }
-    e->smem = (size_t)smem_plan(e->group, k.A, k.D, map_words, e->tile_words).total;
+    e->smem = (size_t)smem_plan(e->group, k.A, k.D, map_words, e->tile_words, e->threads / 32).total;
     B2C_CUDA_OR(cudaFuncSetAttribute(env_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem),
                 delete e);
     B2C_CUDA_OR(cudaMalloc(&e->d_map, (size_t)map_words * 4), delete e);
@@ -391,6 +412,7 @@ static int launch_env(b2c_env* e, const float* actions, const b2c_env_io* o, int
     io.flags = o->flags; io.nei_mask = (unsigned long long*)o->nei_mask; io.mf_mask = (unsigned long long*)o->mf_mask;
     io.nei_reward = o->nei_reward; io.global_reward = o->global_reward; io.nei_list = o->nei_list;
     io.agent_id = o->agent_id; io.lcf = o->lcf; io.scene_done = o->scene_done;
+    io.obs_split = (uint32_t*)o->obs_split; io.kp = (cfg.D + 63) / 64 * 64;
     io.map_words = e->map_words; io.tile_words = e->tile_words;
     io.obs_bulk = ((((size_t)cfg.A * cfg.D * 4) % 16 == 0) && (((uintptr_t)o->obs) % 16 == 0)) ? 1 : 0;
     io.group = e->group;
@@ -431,6 +453,7 @@ int b2c_env_set_num_agents(b2c_env* e, int n) {
     return B2C_OK;
 }
 int b2c_env_obs_dim(const b2c_env* e) { return e ? e->cfg.D : -1; }
+int b2c_env_obs_split_width(const b2c_env* e) { return e ? 2 * ((e->cfg.D + 63) / 64 * 64) : -1; }
 int b2c_env_state_words(const b2c_env* e) { return e ? e->tile_words : -1; }
 int b2c_env_slots_padded(const b2c_env* e) { return e ? e->cfg.AP : -1; }
 int b2c_env_get_state(b2c_env* e, uint32_t* dst_host, void* stream) {

@@ -74,10 +74,11 @@ class _Net:
         return self._tc_w
 
     # inference: no activations kept
-    def forward(self, x, tc_version=None):
+    def forward(self, x, tc_version=None, x_split=None):
         if tc_version is not None and self.tc_ok():
             w1, w2, _ = self.tc_weights(tc_version)
-            _, s1 = ops.tc_linear(ops.tc_split_rows(x), w1, self.b[0], act=1, want_f32=False, want_split=True)
+            s0 = x_split if x_split is not None else ops.tc_split_rows(x)
+            _, s1 = ops.tc_linear(s0, w1, self.b[0], act=1, want_f32=False, want_split=True)
             h2, _ = ops.tc_linear(s1, w2, self.b[1], act=1)
             return ops.linear_forward(h2, self.W[2], self.b[2], 0)
         h = x
@@ -167,11 +168,12 @@ class CCModel:
             net.init(gen)
 
     # ---- reference interface -------------------------------------------------------------------------------
-    def forward(self, obs, state=None, seq_lens=None):
+    def forward(self, obs, state=None, seq_lens=None, obs_split=None):
+        """obs_split: the env's `obs_split` output for the same rows (skips the operand split pass)."""
         if isinstance(obs, dict):
             obs = obs.get("obs_flat", obs.get("obs"))
         obs = obs.reshape(obs.shape[0], -1)
-        logits = self.nets["policy"].forward(obs, self._tc())
+        logits = self.nets["policy"].forward(obs, self._tc(), obs_split)
         return logits if state is None else (logits, state)
 
     __call__ = forward

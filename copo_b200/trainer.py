@@ -74,7 +74,12 @@ class IPPOTrainer:
         self._iteration = 0
         self._step_counter = 0
         self._alloc_rollout()
-        self.env.reset()
+        # the env also emits each observation as the policy's [hi | lo] bf16 operand (two buffers, ping-pong)
+        self._split = [self.env.alloc_obs_split() for _ in range(2)] if self.policy.model.precision == "bf16_split" else None
+        first = dict(self.env.out)
+        if self._split:
+            first["obs_split"] = self._split[0]
+        self.env.reset(out=first)
         self.ro[P.OBS][0].copy_(self.env.out["obs"].reshape(self.N, -1))
 
     def get_policy(self, policy_id="default"):
@@ -109,13 +114,19 @@ class IPPOTrainer:
         if self._iteration > 0:
             ro[P.OBS][0].copy_(ro[P.OBS][self.T])        # the fragment continues where the last one stopped
         for t in range(self.T):
-            logits = pol.model.forward(ro[P.OBS][t])
+            g = self._step_counter
+            out = self._step_out[t]
+            sp = None
+            if self._split:
+                sp = self._split[g % 2].view(self.N, -1)
+                out["obs_split"] = self._split[(g + 1) % 2]
+            logits = pol.model.forward(ro[P.OBS][t], obs_split=sp)
             ro[P.ACTION_DIST_INPUTS][t].copy_(logits)
             actions, logp = ops.gaussian_sample(logits, seed=self.config.get("seed", 0) + self.rank * 7919,
                                                 step=self._step_counter)
             ro[P.ACTIONS][t].copy_(actions)
             ro[P.ACTION_LOGP][t].copy_(logp)
-            self.env.step(ro[P.ACTIONS][t].view(self.env.S, self.env.A, 2), out=self._step_out[t])
+            self.env.step(ro[P.ACTIONS][t].view(self.env.S, self.env.A, 2), out=out)
             self._step_counter += 1
         view = {k: (v[:self.T] if k == P.OBS else v) for k, v in ro.items()}
         view["slots"] = self.env.A

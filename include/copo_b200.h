@@ -66,6 +66,8 @@ typedef struct {
     int32_t* agent_id;            /* [S][A]      running agent number ("agent{id}") */
     float* lcf;                   /* [S][A]      info["lcf"] in [-1, 1] */
     uint8_t* scene_done;          /* [S]         done["__all__"] */
+    uint16_t* obs_split;          /* [S][A][W]   optional: obs as the [hi | lo] bf16 operand of b2c_tc_linear,
+                                                  W = b2c_env_obs_split_width() (saves the b2c_tc_split_rows pass) */
 } b2c_env_io;
 
 enum {
@@ -87,6 +89,7 @@ int b2c_env_set_lcf_dist(b2c_env* env, float mean, float std);
 int b2c_env_set_force_lcf(b2c_env* env, float value);
 int b2c_env_set_num_agents(b2c_env* env, int num_agents);   /* curriculum: ChangeNEnv, env_wrappers.py:450 */
 int b2c_env_obs_dim(const b2c_env* env);
+int b2c_env_obs_split_width(const b2c_env* env);
 int b2c_env_state_words(const b2c_env* env);                /* u32 words per scene tile */
 int b2c_env_slots_padded(const b2c_env* env);
 int b2c_env_get_state(b2c_env* env, uint32_t* dst_host, void* stream);       /* synchronises the stream */

@@ -103,3 +103,21 @@ def test_env_full_size_properties():
         o2 = env2.step(act)
     for k in o:
         assert torch.equal(o[k], o2[k]), k
+
+
+def test_env_emits_the_policy_operand():
+    """`obs_split` equals the [hi | lo] bf16 split of `obs` (bit for bit) - the env saves the policy a pass."""
+    from copo_b200 import ops
+    from copo_b200.batched_env import BatchedDrivingEnv
+    for name, A in (("intersection", 40), ("tollgate", 40), ("parking_lot", 10)):
+        env = BatchedDrivingEnv(name, num_scenes=37, num_slots=A, num_agents=A, seed=2)
+        out = dict(env.out)
+        out["obs_split"] = env.alloc_obs_split()
+        env.reset(out=out)
+        gen = torch.Generator(device="cuda").manual_seed(0)
+        for t in range(5):
+            env.step(torch.rand((37, A, 2), device="cuda", generator=gen) * 2 - 1, out=out)
+        want = ops.tc_split_rows(out["obs"].reshape(37 * A, -1))
+        assert env.split_width == want.shape[1]
+        assert torch.equal(out["obs_split"].reshape(37 * A, -1).view(torch.int16), want.view(torch.int16))
+        env.close()
