@@ -199,12 +199,12 @@ def run_gpu(args):
     state = {"t": 0}
 
     def rollout_step():
-        """policy forward (tcgen05 bf16_split) -> Gaussian sample -> fused scene step; everything stays in HBM"""
+        """policy forward (two tcgen05 kernels; logits + Gaussian sample in the second one's epilogue) -> fused scene
+        step (which also emits the next observation as the policy's bf16 operand); everything stays in HBM"""
         t = state["t"]
         r = t % RING
         src = obs[r] if r or t == 0 else obs[RING]
-        lg = pol.model.forward(src, obs_split=split[t % 2].view(N, -1))
-        actions, logp = ops.gaussian_sample(lg, seed=args.seed + rank * 7919, step=t)
+        lg, actions, logp = pol.model.forward_sample(src, args.seed + rank * 7919, t, obs_split=split[t % 2].view(N, -1))
         outs[r]["obs_split"] = split[(t + 1) % 2]
         env.step(actions.view(S, A, 2), out=outs[r])
         state["t"] = t + 1

@@ -77,7 +77,6 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 
 static constexpr int ENV_MAX_THREADS = 256;
 static constexpr int ENV_MAX_GROUP = 16;      // scene tag in a queue entry is 4 bits
-static constexpr int GEOM_WORDS = 10;         // nx1 nx2 ny1 ny2 cc ss | k0 cnt excl lid_off
 
 // Shared-memory plan of one CTA working on `G` scenes at a time (offsets in bytes, every region 16-byte aligned).
 struct SmemPlan {

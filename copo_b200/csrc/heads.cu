@@ -11,6 +11,7 @@
 #include <math.h>
 #include <stdint.h>
 #include "b2c_internal.h"
+#include "rng.cuh"
 
 namespace b2c {
 
@@ -84,22 +85,6 @@ __global__ void head_backward_kernel(const float* __restrict__ dy, int ldy, cons
         for (int j = 0; j < NOUT; ++j) atomicAdd(&dW[j * K + k], accw[j]);
     }
     if (db && blockIdx.y == 0 && threadIdx.x < NOUT) atomicAdd(&db[threadIdx.x], accb);
-}
-
-__device__ __forceinline__ uint32_t hash32(uint32_t x) {
-    x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
-    return x;
-}
-// two standard normals from a counter (Box-Muller on two hashed 24-bit uniforms)
-__device__ __forceinline__ void normal2(uint32_t seed, uint32_t ctr_hi, uint32_t ctr_lo, float& n0, float& n1) {
-    uint32_t a = hash32(seed ^ hash32(ctr_hi * 0x9E3779B1u + 0x85EBCA77u) ^ (ctr_lo * 0xC2B2AE3Du));
-    uint32_t b = hash32(a + 0x27D4EB2Fu);
-    float u0 = ((float)(a >> 8) + 0.5f) * (1.0f / 16777216.0f);
-    float u1 = ((float)(b >> 8) + 0.5f) * (1.0f / 16777216.0f);
-    float r = sqrtf(-2.0f * logf(u0));
-    float s, c;
-    sincosf(6.28318530717958647692f * u1, &s, &c);
-    n0 = r * c; n1 = r * s;
 }
 
 // logits[m] = (mu0, mu1, ls0, ls1); action = mu + exp(ls) * eps; logp as TorchDiagGaussian.logp

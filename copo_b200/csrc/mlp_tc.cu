@@ -24,6 +24,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "b2c_internal.h"
+#include "rng.cuh"
 
 namespace b2c {
 namespace tc {
@@ -32,7 +33,9 @@ constexpr int BLOCK_M = 128, BLOCK_N = 256, BLOCK_K = 64, UMMA_K = 16, STAGES = 
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;      // 16 KB per half (hi or lo)
 constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;      // 32 KB per half
 constexpr int STAGE_BYTES = 2 * A_STAGE_BYTES + 2 * B_STAGE_BYTES;     // A_hi, A_lo, W_hi, W_lo: 96 KB
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 1024 /*bias*/;
+constexpr int HEAD_MAX = 4;                               // fused narrow output layer: up to 4 outputs
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 1024 /*bias*/ +
+                           HEAD_MAX * BLOCK_N * 4 /*head weights*/ + 2 * BLOCK_M * HEAD_MAX * 4 /*head partials*/;
 constexpr int TMEM_COLS = 512;
 constexpr int EPI_WARPS = 8;
 constexpr int NUM_THREADS = 128 + EPI_WARPS * 32;
@@ -127,6 +130,15 @@ struct LinearArgs {
     uint16_t* out_split;      // [M][512] bf16 (hi | lo) or null
     int M, kp_blocks;         // kp_blocks = Kp / 64 reduction blocks, four products each
     int ld_out, ld_src, act;  // act: 0 none, 1 tanh
+    // fused narrow output layer on the activated result: head_out[m][j] = head_b[j] + sum_n y[m][n] head_w[j][n]
+    const float* head_w;      // [head_n][256] or null
+    const float* head_b;      // [head_n] or null
+    float* head_out;          // [M][head_n]
+    int head_n;               // 1 (value) or 4 (policy logits)
+    // Gaussian sample on the 4 logits (TorchDiagGaussian): actions [M][2], logp [M]; eps from (seed, step, row)
+    float* actions;
+    float* logp;
+    uint32_t seed, step;
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -140,6 +152,8 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
     float* s_bias = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);
+    float* s_head_w = s_bias + BLOCK_N;                          // [HEAD_MAX][256]
+    float* s_part = s_head_w + HEAD_MAX * BLOCK_N;               // [2 halves... upper half's partials][128][HEAD_MAX]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_tiles = (args.M + BLOCK_M - 1) / BLOCK_M;
@@ -161,6 +175,8 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     for (int i = threadIdx.x; i < BLOCK_N; i += NUM_THREADS) s_bias[i] = args.bias ? args.bias[i] : 0.0f;
+    if (args.head_w)
+        for (int i = threadIdx.x; i < args.head_n * BLOCK_N; i += NUM_THREADS) s_head_w[i] = args.head_w[i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -226,6 +242,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const int row = tile * BLOCK_M + q * 32 + lane;
             const bool live = row < args.M;
             const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+            float hacc[HEAD_MAX] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll 1
             for (int cc = 0; cc < BLOCK_N / 64; ++cc) {
                 const int c = half * (BLOCK_N / 64) + cc;        // 32-column chunk index
@@ -242,6 +259,19 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 if (args.act == 1) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = fast_tanh(v[j]);
+                }
+                if (args.head_w) {
+                    for (int hj = 0; hj < args.head_n; ++hj) {
+                        const float4* w4 = reinterpret_cast<const float4*>(s_head_w + hj * BLOCK_N + c * 32);
+                        float a = hacc[hj];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float4 ww = w4[j];
+                            a = fmaf(v[4 * j], ww.x, a); a = fmaf(v[4 * j + 1], ww.y, a);
+                            a = fmaf(v[4 * j + 2], ww.z, a); a = fmaf(v[4 * j + 3], ww.w, a);
+                        }
+                        hacc[hj] = a;
+                    }
                 }
                 if (live) {
                     if (args.dtanh_src) {
@@ -282,6 +312,37 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (args.head_w) {
+                // the two column halves of a row live in warps w and w + 4: the upper half hands its partial sums
+                // over through shared memory (named barrier 1 = the 8 epilogue warps)
+                const int rloc = q * 32 + lane;
+                if (half == 1) {
+#pragma unroll
+                    for (int hj = 0; hj < HEAD_MAX; ++hj) s_part[rloc * HEAD_MAX + hj] = hacc[hj];
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+                if (half == 0 && live) {
+                    float o[HEAD_MAX];
+#pragma unroll
+                    for (int hj = 0; hj < HEAD_MAX; ++hj)
+                        o[hj] = (hj < args.head_n) ? hacc[hj] + s_part[rloc * HEAD_MAX + hj] + args.head_b[hj] : 0.0f;
+                    if (args.head_n == 4) {
+                        reinterpret_cast<float4*>(args.head_out)[row] = make_float4(o[0], o[1], o[2], o[3]);
+                        if (args.actions) {
+                            float e0, e1;
+                            normal2(args.seed, args.step, (uint32_t)row, e0, e1);
+                            float s0 = expf(o[2]), s1 = expf(o[3]);
+                            float a0 = o[0] + s0 * e0, a1 = o[1] + s1 * e1;
+                            float z0 = (a0 - o[0]) / s0, z1 = (a1 - o[1]) / s1;
+                            reinterpret_cast<float2*>(args.actions)[row] = make_float2(a0, a1);
+                            if (args.logp) args.logp[row] = -0.5f * (z0 * z0 + z1 * z1) - 1.8378770664093453f - (o[2] + o[3]);
+                        }
+                    } else {
+                        for (int hj = 0; hj < args.head_n; ++hj) args.head_out[(size_t)row * args.head_n + hj] = o[hj];
+                    }
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+            }
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
     }
@@ -543,9 +604,31 @@ int b2c_tc_prep_weight(const float* W, uint16_t* out, int N, int K, int Kp, int 
     return B2C_OK;
 }
 
+static int tc_linear_launch(const uint16_t* a_split, const uint16_t* w_prep, const float* bias, const float* dtanh_src,
+                            int ld_src, float* out_f32, int ld_out, uint16_t* out_split, int M, int Kp, int act,
+                            const b2c_tc_head* head, void* stream);
+
 int b2c_tc_linear(const uint16_t* a_split, const uint16_t* w_prep, const float* bias, const float* dtanh_src, int ld_src,
                   float* out_f32, int ld_out, uint16_t* out_split, int M, int Kp, int act, void* stream) {
-    if (!a_split || !w_prep || (!out_f32 && !out_split) || Kp < BLOCK_K || Kp % BLOCK_K || M < 0)
+    if (!out_f32 && !out_split) return b2c_set_error(B2C_ERR_ARG, "b2c_tc_linear: no output requested");
+    return tc_linear_launch(a_split, w_prep, bias, dtanh_src, ld_src, out_f32, ld_out, out_split, M, Kp, act, nullptr,
+                            stream);
+}
+
+int b2c_tc_linear_head(const uint16_t* a_split, const uint16_t* w_prep, const float* bias, float* out_f32, int ld_out,
+                       int M, int Kp, int act, const b2c_tc_head* head, void* stream) {
+    if (!head || !head->weight || !head->bias || !head->out || (head->n != 1 && head->n != 4))
+        return b2c_set_error(B2C_ERR_ARG, "b2c_tc_linear_head: the fused output layer needs weight, bias, out and n in {1, 4}");
+    if (head->actions && head->n != 4) return b2c_set_error(B2C_ERR_ARG, "b2c_tc_linear_head: sampling needs the 4 policy logits");
+    if (((uintptr_t)head->out | (uintptr_t)head->actions) & 15)
+        return b2c_set_error(B2C_ERR_ARG, "b2c_tc_linear_head: outputs must be 16-byte aligned");
+    return tc_linear_launch(a_split, w_prep, bias, nullptr, 0, out_f32, ld_out, nullptr, M, Kp, act, head, stream);
+}
+
+static int tc_linear_launch(const uint16_t* a_split, const uint16_t* w_prep, const float* bias, const float* dtanh_src,
+                            int ld_src, float* out_f32, int ld_out, uint16_t* out_split, int M, int Kp, int act,
+                            const b2c_tc_head* head, void* stream) {
+    if (!a_split || !w_prep || Kp < BLOCK_K || Kp % BLOCK_K || M < 0)
         return b2c_set_error(B2C_ERR_ARG, "b2c_tc_linear: bad argument");
     if (((uintptr_t)a_split | (uintptr_t)w_prep | (uintptr_t)out_f32 | (uintptr_t)out_split | (uintptr_t)dtanh_src) & 15)
         return b2c_set_error(B2C_ERR_ARG, "b2c_tc_linear: pointers must be 16-byte aligned");
@@ -569,6 +652,12 @@ int b2c_tc_linear(const uint16_t* a_split, const uint16_t* w_prep, const float* 
     LinearArgs a;
     a.bias = bias; a.dtanh_src = dtanh_src; a.out_f32 = out_f32; a.out_split = out_split; a.M = M;
     a.kp_blocks = Kp / BLOCK_K; a.ld_out = ld_out; a.ld_src = ld_src; a.act = act;
+    a.head_w = nullptr; a.head_b = nullptr; a.head_out = nullptr; a.head_n = 0; a.actions = nullptr; a.logp = nullptr;
+    a.seed = 0; a.step = 0;
+    if (head) {
+        a.head_w = head->weight; a.head_b = head->bias; a.head_out = head->out; a.head_n = head->n;
+        a.actions = head->actions; a.logp = head->logp; a.seed = head->seed; a.step = head->step;
+    }
     int tiles = (M + BLOCK_M - 1) / BLOCK_M;
     int grid = tiles < num_sms ? tiles : num_sms;
     tc_linear_kernel<<<grid, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(map_a, map_w, a);

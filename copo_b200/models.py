@@ -74,11 +74,15 @@ class _Net:
         return self._tc_w
 
     # inference: no activations kept
-    def forward(self, x, tc_version=None, x_split=None):
+    def forward(self, x, tc_version=None, x_split=None, sample=None, out=None, actions=None, logp=None):
         if tc_version is not None and self.tc_ok():
             w1, w2, _ = self.tc_weights(tc_version)
             s0 = x_split if x_split is not None else ops.tc_split_rows(x)
             _, s1 = ops.tc_linear(s0, w1, self.b[0], act=1, want_f32=False, want_split=True)
+            if self.out_dim in (1, 4):       # the narrow output layer rides in the layer-2 epilogue
+                out, actions, logp, _ = ops.tc_linear_head(s1, w2, self.b[1], self.W[2], self.b[2], act=1, sample=sample,
+                                                           out=out, actions=actions, logp=logp)
+                return out if sample is None else (out, actions, logp)
             h2, _ = ops.tc_linear(s1, w2, self.b[1], act=1)
             return ops.linear_forward(h2, self.W[2], self.b[2], 0)
         h = x
@@ -177,6 +181,22 @@ class CCModel:
         return logits if state is None else (logits, state)
 
     __call__ = forward
+
+    def forward_sample(self, obs, seed, step, obs_split=None, out=None, actions=None, logp=None):
+        """Rollout step of the policy: logits, sampled actions and their log-probabilities.  On the tensor-core path
+        this is two kernels (layer 1; layer 2 + logits + Gaussian sample in its epilogue)."""
+        net = self.nets["policy"]
+        if self._tc() is not None and net.tc_ok():
+            return net.forward(obs, self._tc(), obs_split, sample=(seed, step), out=out, actions=actions, logp=logp)
+        logits = net.forward(obs, None)
+        a, lp = ops.gaussian_sample(logits, seed=seed, step=step)
+        if out is not None:
+            out.copy_(logits); logits = out
+        if actions is not None:
+            actions.copy_(a); a = actions
+        if logp is not None:
+            logp.copy_(lp); lp = logp
+        return logits, a, lp
 
     def value_function(self):
         raise ValueError("Centralized Value Function should not be called directly! "

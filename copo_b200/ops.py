@@ -296,3 +296,36 @@ def colsum(dy, db):
     pdy, M, N, ldy = _rows2d(dy)
     _lib.check(lib.b2c_colsum(pdy, c_int(ldy), P(db), c_int(M), c_int(N), _lib.stream_ptr()))
     return db
+
+
+class TcHead(ctypes.Structure):
+    _fields_ = [("weight", ctypes.c_void_p), ("bias", ctypes.c_void_p), ("out", ctypes.c_void_p), ("n", ctypes.c_int32),
+                ("actions", ctypes.c_void_p), ("logp", ctypes.c_void_p), ("seed", ctypes.c_uint32),
+                ("step", ctypes.c_uint32)]
+
+
+def tc_linear_head(a_split, w_prep, bias, head_w, head_b, act=1, sample=None, want_f32=False, out=None, actions=None,
+                   logp=None):
+    """256-wide layer + fused narrow output layer (n = 1 or 4).  sample = (seed, step) also draws the Gaussian action
+    in the epilogue.  Returns (head_out [M, n], actions or None, logp or None, hidden fp32 or None)."""
+    lib = _lib_ready()
+    M, two_kp = a_split.shape
+    Kp = two_kp // 2
+    n = head_w.shape[0]
+    dev = a_split.device
+    assert head_w.shape == (n, 256) and head_w.is_contiguous() and w_prep.shape == (256, 2 * Kp)
+    if out is None:
+        out = torch.empty((M, n), dtype=torch.float32, device=dev)
+    h = torch.empty((M, 256), dtype=torch.float32, device=dev) if want_f32 else None
+    hd = TcHead()
+    hd.weight, hd.bias, hd.out, hd.n = head_w.data_ptr(), head_b.data_ptr(), out.data_ptr(), n
+    if sample is not None:
+        if actions is None:
+            actions = torch.empty((M, 2), dtype=torch.float32, device=dev)
+        if logp is None:
+            logp = torch.empty((M,), dtype=torch.float32, device=dev)
+        hd.actions, hd.logp = actions.data_ptr(), logp.data_ptr()
+        hd.seed, hd.step = sample[0] & 0xFFFFFFFF, sample[1] & 0xFFFFFFFF
+    _lib.check(lib.b2c_tc_linear_head(P(a_split), P(w_prep), P(bias), P(h), c_int(256 if want_f32 else 0), c_int(M),
+                                      c_int(Kp), c_int(act), ctypes.byref(hd), _lib.stream_ptr()))
+    return out, actions, logp, h

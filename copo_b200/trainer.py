@@ -120,12 +120,10 @@ class IPPOTrainer:
             if self._split:
                 sp = self._split[g % 2].view(self.N, -1)
                 out["obs_split"] = self._split[(g + 1) % 2]
-            logits = pol.model.forward(ro[P.OBS][t], obs_split=sp)
-            ro[P.ACTION_DIST_INPUTS][t].copy_(logits)
-            actions, logp = ops.gaussian_sample(logits, seed=self.config.get("seed", 0) + self.rank * 7919,
-                                                step=self._step_counter)
-            ro[P.ACTIONS][t].copy_(actions)
-            ro[P.ACTION_LOGP][t].copy_(logp)
+            # policy forward + Gaussian sample write straight into the rollout columns
+            pol.model.forward_sample(ro[P.OBS][t], self.config.get("seed", 0) + self.rank * 7919, g, obs_split=sp,
+                                     out=ro[P.ACTION_DIST_INPUTS][t], actions=ro[P.ACTIONS][t],
+                                     logp=ro[P.ACTION_LOGP][t])
             self.env.step(ro[P.ACTIONS][t].view(self.env.S, self.env.A, 2), out=out)
             self._step_counter += 1
         view = {k: (v[:self.T] if k == P.OBS else v) for k, v in ro.items()}

@@ -204,6 +204,21 @@ int b2c_tc_split_rows(const float* x, int ldx, uint16_t* out, int M, int K, int 
 int b2c_tc_prep_weight(const float* W, uint16_t* out, int N, int K, int Kp, int transpose, void* stream);
 /* out = epilogue(a W'^T): + bias, tanh (act = 1), * (1 - dtanh_src^2); writes fp32 [M][ld_out] and / or the
  * [hi | lo] bf16 operand of the next layer [M][512].  Output width is 256. */
+/* Same layer with the narrow output layer fused into the epilogue (the activated 256-wide result never leaves the
+ * SM unless out_f32 is given): head.out[m][j] = head.bias[j] + sum_n y[m][n] head.weight[j][n], n in {1, 4}.
+ * With head.actions set (n = 4) the epilogue also draws the action from TorchDiagGaussian(logits) with the
+ * counter-based generator keyed by (seed, step, row) and writes its log-probability (rollout step, a7). */
+typedef struct {
+    const float* weight;          /* [n][256] */
+    const float* bias;            /* [n] */
+    float* out;                   /* [M][n] */
+    int32_t n;
+    float* actions;               /* [M][2] or NULL */
+    float* logp;                  /* [M] or NULL */
+    uint32_t seed, step;
+} b2c_tc_head;
+int b2c_tc_linear_head(const uint16_t* a_split, const uint16_t* w_prep, const float* bias, float* out_f32, int ld_out,
+                       int M, int Kp, int act, const b2c_tc_head* head, void* stream);
 /* Weight gradient of a 256-wide layer on the tensor cores: dW[256][K] += dz^T x from the [hi | lo] operands
  * (dz_split [M][512], x_split [M][2*Kp], Kp <= 256).  workspace: b2c_tc_wgrad_parts() * 256 * Kp floats; the
  * per-CTA partial sums are added in a fixed order (deterministic). */

@@ -98,3 +98,29 @@ def test_tc_weight_gradient(M, K):
     dW2 = torch.full((256, K), 0.5, device="cuda")
     ops.tc_wgrad(ops.tc_split_rows(dz.cuda()), ops.tc_split_rows(x.cuda()), dW2)
     assert torch.equal(dW, dW2)                            # fixed summation order: bitwise reproducible
+
+
+@pytest.mark.parametrize("M", [1, 129, 5000])
+def test_tc_fused_head_and_sample(M):
+    """Layer 2 with the logits / value layer (and the Gaussian sample) fused into its epilogue equals the unfused
+    kernels; sampled actions are consistent with their log-probabilities."""
+    from copo_b200 import ops
+    from oracle import models as om
+    g = torch.Generator().manual_seed(M)
+    x = torch.rand(M, 256, generator=g).cuda()
+    W2, b2 = (torch.randn(256, 256, generator=g) / 16).cuda(), (0.1 * torch.randn(256, generator=g)).cuda()
+    W3, b3 = (torch.randn(4, 256, generator=g) / 16).cuda(), (0.1 * torch.randn(4, generator=g)).cuda()
+    a, w = ops.tc_split_rows(x), ops.tc_prep_weight(W2)
+    h2, _ = ops.tc_linear(a, w, b2, act=1)
+    want = ops.linear_forward(h2, W3, b3, 0)
+    logits, actions, logp, h = ops.tc_linear_head(a, w, b2, W3, b3, act=1, sample=(5, 9), want_f32=True)
+    assert float((logits - want).abs().max()) < 2e-5 and torch.equal(h, h2)
+    d = om.DiagGaussian(logits.cpu())
+    assert float((d.logp(actions.cpu()) - logp.cpu()).abs().max()) < 1e-4
+    z = (actions.cpu() - d.mean) / d.std
+    if M >= 5000:
+        assert abs(float(z.mean())) < 0.05 and abs(float(z.std()) - 1) < 0.05
+    l2, a2, p2, _ = ops.tc_linear_head(a, w, b2, W3, b3, act=1, sample=(5, 9))
+    assert torch.equal(a2, actions) and torch.equal(l2, logits)
+    v, _, _, _ = ops.tc_linear_head(a, w, b2, W3[:1].contiguous(), b3[:1].contiguous(), act=1)
+    assert float((v[:, 0] - want[:, 0]).abs().max()) < 2e-5
