@@ -262,17 +262,29 @@ def run_gpu(args):
     l2_ms = time_kernel(lambda: ops.tc_linear(s1, w2, net.b[1], act=1, out_f32=h2))
     l1_ms = time_kernel(lambda: ops.tc_linear(a1, w1, net.b[0], act=1, want_f32=False, out_split=s1, want_split=True))
 
-    # ---- end to end through the host-buffer API ------------------------------------------------------------
-    host_acts = [(torch.rand((S, A, 2)) * 2 - 1).pin_memory() for _ in range(4)]
+    # ---- end to end, host in the loop: pinned host actions -> device, scene step, every env output -> pinned host,
+    # policy forward + sample on the new observations, sampled actions -> pinned host (they are the next step's input)
+    e2e_out = dict(env.out)
+    e2e_out["obs_split"] = split[0]
+    env.out = e2e_out
+    host_act = torch.zeros((S, A, 2)).pin_memory()
+
+    def e2e_step(t):
+        env.step_host(host_act)
+        lg, a, lp = pol.model.forward_sample(env.out["obs"].view(N, D), args.seed + rank * 7919, 100000 + t,
+                                             obs_split=split[0].view(N, -1))
+        host_act.copy_(a.view(S, A, 2), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
     for t in range(3):
-        env.step_host(host_acts[t % 4])
+        e2e_step(t)
     e2e_steps = max(3, min(args.steps, 50))
     m0 = env.agent_steps()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for t in range(e2e_steps):
-        env.step_host(host_acts[t % 4])
+        e2e_step(3 + t)
     e1.record(stream)
     barrier()
     e2e_ms = e0.elapsed_time(e1)
@@ -343,8 +355,10 @@ def run_gpu(args):
         "kernel_ms": {"env_step": env_ms, "tc_linear_layer1": l1_ms, "tc_linear_layer2": l2_ms},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": env.h2d_bytes_per_step * world,
-                "d2h_bytes_per_step": env.d2h_bytes_per_step * world, "steps": e2e_steps,
-                "api": "BatchedDrivingEnv.step_host: pinned host actions in, every env output back to pinned host"},
+                "d2h_bytes_per_step": (env.d2h_bytes_per_step + env.h2d_bytes_per_step) * world, "steps": e2e_steps,
+                "api": "host-in-the-loop rollout step: BatchedDrivingEnv.step_host (pinned host actions in, every env "
+                       "output back to pinned host) + CoPOModel.forward_sample on the device, sampled actions back to "
+                       "pinned host"},
         "gpu_launches": launches,
         "clocks": clk,
         "train": train,

@@ -119,3 +119,23 @@ def test_tensor_core_values_keep_gae_within_tolerance():
         err = float((a - b)[valid].abs().max())
         assert err <= 1e-4 * scale + 1e-6, (k, err, scale)
     tr.stop()
+
+
+def test_batched_evaluation_of_a_shipped_policy():
+    """a shipped CoPO policy (golden fixture weights, TF-era naming) loads and is evaluated on
+    the batched simulator; the report carries the reference's evaluation columns."""
+    import os
+    from copo_b200.evaluate import evaluate
+    from copo_b200.models import CCModel
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mlp_golden.npz"))
+    sub = {k[len("copo_inter") + 1:]: z[k] for k in z.files if k.startswith("copo_inter/")}
+    m = CCModel(92)
+    m.load_policy_npz(sub)
+    res = evaluate(m, "MultiAgentIntersectionEnv", num_scenes=16, num_agents=30, horizon=150, seed=1, lcf_mean=0.225,
+                   lcf_std=0.1)
+    for k in ("success_rate", "crash_rate", "out_rate", "max_step_rate", "velocity_step_mean_episode_mean",
+              "num_neighbours_step_mean", "step_reward_mean", "num_agents_success_per_300_steps"):
+        assert math.isfinite(res[k]), k
+    total = res["success_rate"] + res["crash_rate"] + res["out_rate"] + res["max_step_rate"]
+    assert 0.99 <= total <= 2.0              # an agent can crash and leave the road in the same step
+    assert res["agent_steps"] > 16 * 20 * 100 and res["velocity_step_mean_episode_max"] > 1.0
