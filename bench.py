@@ -329,8 +329,9 @@ def run_gpu(args):
                 "note": "issue-bound (72-laser lidar + neighbour search): see profiles/ for the instruction mix"}
     mlp_roof = {"bound": "tensor", "achieved": l2_tf, "peak": tc_peak, "unit": "TFLOP/s", "frac": l2_tf / tc_peak,
                 "traffic": None, "peak_source": peak_src, "kernel": "tc_linear_kernel (256x256 layer, bf16_split)",
-                "algorithmic_flops_per_launch": l2_flops, "kernel_ms": l2_ms, "tensor_flops_issued": 3 * l2_flops,
-                "note": "achieved counts fp32-equivalent flops; the kernel issues 3x as many bf16 flops (split operands)"}
+                "algorithmic_flops_per_launch": l2_flops, "kernel_ms": l2_ms, "tensor_flops_issued": 4 * l2_flops,
+                "note": "achieved counts fp32-equivalent flops; the kernel issues 4x as many bf16 flops (hi/lo split "
+                        "operands, four products)"}
     dominant_is_env = env_ms >= (l1_ms + l2_ms)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:

@@ -405,7 +405,7 @@ class OracleSim:
         eq = (dkey[:, :, None, :] == dkey[:, :, :, None]) & (np.arange(A)[None, None, None, :] <
                                                              np.arange(A)[None, None, :, None])
         rank = (lt | eq).sum(axis=3)
-        rank = np.where(inr, rank, A)
+        rank = np.where(inr, rank, A + NEI_K)          # sentinel beyond every k (also when A <= NEI_K)
         nei_list = np.full((S, A, NEI_K), -1, np.int8)
         for kk in range(NEI_K):
             sel = rank == kk

@@ -33,6 +33,9 @@ def _to_np(out):
     ("bottleneck", 3, 20, 120, dict(delay_done=0)),
     ("intersection", 3, 40, 80, dict(append_lcf=False, num_agents=30, neighbours_distance=10.0)),
     ("intersection", 2, 40, 60, dict(lcf_uniform=True, allow_respawn=False, auto_reset=False, horizon=40)),
+    ("intersection", 5, 64, 50, dict()),                      # maximum slot count (more slots than spawn places)
+    ("parking_lot", 33, 1, 40, dict()),                       # single-slot scenes, ragged last CTA group
+    ("roundabout", 1, 3, 30, dict(force_lcf=0.5, delay_done=1)),
 ])
 def test_env_step_bit_exact(map_name, S, A, T, kw):
     from copo_b200.batched_env import BatchedDrivingEnv

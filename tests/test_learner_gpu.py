@@ -341,3 +341,22 @@ def test_adam_and_dot():
     close(q, p, 1e-6, 1e-7)
     a, b = torch.randn(100000, device="cuda"), torch.randn(100000, device="cuda")
     assert abs(float(ops.dot(a, b)) - float((a.double() * b.double()).sum())) < 1e-6
+
+
+def test_empty_inputs_are_accepted():
+    """Zero-row calls are legal everywhere (a rank can hold no valid rows in a minibatch slice)."""
+    from copo_b200 import ops
+    e = lambda *shape: torch.empty(shape, device="cuda")
+    W, b = torch.randn(256, 92, device="cuda"), torch.zeros(256, device="cuda")
+    assert ops.linear_forward(e(0, 92), W, b, 1).shape == (0, 256)
+    assert ops.tc_split_rows(e(0, 92)).shape == (0, 256)
+    y, _ = ops.tc_linear(ops.tc_split_rows(e(0, 92)), ops.tc_prep_weight(W), b, act=1)
+    assert y.shape == (0, 256)
+    a, lp = ops.gaussian_sample(e(0, 4))
+    assert a.shape == (0, 2) and lp.shape == (0,)
+    dW = torch.zeros(256, 92, device="cuda")
+    ops.linear_backward(e(0, 256), e(0, 92), W, dW, torch.zeros(256, device="cuda"), False, need_dx=False)
+    assert float(dW.abs().max()) == 0.0
+    assert ops.gather_rows(e(10, 7), torch.empty(0, dtype=torch.int64, device="cuda")).shape == (0, 7)
+    st = ops.lcf_mix_stats(torch.empty(0, dtype=torch.uint8, device="cuda"), e(0), e(0), e(0), e(0))
+    assert st.tolist() == [0.0] * 5

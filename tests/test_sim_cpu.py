@@ -31,6 +31,9 @@ def _policy(obs, rng, S, A):
     ("intersection", 2, 40, 50, dict(append_lcf=False, num_agents=30, neighbours_distance=10.0)),
     ("intersection", 2, 12, 60, dict(lcf_uniform=True, allow_respawn=False, auto_reset=False, horizon=40)),
     ("intersection", 1, 7, 30, dict(force_lcf=0.5)),
+    ("intersection", 2, 64, 25, dict()),
+    ("parking_lot", 5, 1, 30, dict()),
+    ("roundabout", 1, 3, 30, dict(force_lcf=0.5, delay_done=1)),
 ])
 def test_host_phases_match_spec(map_name, S, A, T, kw):
     tables = build_map(map_name)
