@@ -173,7 +173,10 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("B2C_NCCL_DEBUG", "WARN")    # keep stdout to the one JSON line
+        if "B2C_NCCL_DEBUG" in os.environ:                   # NCCL prints its banner on stdout: keep stdout to the
+            os.environ["NCCL_DEBUG"] = os.environ["B2C_NCCL_DEBUG"]      # one JSON line unless asked otherwise
+        else:
+            os.environ.pop("NCCL_DEBUG", None)
         dist.init_process_group("nccl", device_id=dev)
     S, A = args.scenes, SLOTS
     N = S * A
