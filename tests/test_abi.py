@@ -62,3 +62,32 @@ def test_product_never_imports_the_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
                 assert "_hostsim.so" not in txt, f
+
+
+def test_ctypes_structs_match_the_header(tmp_path):
+    """Sizes and field offsets of every struct crossing the ABI: the C header compiled with gcc vs the ctypes mirrors."""
+    import subprocess
+    from copo_b200 import _lib, ops
+    pairs = {"b2c_env_config": _lib.EnvConfig, "b2c_env_io": _lib.EnvIO, "b2c_ppo_head_args": ops.PpoHeadArgs,
+             "b2c_gae_args": ops.GaeArgs, "b2c_tc_head": ops.TcHead}
+    fields = {"b2c_env_config": ["num_scenes", "seed", "neighbours_distance", "force_lcf"],
+              "b2c_env_io": ["obs", "scene_done", "obs_split"],
+              "b2c_ppo_head_args": ["logits", "v_cur", "dlogits", "dv", "stats", "rows", "mode", "clip_param", "kl_coeff"],
+              "b2c_gae_args": ["flags", "rewards", "targets", "T", "global_reward_per_scene", "gamma", "lambda_"],
+              "b2c_tc_head": ["weight", "out", "n", "actions", "logp", "seed", "step"]}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "copo_b200.h"', 'int main(void) {']
+    for s, fs in fields.items():
+        lines.append('printf("%s size %%zu\\n", sizeof(%s));' % (s, s))
+        for f in fs:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (s, f, s, f))
+    lines += ["return 0; }"]
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)], text=True)
+    got = dict(line.rsplit(" ", 1) for line in out.strip().splitlines())
+    for s, cls in pairs.items():
+        assert int(got["%s size" % s]) == ctypes.sizeof(cls), s
+        for f in fields[s]:
+            assert int(got["%s.%s" % (s, f)]) == getattr(cls, f).offset, (s, f)
