@@ -36,6 +36,10 @@ struct EnvIO {
     uint8_t* scene_done;
     uint32_t* obs_split;   // [S][A][kp] bf16 pairs: the policy's tensor-core operand ([hi | lo], mlp_tc.cu), or null
     int kp;                // padded observation width (multiple of 64)
+    // two-kernel mode: the state kernel hands these to the lidar kernel
+    float* pose;           // [S][4 * A + 4]: x[A], y[A], cos[A], sin[A], then {pair count, part mask lo, hi, 0}
+    uint16_t* pairs;       // [S][pair_stride]: queued (observer << 6 | box) lidar pairs
+    int pair_stride;
     int map_words;
     int tile_words;
     int obs_bulk;   // 1 when the obs tiles can leave through a bulk store (16-byte aligned base)
@@ -82,15 +86,16 @@ static constexpr int ENV_MAX_GROUP = 16;      // scene tag in a queue entry is 4
 struct SmemPlan {
     int map, st, obs, f, i, need, masks, queue, geom, total;
 };
-__host__ __device__ inline SmemPlan smem_plan(int G, int A, int D, int map_words, int tile_words, int n_warps) {
+__host__ __device__ inline SmemPlan smem_plan(int G, int A, int D, int map_words, int tile_words, int n_warps,
+                                              bool split = false) {
     SmemPlan p;
     int o = 16;                                          // mbarrier
     p.map = o;   o += map_words * 4;
     p.st = o;    o += G * tile_words * 4;
-    p.obs = o;   o += ((G * A * D + 3) & ~3) * 4;
+    p.obs = o;   o += split ? 0 : ((G * A * D + 3) & ~3) * 4;      // two-kernel mode: observations go straight to HBM
     p.f = o;     o += ((G * 6 * A + 3) & ~3) * 4;
     p.i = o;     o += ((G * (4 * A + MAX_SPAWN) + 3) & ~3) * 4;
-    p.need = o;  o += ((2 * G + 4 + 3) & ~3) * 4;        // need[G], scene_done[G], queue fill
+    p.need = o;  o += ((3 * G + 4 + 3) & ~3) * 4;        // need[G], scene_done[G], queue fill (1 or per scene)
     p.masks = o; o += G * 2 * 8;                         // per scene: participant / present slot masks
     p.queue = o; o += ((G * A * A + 7) & ~7) * 2;
     p.geom = o;  (void)n_warps;
@@ -98,12 +103,17 @@ __host__ __device__ inline SmemPlan smem_plan(int G, int A, int D, int map_words
     return p;
 }
 
-__global__ void __launch_bounds__(ENV_MAX_THREADS, 2)
+// SPLIT = false: the whole step in one kernel (observation tile in shared memory, lidar included).
+// SPLIT = true: the state half of the two-kernel mode - per-slot phases only, small shared-memory footprint (no
+// observation tile) so several times more scenes are resident per SM; ego / navigation features go straight to HBM,
+// poses + queued lidar pairs go to a scratch buffer for env_lidar_kernel.
+template <bool SPLIT>
+__global__ void __launch_bounds__(SPLIT ? 128 : ENV_MAX_THREADS, SPLIT ? 7 : 2)
 env_step_kernel(const __grid_constant__ EnvConfig cfg, const __grid_constant__ EnvIO io) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int A = cfg.A, AP = cfg.AP, D = cfg.D, G = io.group;
     const int tid = threadIdx.x, NT = blockDim.x;
-    const SmemPlan pl = smem_plan(G, A, D, io.map_words, io.tile_words, (int)(blockDim.x >> 5));
+    const SmemPlan pl = smem_plan(G, A, D, io.map_words, io.tile_words, (int)(blockDim.x >> 5), SPLIT);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     uint32_t* s_map = reinterpret_cast<uint32_t*>(smem_raw + pl.map);
     uint32_t* s_st = reinterpret_cast<uint32_t*>(smem_raw + pl.st);
@@ -116,14 +126,17 @@ env_step_kernel(const __grid_constant__ EnvConfig cfg, const __grid_constant__ E
     uint16_t* s_queue = reinterpret_cast<uint16_t*>(smem_raw + pl.queue);
     unsigned long long* s_masks = reinterpret_cast<unsigned long long*>(smem_raw + pl.masks);
 
+    int scene_base = 0;                                  // first scene of the group being worked on
     auto view = [&](int sl) {
         SceneView v;
-        v.map = s_map; v.st = s_st + sl * io.tile_words; v.obs = s_obs + (size_t)sl * A * D;
+        v.map = s_map; v.st = s_st + sl * io.tile_words;
+        v.obs = SPLIT ? io.obs + (size_t)(scene_base + sl) * A * D : s_obs + (size_t)sl * A * D;
         float* f = s_f + sl * 6 * A;
         v.cs = f; v.sn = f + A; v.rew = f + 2 * A; v.long_last = f + 3 * A; v.loc_s = f + 4 * A; v.loc_l = f + 5 * A;
         int* q = s_i + sl * (4 * A + MAX_SPAWN);
         v.flags = q; v.crash = q + A; v.acted = q + 2 * A; v.linger = q + 3 * A; v.place_free = q + 4 * A;
-        v.nqueue = s_nq; v.queue = s_queue; v.scene_local = sl; v.masks = s_masks + 2 * sl;
+        v.nqueue = SPLIT ? s_nq + sl : s_nq; v.queue = SPLIT ? s_queue + sl * A * A : s_queue;
+        v.scene_local = SPLIT ? 0 : sl; v.masks = s_masks + 2 * sl;
         v.A = A; v.AP = AP; v.D = D;
         return v;
     };
@@ -140,6 +153,7 @@ env_step_kernel(const __grid_constant__ EnvConfig cfg, const __grid_constant__ E
 
     for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
         const int scene0 = grp * G;
+        scene_base = scene0;
         const int ng = (cfg.S - scene0 < G) ? cfg.S - scene0 : G;
         uint32_t* g_tiles = io.state + (size_t)scene0 * io.tile_words;
         const bool has_agent = tid < ng * A;
@@ -151,6 +165,7 @@ env_step_kernel(const __grid_constant__ EnvConfig cfg, const __grid_constant__ E
             bulk_g2s(s_st, g_tiles, (uint32_t)ng * tile_bytes, bar);
             *s_nq = 0;
         }
+        if (SPLIT && tid < G) s_nq[tid] = 0;
         float act0 = 0.0f, act1 = 0.0f;
         if (has_agent && !cfg.do_reset) {
             float2 a = reinterpret_cast<const float2*>(io.actions)[(size_t)scene0 * A + tid];
@@ -222,7 +237,7 @@ env_step_kernel(const __grid_constant__ EnvConfig cfg, const __grid_constant__ E
             if (io.agent_id) io.agent_id[g] = v.geti(F_ID, ia);
             if (io.lcf) io.lcf[g] = v.f(F_LCF, ia);
             phase_observe_ego(v, cfg, ia);
-            phase_lidar_init(v, ia);
+            if (!SPLIT) phase_lidar_init(v, ia);
         }
         {
             int sl = spare ? tid - ng * A : ((has_agent && ia == A - 1) ? sl_a : -1);
@@ -233,6 +248,7 @@ env_step_kernel(const __grid_constant__ EnvConfig cfg, const __grid_constant__ E
             }
         }
         __syncthreads();
+        if constexpr (!SPLIT) {
         // ---- P7: lidar.  Each warp takes 32 queued (observer, box) pairs, sets them up one per lane, then
         // spreads the pairs' lasers evenly over its lanes (prefix sum + search through shuffles) -------------
         {
@@ -284,9 +300,32 @@ env_step_kernel(const __grid_constant__ EnvConfig cfg, const __grid_constant__ E
                 }
             }
         }
+        }
         fence_async_smem();
         __syncthreads();
-        // ---- write back: state tiles + observation tiles through bulk stores ------------------------------
+        // ---- write back ------------------------------------------------------------------------------------
+        if constexpr (SPLIT) {
+            // state tiles through a bulk store; poses, participant mask and the queued pairs to the scratch buffer
+            if (tid == 0) {
+                bulk_s2g(g_tiles, s_st, (uint32_t)ng * tile_bytes);
+                bulk_commit();
+            }
+            const int rec = 4 * A + 4;
+            if (has_agent) {
+                float* pr = io.pose + (size_t)(scene0 + sl_a) * rec;
+                pr[ia] = v.f(F_X, ia); pr[A + ia] = v.f(F_Y, ia); pr[2 * A + ia] = v.cs[ia]; pr[3 * A + ia] = v.sn[ia];
+                if (ia == 0) {
+                    uint32_t* pi = reinterpret_cast<uint32_t*>(pr + 4 * A);
+                    unsigned long long pm = v.masks[0];
+                    pi[0] = (uint32_t)s_nq[sl_a]; pi[1] = (uint32_t)pm; pi[2] = (uint32_t)(pm >> 32); pi[3] = 0u;
+                }
+            }
+            for (int sl = 0; sl < ng; ++sl) {
+                const int nq = s_nq[sl];
+                uint16_t* gq = io.pairs + (size_t)(scene0 + sl) * io.pair_stride;
+                for (int e = tid; e < nq; e += NT) gq[e] = s_queue[sl * A * A + e];
+            }
+        } else {
         float* g_obs = io.obs + (size_t)scene0 * A * D;
         const uint32_t obs_bytes = (uint32_t)(ng * A * D * 4);
         const bool obs_bulk = io.obs_bulk && (obs_bytes % 16u == 0u);
@@ -315,7 +354,147 @@ env_step_kernel(const __grid_constant__ EnvConfig cfg, const __grid_constant__ E
             }
         }
     }
+        }
     if (tid == 0) bulk_wait_read0();
+}
+
+// ---- lidar half of the two-kernel mode ---------------------------------------------------------------------------
+// One CTA works on `G` scenes at a time: poses (x, y, cos, sin per slot) + pair count + participant mask arrive with
+// one bulk copy per group, the 72-laser tile of every slot lives in shared memory, queued pairs are read straight
+// from HBM (coalesced, 2 bytes each).  Same pair set-up / laser distribution as the fused kernel; the tile leaves
+// with coalesced stores into the observation rows, optionally again as the policy's bf16 [hi | lo] operand.
+struct LidarIO {
+    const uint32_t* map;
+    const float* pose;
+    const uint16_t* pairs;
+    float* obs;
+    uint32_t* obs_split;
+    int pair_stride, kp, group, S, A, D;
+};
+
+__global__ void __launch_bounds__(ENV_MAX_THREADS, 3)
+env_lidar_kernel(const __grid_constant__ LidarIO io) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const int A = io.A, D = io.D, G = io.group;
+    const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, n_warps = NT >> 5;
+    const int n_ray = (int)io.map[M_NRAY];
+    const int rec = 4 * A + 4;                                    // floats per scene record
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    float2* s_ray = reinterpret_cast<float2*>(smem_raw + 16);
+    float* s_pose = reinterpret_cast<float*>(smem_raw + 16 + ((n_ray * 8 + 15) & ~15));
+    float* s_tile = s_pose + ((G * rec + 3) & ~3);                // [G][A][n_ray]
+    {
+        const float2* gr = reinterpret_cast<const float2*>(io.map + io.map[M_OFF_RAY]);
+        for (int k = tid; k < n_ray; k += NT) s_ray[k] = gr[k];
+    }
+    uint32_t parity = 0;
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    const int n_groups = (io.S + G - 1) / G;
+    const int lid0 = EGO_DIM + NAVI_DIM;
+    for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+        const int scene0 = grp * G;
+        const int ng = (io.S - scene0 < G) ? io.S - scene0 : G;
+        if (tid == 0) {
+            mbar_expect_tx(bar, (uint32_t)(ng * rec * 4));
+            bulk_g2s(s_pose, io.pose + (size_t)scene0 * rec, (uint32_t)(ng * rec * 4), bar);
+        }
+        mbar_wait(bar, parity);
+        parity ^= 1u;
+        // laser entries start at "nothing within range" for participants, 0 for empty rows
+        for (int idx = tid; idx < ng * A * n_ray; idx += NT) {
+            int row = idx / n_ray, sl = row / A, i = row - sl * A;
+            const uint32_t* hd = reinterpret_cast<const uint32_t*>(s_pose + sl * rec + 4 * A);
+            unsigned long long pm = (unsigned long long)hd[1] | ((unsigned long long)hd[2] << 32);
+            s_tile[idx] = ((pm >> i) & 1ull) ? 1.0f : 0.0f;
+        }
+        __syncthreads();
+        for (int sl = 0; sl < ng; ++sl) {
+            const float* ps = s_pose + sl * rec;
+            const int nq = (int)reinterpret_cast<const uint32_t*>(ps + 4 * A)[0];
+            const uint16_t* gq = io.pairs + (size_t)(scene0 + sl) * io.pair_stride;
+            float* tile = s_tile + (size_t)sl * A * n_ray;
+            for (int base = warp * 32; base < nq; base += n_warps * 32) {
+                const int e = base + lane;
+                PairGeom g;
+                g.nx1 = g.nx2 = g.ny1 = g.ny2 = g.cc = g.ss = 0.0f; g.k0 = 0; g.cnt = 0;
+                int lid_off = 0;
+                if (e < nq) {
+                    int code = gq[e];
+                    int oi = (code >> 6) & 63, oj = code & 63;
+                    lidar_pair_geom(ps[oi], ps[A + oi], ps[2 * A + oi], ps[3 * A + oi], ps[oj], ps[A + oj], ps[2 * A + oj],
+                                    ps[3 * A + oj], n_ray, g);
+                    lid_off = oi * n_ray;
+                }
+                int incl = g.cnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    int nb = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += nb;
+                }
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                const int excl = incl - g.cnt;
+                for (int r0 = 0; r0 < total; r0 += 32) {
+                    const int r = r0 + lane;
+                    const bool act = r < total;
+                    const int rr = act ? r : 0;
+                    int lo = 0;
+#pragma unroll
+                    for (int step = 16; step >= 1; step >>= 1) {
+                        int ex = __shfl_sync(0xffffffffu, excl, lo + step);
+                        if (ex <= rr) lo += step;
+                    }
+                    const int ex0 = __shfl_sync(0xffffffffu, excl, lo);
+                    const int k0 = __shfl_sync(0xffffffffu, g.k0, lo);
+                    const int off = __shfl_sync(0xffffffffu, lid_off, lo);
+                    const float nx1 = __shfl_sync(0xffffffffu, g.nx1, lo), nx2 = __shfl_sync(0xffffffffu, g.nx2, lo);
+                    const float ny1 = __shfl_sync(0xffffffffu, g.ny1, lo), ny2 = __shfl_sync(0xffffffffu, g.ny2, lo);
+                    const float cc = __shfl_sync(0xffffffffu, g.cc, lo), ss = __shfl_sync(0xffffffffu, g.ss, lo);
+                    if (act) {
+                        int k = k0 + (rr - ex0);
+                        k = (k >= n_ray) ? k - n_ray : k;
+                        float2 rd = s_ray[k];
+                        lidar_ray(nx1, nx2, ny1, ny2, cc, ss, rd.x, rd.y, tile + off + k);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // laser part of the observation rows
+        float* g_obs = io.obs + (size_t)scene0 * A * D;
+        for (int idx = tid; idx < ng * A * n_ray; idx += NT) {
+            int row = idx / n_ray, k = idx - row * n_ray;
+            g_obs[(size_t)row * D + lid0 + k] = s_tile[idx];
+        }
+        if (io.obs_split) {
+            // whole rows as the policy's [hi | lo] bf16 operand: lasers from the tile, the rest from the rows the state
+            // kernel wrote
+            const int half = io.kp >> 1;
+            uint32_t* g_sp = io.obs_split + (size_t)scene0 * A * io.kp;
+            for (int idx = tid; idx < ng * A * half; idx += NT) {
+                int row = idx / half, c2 = idx - row * half;
+                float v2[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    int k = 2 * c2 + u;
+                    float x = 0.0f;
+                    if (k < D) x = (k >= lid0 && k < lid0 + n_ray) ? s_tile[row * n_ray + (k - lid0)] : g_obs[(size_t)row * D + k];
+                    v2[u] = x;
+                }
+                __nv_bfloat16 h0 = __float2bfloat16_rn(v2[0]), h1 = __float2bfloat16_rn(v2[1]);
+                __nv_bfloat16 l0 = __float2bfloat16_rn(v2[0] - __bfloat162float(h0));
+                __nv_bfloat16 l1 = __float2bfloat16_rn(v2[1] - __bfloat162float(h1));
+                g_sp[(size_t)row * io.kp + c2] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                g_sp[(size_t)row * io.kp + half + c2] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+static size_t lidar_smem_bytes(int G, int A, int n_ray) {
+    size_t rec = 4 * A + 4;
+    return 16 + ((n_ray * 8 + 15) & ~15) + (((size_t)G * rec + 3) & ~(size_t)3) * 4 + (size_t)G * A * n_ray * 4 + 16;
 }
 
 }  // namespace b2c
@@ -327,6 +506,12 @@ struct b2c_env {
     EnvConfig cfg;
     int group;
     int threads;
+    int split;               // 1: two-kernel mode (state kernel + lidar kernel)
+    int lidar_group, lidar_threads;
+    size_t lidar_smem;
+    float* d_pose;
+    uint16_t* d_pairs;
+    int pair_stride, n_ray;
     uint32_t* d_map;
     uint32_t* d_state;
     int map_words;
@@ -364,25 +549,52 @@ int b2c_env_create(const b2c_env_config* c, const uint32_t* map_blob, int map_wo
     e->tile_words = NUM_FIELDS * k.AP + HEADER_WORDS;
     B2C_CUDA_OR(cudaGetDevice(&e->device), delete e);
     B2C_CUDA_OR(cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, e->device), delete e);
-    // scenes per CTA: one thread per slot in the per-slot phases, as many scenes as keep four CTAs per SM
-    // (measured on B200, profiles/r01_sweep.txt: small CTAs hide the phase barriers best)
+    // Launch shapes (measured on B200, profiles/r01_sweep.txt: small CTAs hide the phase barriers best).
+    //   fused mode: one thread per slot in the per-slot phases, as many scenes per CTA as keep four CTAs per SM
+    //   two-kernel mode (default from 16 slots up; B2C_ENV_SPLIT=0/1 overrides): the state kernel has no observation
+    //   tile, so it packs its 128 threads with slots (3 scenes of 40) at 7 CTAs per SM; the lidar kernel takes one
+    //   scene per CTA at 8+ CTAs per SM (profiles/r01_e_split_sweep.txt)
+    e->split = (c->num_slots >= 16) ? 1 : 0;       // small scenes (parking lot, 10 slots) are faster fused
+    if (const char* sp = getenv("B2C_ENV_SPLIT")) e->split = atoi(sp) ? 1 : 0;
     e->threads = 128;
     if (const char* t = getenv("B2C_ENV_THREADS")) e->threads = atoi(t);
-    if (e->threads < 32 || e->threads > ENV_MAX_THREADS || (e->threads & 31)) e->threads = 128;
+    if (e->threads < 32 || e->threads > (e->split ? 128 : ENV_MAX_THREADS) || (e->threads & 31)) e->threads = 128;
     while (e->threads < k.A) e->threads += 32;
     int fit = e->threads / k.A;
     if (fit > ENV_MAX_GROUP) fit = ENV_MAX_GROUP;
     if (fit > k.S) fit = k.S;
     if (fit < 1) { delete e; return b2c_set_error(B2C_ERR_ARG, "num_slots does not fit one CTA"); }
     e->group = fit;
-    while (e->group > 1 && smem_plan(e->group, k.A, k.D, map_words, e->tile_words, e->threads / 32).total > 56 * 1024) e->group -= 1;
+    const int smem_cap = e->split ? 36 * 1024 : 56 * 1024;
+    while (e->group > 1 && smem_plan(e->group, k.A, k.D, map_words, e->tile_words, e->threads / 32, e->split).total > smem_cap)
+        e->group -= 1;
     if (const char* g = getenv("B2C_ENV_GROUP")) {
         int gg = atoi(g);
         if (gg >= 1 && gg <= fit) e->group = gg;
     }
-    e->smem = (size_t)smem_plan(e->group, k.A, k.D, map_words, e->tile_words, e->threads / 32).total;
-    B2C_CUDA_OR(cudaFuncSetAttribute(env_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem),
-                delete e);
+    e->smem = (size_t)smem_plan(e->group, k.A, k.D, map_words, e->tile_words, e->threads / 32, e->split).total;
+    e->n_ray = (int)map_blob[M_NRAY];
+    e->d_pose = nullptr; e->d_pairs = nullptr;
+    if (e->split) {
+        B2C_CUDA_OR(cudaFuncSetAttribute(env_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem),
+                    delete e);
+        e->lidar_threads = 128;
+        if (const char* t = getenv("B2C_LIDAR_THREADS")) e->lidar_threads = atoi(t);
+        if (e->lidar_threads < 32 || e->lidar_threads > ENV_MAX_THREADS || (e->lidar_threads & 31)) e->lidar_threads = 128;
+        e->lidar_group = 1;
+        if (const char* g = getenv("B2C_LIDAR_GROUP")) e->lidar_group = atoi(g) > 0 ? atoi(g) : 1;
+        while (e->lidar_group > 1 && lidar_smem_bytes(e->lidar_group, k.A, e->n_ray) > 100 * 1024) e->lidar_group -= 1;
+        if (e->lidar_group > k.S) e->lidar_group = k.S;
+        e->lidar_smem = lidar_smem_bytes(e->lidar_group, k.A, e->n_ray);
+        B2C_CUDA_OR(cudaFuncSetAttribute(env_lidar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->lidar_smem),
+                    delete e);
+        e->pair_stride = (k.A * k.A + 7) & ~7;
+        B2C_CUDA_OR(cudaMalloc(&e->d_pose, (size_t)k.S * (4 * k.A + 4) * 4), delete e);
+        B2C_CUDA_OR(cudaMalloc(&e->d_pairs, (size_t)k.S * e->pair_stride * 2), delete e);
+    } else {
+        B2C_CUDA_OR(cudaFuncSetAttribute(env_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem),
+                    delete e);
+    }
     B2C_CUDA_OR(cudaMalloc(&e->d_map, (size_t)map_words * 4), delete e);
     B2C_CUDA_OR(cudaMalloc(&e->d_state, (size_t)k.S * e->tile_words * 4), delete e);
     B2C_CUDA_OR(cudaMemcpy(e->d_map, map_blob, (size_t)map_words * 4, cudaMemcpyHostToDevice), delete e);
@@ -395,6 +607,8 @@ int b2c_env_destroy(b2c_env* e) {
     if (!e) return B2C_OK;
     cudaFree(e->d_map);
     cudaFree(e->d_state);
+    cudaFree(e->d_pose);
+    cudaFree(e->d_pairs);
     delete e;
     return B2C_OK;
 }
@@ -415,6 +629,7 @@ static int launch_env(b2c_env* e, const float* actions, const b2c_env_io* o, int
     io.map_words = e->map_words; io.tile_words = e->tile_words;
     io.obs_bulk = ((((size_t)cfg.A * cfg.D * 4) % 16 == 0) && (((uintptr_t)o->obs) % 16 == 0)) ? 1 : 0;
     io.group = e->group;
+    io.pose = e->d_pose; io.pairs = e->d_pairs; io.pair_stride = e->pair_stride;
     int ctas_per_sm = (int)(227 * 1024 / (e->smem + 1024));
     int by_threads = 2048 / e->threads;
     if (ctas_per_sm > by_threads) ctas_per_sm = by_threads;
@@ -422,7 +637,24 @@ static int launch_env(b2c_env* e, const float* actions, const b2c_env_io* o, int
     int n_groups = (cfg.S + e->group - 1) / e->group;
     int grid = e->num_sms * ctas_per_sm;
     if (grid > n_groups) grid = n_groups;
-    env_step_kernel<<<grid, e->threads, e->smem, (cudaStream_t)stream>>>(cfg, io);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!e->split) {
+        env_step_kernel<false><<<grid, e->threads, e->smem, st>>>(cfg, io);
+    } else {
+        env_step_kernel<true><<<grid, e->threads, e->smem, st>>>(cfg, io);
+        B2C_CUDA(cudaGetLastError());
+        LidarIO li;
+        li.map = e->d_map; li.pose = e->d_pose; li.pairs = e->d_pairs; li.obs = o->obs; li.obs_split = io.obs_split;
+        li.pair_stride = e->pair_stride; li.kp = io.kp; li.group = e->lidar_group; li.S = cfg.S; li.A = cfg.A; li.D = cfg.D;
+        int lc = (int)(227 * 1024 / (e->lidar_smem + 1024));
+        int lt = 2048 / e->lidar_threads;
+        if (lc > lt) lc = lt;
+        if (lc < 1) lc = 1;
+        int lg = (cfg.S + e->lidar_group - 1) / e->lidar_group;
+        int lgrid = e->num_sms * lc;
+        if (lgrid > lg) lgrid = lg;
+        env_lidar_kernel<<<lgrid, e->lidar_threads, e->lidar_smem, st>>>(li);
+    }
     B2C_CUDA(cudaGetLastError());
     return B2C_OK;
 }

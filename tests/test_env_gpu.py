@@ -37,7 +37,10 @@ def _to_np(out):
     ("parking_lot", 33, 1, 40, dict()),                       # single-slot scenes, ragged last CTA group
     ("roundabout", 1, 3, 30, dict(force_lcf=0.5, delay_done=1)),
 ])
-def test_env_step_bit_exact(map_name, S, A, T, kw):
+@pytest.mark.parametrize("split", [0, 1])
+def test_env_step_bit_exact(map_name, S, A, T, kw, split, monkeypatch):
+    """split = 0: the fused single-kernel step; split = 1: state kernel + lidar kernel (B2C_ENV_SPLIT)."""
+    monkeypatch.setenv("B2C_ENV_SPLIT", str(split))
     from copo_b200.batched_env import BatchedDrivingEnv
     tables = build_map(map_name)
     cfg = osim.SimConfig(seed=11, **kw)
@@ -48,7 +51,8 @@ def test_env_step_bit_exact(map_name, S, A, T, kw):
                             delay_done=cfg.delay_done, horizon=cfg.horizon, agent_horizon=cfg.agent_horizon,
                             neighbours_distance=float(cfg.neighbours_distance),
                             mf_nei_distance=float(cfg.mf_nei_distance), allow_respawn=cfg.allow_respawn,
-                            auto_reset=cfg.auto_reset, append_lcf=cfg.append_lcf, lcf_uniform=cfg.lcf_uniform)
+                            auto_reset=cfg.auto_reset, append_lcf=cfg.append_lcf, lcf_uniform=cfg.lcf_uniform,
+                            force_lcf=float(cfg.force_lcf))
     r = ref.reset()
     g = _to_np(env.reset())
     sc.compare_outputs(r, g, "reset")
@@ -108,8 +112,10 @@ def test_env_full_size_properties():
         assert torch.equal(o[k], o2[k]), k
 
 
-def test_env_emits_the_policy_operand():
+@pytest.mark.parametrize("split", [0, 1])
+def test_env_emits_the_policy_operand(split, monkeypatch):
     """`obs_split` equals the [hi | lo] bf16 split of `obs` (bit for bit) - the env saves the policy a pass."""
+    monkeypatch.setenv("B2C_ENV_SPLIT", str(split))
     from copo_b200 import ops
     from copo_b200.batched_env import BatchedDrivingEnv
     for name, A in (("intersection", 40), ("tollgate", 40), ("parking_lot", 10)):
