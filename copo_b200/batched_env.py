@@ -52,6 +52,7 @@ class BatchedDrivingEnv:
         self.D = int(self.lib.b2c_env_obs_dim(self._h))
         self.tile_words = int(self.lib.b2c_env_state_words(self._h))
         self.split_width = int(self.lib.b2c_env_obs_split_width(self._h))
+        self.kernels_per_step = int(self.lib.b2c_env_kernels_per_step(self._h))
         self.num_agents = int(num_agents)
         self.lcf_mean, self.lcf_std, self.force_lcf = float(lcf_mean), float(lcf_std), float(force_lcf)
         self.out = self.alloc_outputs()
@@ -87,6 +88,7 @@ class BatchedDrivingEnv:
         assert tuple(actions.shape) == (self.S, self.A, 2), actions.shape
         io = self._io(out)
         _lib.check(self.lib.b2c_env_step(self._h, _lib.ptr(actions), ctypes.byref(io), _lib.stream_ptr()))
+        _lib.LAUNCHES += self.kernels_per_step - 1          # the launch counter counts kernels, not calls
         return out
 
     # -- host-buffer stepping (what a CPU-side caller of the reference's env.step sees) ---------------------

@@ -341,16 +341,20 @@ env_step_kernel(const __grid_constant__ EnvConfig cfg, const __grid_constant__ E
             // the same observations as the [hi | lo] bf16 operand of the policy's first layer (two columns per item)
             const int half = io.kp >> 1;
             uint32_t* g_sp = io.obs_split + (size_t)scene0 * A * io.kp;
-            for (int idx = tid; idx < ng * A * half; idx += NT) {
-                int row = idx / half, c2 = idx - row * half;
-                int k = 2 * c2;
-                float v0 = (k < D) ? s_obs[row * D + k] : 0.0f;
-                float v1 = (k + 1 < D) ? s_obs[row * D + k + 1] : 0.0f;
-                __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
-                __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0));
-                __nv_bfloat16 l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
-                g_sp[(size_t)row * io.kp + c2] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                g_sp[(size_t)row * io.kp + half + c2] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            const int lane = tid & 31, warp = tid >> 5;
+            for (int row = warp; row < ng * A; row += n_warps) {
+                const float* orow = s_obs + (size_t)row * D;
+                uint32_t* srow = g_sp + (size_t)row * io.kp;
+                for (int c2 = lane; c2 < half; c2 += 32) {
+                    int k = 2 * c2;
+                    float v0 = (k < D) ? orow[k] : 0.0f;
+                    float v1 = (k + 1 < D) ? orow[k + 1] : 0.0f;
+                    __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+                    __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0));
+                    __nv_bfloat16 l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
+                    srow[c2] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                    srow[half + c2] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                }
             }
         }
     }
@@ -401,12 +405,15 @@ env_lidar_kernel(const __grid_constant__ LidarIO io) {
         }
         mbar_wait(bar, parity);
         parity ^= 1u;
-        // laser entries start at "nothing within range" for participants, 0 for empty rows
-        for (int idx = tid; idx < ng * A * n_ray; idx += NT) {
-            int row = idx / n_ray, sl = row / A, i = row - sl * A;
+        // laser entries start at "nothing within range" for participants, 0 for empty rows (one warp per row)
+        for (int sl = 0; sl < ng; ++sl) {
             const uint32_t* hd = reinterpret_cast<const uint32_t*>(s_pose + sl * rec + 4 * A);
-            unsigned long long pm = (unsigned long long)hd[1] | ((unsigned long long)hd[2] << 32);
-            s_tile[idx] = ((pm >> i) & 1ull) ? 1.0f : 0.0f;
+            const unsigned long long pm = (unsigned long long)hd[1] | ((unsigned long long)hd[2] << 32);
+            for (int i = warp; i < A; i += n_warps) {
+                const float val = ((pm >> i) & 1ull) ? 1.0f : 0.0f;
+                float* trow = s_tile + (size_t)(sl * A + i) * n_ray;
+                for (int k = lane; k < n_ray; k += 32) trow[k] = val;
+            }
         }
         __syncthreads();
         for (int sl = 0; sl < ng; ++sl) {
@@ -460,32 +467,38 @@ env_lidar_kernel(const __grid_constant__ LidarIO io) {
             }
         }
         __syncthreads();
-        // laser part of the observation rows
+        // laser part of the observation rows, one warp per row (coalesced along the lasers)
         float* g_obs = io.obs + (size_t)scene0 * A * D;
-        for (int idx = tid; idx < ng * A * n_ray; idx += NT) {
-            int row = idx / n_ray, k = idx - row * n_ray;
-            g_obs[(size_t)row * D + lid0 + k] = s_tile[idx];
+        const int n_rows = ng * A;
+        for (int row = warp; row < n_rows; row += n_warps) {
+            const float* trow = s_tile + (size_t)row * n_ray;
+            float* orow = g_obs + (size_t)row * D + lid0;
+            for (int k = lane; k < n_ray; k += 32) orow[k] = trow[k];
         }
         if (io.obs_split) {
             // whole rows as the policy's [hi | lo] bf16 operand: lasers from the tile, the rest from the rows the state
             // kernel wrote
             const int half = io.kp >> 1;
             uint32_t* g_sp = io.obs_split + (size_t)scene0 * A * io.kp;
-            for (int idx = tid; idx < ng * A * half; idx += NT) {
-                int row = idx / half, c2 = idx - row * half;
-                float v2[2];
+            for (int row = warp; row < n_rows; row += n_warps) {
+                const float* trow = s_tile + (size_t)row * n_ray;
+                const float* orow = g_obs + (size_t)row * D;
+                uint32_t* srow = g_sp + (size_t)row * io.kp;
+                for (int c2 = lane; c2 < half; c2 += 32) {
+                    float v2[2];
 #pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    int k = 2 * c2 + u;
-                    float x = 0.0f;
-                    if (k < D) x = (k >= lid0 && k < lid0 + n_ray) ? s_tile[row * n_ray + (k - lid0)] : g_obs[(size_t)row * D + k];
-                    v2[u] = x;
+                    for (int u = 0; u < 2; ++u) {
+                        int k = 2 * c2 + u;
+                        float x = 0.0f;
+                        if (k < D) x = (k >= lid0 && k < lid0 + n_ray) ? trow[k - lid0] : orow[k];
+                        v2[u] = x;
+                    }
+                    __nv_bfloat16 h0 = __float2bfloat16_rn(v2[0]), h1 = __float2bfloat16_rn(v2[1]);
+                    __nv_bfloat16 l0 = __float2bfloat16_rn(v2[0] - __bfloat162float(h0));
+                    __nv_bfloat16 l1 = __float2bfloat16_rn(v2[1] - __bfloat162float(h1));
+                    srow[c2] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                    srow[half + c2] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
                 }
-                __nv_bfloat16 h0 = __float2bfloat16_rn(v2[0]), h1 = __float2bfloat16_rn(v2[1]);
-                __nv_bfloat16 l0 = __float2bfloat16_rn(v2[0] - __bfloat162float(h0));
-                __nv_bfloat16 l1 = __float2bfloat16_rn(v2[1] - __bfloat162float(h1));
-                g_sp[(size_t)row * io.kp + c2] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                g_sp[(size_t)row * io.kp + half + c2] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
             }
         }
         __syncthreads();
@@ -684,6 +697,7 @@ int b2c_env_set_num_agents(b2c_env* e, int n) {
     return B2C_OK;
 }
 int b2c_env_obs_dim(const b2c_env* e) { return e ? e->cfg.D : -1; }
+int b2c_env_kernels_per_step(const b2c_env* e) { return e ? (e->split ? 2 : 1) : -1; }
 int b2c_env_obs_split_width(const b2c_env* e) { return e ? 2 * ((e->cfg.D + 63) / 64 * 64) : -1; }
 int b2c_env_state_words(const b2c_env* e) { return e ? e->tile_words : -1; }
 int b2c_env_slots_padded(const b2c_env* e) { return e ? e->cfg.AP : -1; }

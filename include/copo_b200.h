@@ -90,6 +90,7 @@ int b2c_env_set_force_lcf(b2c_env* env, float value);
 int b2c_env_set_num_agents(b2c_env* env, int num_agents);   /* curriculum: ChangeNEnv, env_wrappers.py:450 */
 int b2c_env_obs_dim(const b2c_env* env);
 int b2c_env_obs_split_width(const b2c_env* env);
+int b2c_env_kernels_per_step(const b2c_env* env);            /* 1: fused kernel, 2: state kernel + lidar kernel */
 int b2c_env_state_words(const b2c_env* env);                /* u32 words per scene tile */
 int b2c_env_slots_padded(const b2c_env* env);
 int b2c_env_get_state(b2c_env* env, uint32_t* dst_host, void* stream);       /* synchronises the stream */
