@@ -120,21 +120,20 @@ __global__ void cc_obs_fuse_kernel(const float* __restrict__ obs, const float* _
     if (!valid || mode == 0) return;
     const size_t scene_row0 = row - (row % A);            // first slot of this (t, scene)
     if (mode == 1) {
-        unsigned long long m = mf_mask[row];
-        int cnt = 0;
-        for (unsigned long long mm = m; mm; mm &= mm - 1) {
-            int j = __ffsll((long long)mm) - 1;
-            if (flags[scene_row0 + j] & FLAG_VALID) ++cnt;
-        }
+        // neighbours that have a row at this t: lane j checks slot j and j + 32, the warp votes the mask together
+        const unsigned long long m = mf_mask[row];
+        const bool v0 = ((m >> lane) & 1ull) && lane < A && (flags[scene_row0 + lane] & FLAG_VALID);
+        const bool v1 = ((m >> (lane + 32)) & 1ull) && lane + 32 < A && (flags[scene_row0 + lane + 32] & FLAG_VALID);
+        const unsigned long long vm = (unsigned long long)__ballot_sync(0xffffffffu, v0) |
+                                      ((unsigned long long)__ballot_sync(0xffffffffu, v1) << 32);
+        const int cnt = __popcll(vm);
         if (cnt == 0) return;
         const float inv = 1.0f / (float)cnt;
         const int W = D + (counterfactual ? AD : 0);
         for (int d = lane; d < W; d += 32) {
             float s = 0.0f;
-            for (unsigned long long mm = m; mm; mm &= mm - 1) {
-                int j = __ffsll((long long)mm) - 1;
-                size_t r = scene_row0 + j;
-                if (!(flags[r] & FLAG_VALID)) continue;
+            for (unsigned long long mm = vm; mm; mm &= mm - 1) {
+                const size_t r = scene_row0 + (__ffsll((long long)mm) - 1);
                 s += (d < D) ? obs[r * D + d] : act[r * AD + (d - D)];
             }
             out[D + d] = s * inv;
@@ -213,8 +212,8 @@ int b2c_gae3(const b2c_gae_args* p, void* stream) {
 
 int b2c_lcf_mix_stats(const uint8_t* flags, const float* adv, const float* nei_adv, const float* step_lcf,
                       const float* global_adv, size_t rows, double* out5, void* stream) {
-    if (!adv || !out5 || (nei_adv && !step_lcf)) return b2c_set_error(B2C_ERR_ARG, "b2c_lcf_mix_stats: bad argument");
     if (rows == 0) return B2C_OK;
+    if (!adv || !out5 || (nei_adv && !step_lcf)) return b2c_set_error(B2C_ERR_ARG, "b2c_lcf_mix_stats: bad argument");
     lcf_mix_stats_kernel<<<grid_for(rows, 256), 256, 0, (cudaStream_t)stream>>>(flags, adv, nei_adv, step_lcf, global_adv,
                                                                                rows, out5);
     B2C_CUDA(cudaGetLastError());
@@ -224,8 +223,8 @@ int b2c_lcf_mix_stats(const uint8_t* flags, const float* adv, const float* nei_a
 int b2c_lcf_mix_apply(const uint8_t* flags, const float* adv, const float* nei_adv, const float* step_lcf,
                       float* global_adv, float* normalized_adv, size_t rows, float mean, float std, float gmean,
                       float gstd, void* stream) {
-    if (!adv || !normalized_adv) return b2c_set_error(B2C_ERR_ARG, "b2c_lcf_mix_apply: bad argument");
     if (rows == 0) return B2C_OK;
+    if (!adv || !normalized_adv) return b2c_set_error(B2C_ERR_ARG, "b2c_lcf_mix_apply: bad argument");
     float s = std > 1e-4f ? std : 1e-4f, gs = gstd > 1e-4f ? gstd : 1e-4f;      // max(1e-4, std): rllib standardized
     lcf_mix_apply_kernel<<<grid_for(rows, 256), 256, 0, (cudaStream_t)stream>>>(flags, adv, nei_adv, step_lcf, global_adv,
                                                                                normalized_adv, rows, mean, 1.0f / s,
@@ -237,6 +236,7 @@ int b2c_lcf_mix_apply(const uint8_t* flags, const float* adv, const float* nei_a
 int b2c_cc_obs_fuse(const float* obs, const float* actions, const uint8_t* flags, const uint64_t* mf_mask,
                     const int8_t* nei_list, float* cobs, size_t rows, int slots, int obs_dim, int act_dim, int cobs_dim,
                     int mode, int counterfactual, void* stream) {
+    if (rows == 0) return B2C_OK;
     if (!obs || !flags || !cobs || slots < 1 || mode < 0 || mode > 2)
         return b2c_set_error(B2C_ERR_ARG, "b2c_cc_obs_fuse: bad argument");
     int n_other = mode == 0 ? 0 : (mode == 1 ? 1 : 4);
@@ -244,7 +244,6 @@ int b2c_cc_obs_fuse(const float* obs, const float* actions, const uint8_t* flags
     if (cobs_dim != want) return b2c_set_error(B2C_ERR_ARG, "b2c_cc_obs_fuse: cobs_dim %d, expected %d (algo_ccppo.py:55-71)", cobs_dim, want);
     if ((mode == 1 && !mf_mask) || (mode == 2 && !nei_list) || (mode && counterfactual && !actions))
         return b2c_set_error(B2C_ERR_ARG, "b2c_cc_obs_fuse: missing neighbour columns");
-    if (rows == 0) return B2C_OK;
     size_t blocks = (rows + 7) / 8;
     cc_obs_fuse_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(obs, actions, flags, (const unsigned long long*)mf_mask,
                                                                           nei_list, cobs, rows, slots, obs_dim, act_dim,
@@ -255,8 +254,8 @@ int b2c_cc_obs_fuse(const float* obs, const float* actions, const uint8_t* flags
 
 int b2c_gather_rows(const float* src, size_t ld_src, const int64_t* idx, float* dst, size_t ld_dst, size_t rows, int width,
                     void* stream) {
-    if (!src || !idx || !dst || width < 1) return b2c_set_error(B2C_ERR_ARG, "b2c_gather_rows: bad argument");
     if (rows == 0) return B2C_OK;
+    if (!src || !idx || !dst || width < 1) return b2c_set_error(B2C_ERR_ARG, "b2c_gather_rows: bad argument");
     size_t blocks = (rows + 7) / 8;
     gather_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, ld_src, idx, dst, ld_dst, rows, width);
     B2C_CUDA(cudaGetLastError());
@@ -265,8 +264,8 @@ int b2c_gather_rows(const float* src, size_t ld_src, const int64_t* idx, float* 
 
 int b2c_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1,
                   float beta2, float eps, int step, float grad_scale, void* stream) {
-    if (!param || !grad || !exp_avg || !exp_avg_sq || step < 1) return b2c_set_error(B2C_ERR_ARG, "b2c_adam_step: bad argument");
     if (n == 0) return B2C_OK;
+    if (!param || !grad || !exp_avg || !exp_avg_sq || step < 1) return b2c_set_error(B2C_ERR_ARG, "b2c_adam_step: bad argument");
     double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
     adam_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, (float)(lr / bc1),
                                                                    (float)(1.0 / sqrt(bc2)), beta1, beta2, eps, grad_scale);
@@ -275,8 +274,8 @@ int b2c_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
 }
 
 int b2c_dot(const float* a, const float* b, size_t n, double* out, void* stream) {
-    if (!a || !b || !out) return b2c_set_error(B2C_ERR_ARG, "b2c_dot: null argument");
     if (n == 0) return B2C_OK;
+    if (!a || !b || !out) return b2c_set_error(B2C_ERR_ARG, "b2c_dot: null argument");
     dot_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(a, b, n, out);
     B2C_CUDA(cudaGetLastError());
     return B2C_OK;

@@ -160,8 +160,8 @@ extern "C" {
 
 int b2c_linear_forward(const float* x, int ldx, const float* W, const float* b, float* y, int ldy, int M, int K, int N,
                        int act, void* stream) {
-    if (!x || !W || !y || M < 0 || K < 1 || N < 1) return b2c_set_error(B2C_ERR_ARG, "b2c_linear_forward: bad argument");
     if (M == 0) return B2C_OK;
+    if (!x || !W || !y || M < 0 || K < 1 || N < 1) return b2c_set_error(B2C_ERR_ARG, "b2c_linear_forward: bad argument");
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, 1);
     cudaStream_t s = (cudaStream_t)stream;
     if (act == 1 && b) sgemm_kernel<false, true, EPI_BIAS_TANH><<<grid, NTHREADS, 0, s>>>(x, ldx, W, K, y, ldy, M, N, K, b, nullptr, 0, K);
@@ -174,8 +174,8 @@ int b2c_linear_forward(const float* x, int ldx, const float* W, const float* b, 
 
 int b2c_linear_backward_input(const float* dy, int ldy, const float* W, const float* h_prev, int ldh, float* dx, int ldx,
                               int M, int K, int N, void* stream) {
-    if (!dy || !W || !dx || M < 0) return b2c_set_error(B2C_ERR_ARG, "b2c_linear_backward_input: bad argument");
     if (M == 0) return B2C_OK;
+    if (!dy || !W || !dx || M < 0) return b2c_set_error(B2C_ERR_ARG, "b2c_linear_backward_input: bad argument");
     // dx[M x K] = dy[M x N] * W[N x K]   (reduction over N)
     dim3 grid((K + BN - 1) / BN, (M + BM - 1) / BM, 1);
     cudaStream_t s = (cudaStream_t)stream;
@@ -187,8 +187,8 @@ int b2c_linear_backward_input(const float* dy, int ldy, const float* W, const fl
 
 int b2c_linear_backward_weight(const float* dy, int ldy, const float* x, int ldx, float* dW, float* db, int M, int K,
                                int N, void* stream) {
-    if (!dy || !x || !dW || M < 0) return b2c_set_error(B2C_ERR_ARG, "b2c_linear_backward_weight: bad argument");
     if (M == 0) return B2C_OK;
+    if (!dy || !x || !dW || M < 0) return b2c_set_error(B2C_ERR_ARG, "b2c_linear_backward_weight: bad argument");
     // dW[N x K] += dy^T[N x M] * x[M x K]   (reduction over M, split over grid.z, atomics into dW)
     int chunk = 2048;
     int splits = (M + chunk - 1) / chunk;
@@ -207,8 +207,8 @@ int b2c_linear_backward_weight(const float* dy, int ldy, const float* x, int ldx
 }
 
 int b2c_colsum(const float* dy, int ldy, float* db, int M, int N, void* stream) {
-    if (!dy || !db || M < 0 || N < 1) return b2c_set_error(B2C_ERR_ARG, "b2c_colsum: bad argument");
     if (M == 0) return B2C_OK;
+    if (!dy || !db || M < 0 || N < 1) return b2c_set_error(B2C_ERR_ARG, "b2c_colsum: bad argument");
     int rows = 128;
     dim3 g2((N + 127) / 128, (M + rows - 1) / rows);
     colsum_kernel<<<g2, 128, 0, (cudaStream_t)stream>>>(dy, ldy, db, M, N, rows);

@@ -7,6 +7,7 @@
 //                                  policy losses inside CoPOPolicy.meta_update (algo_copo.py:250-272)
 //   lcf_meta_terms                 LCF side of the meta-gradient (algo_copo.py:280-287 with model.compute_coordinated
 //                                  algo_copo.py:155-161)
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -56,29 +57,47 @@ __global__ void head_forward_kernel(const float* __restrict__ h, int ldh, const 
 }
 
 // thread k of a CTA owns column k: dz[m][k] = (sum_j dy[m][j] W[j][k]) * (1 - h[m][k]^2), dW[j][k] += sum_m dy h,
-// db[j] += sum_m dy[m][j].  A CTA walks a contiguous chunk of rows.
+// db[j] += sum_m dy[m][j].  A CTA walks a contiguous chunk of rows, four rows in flight per thread; dz can also
+// leave as the [hi | lo] bf16 operand of the tensor-core kernels (dz_split [M][2 * K], K = 256).
 template <int NOUT>
 __global__ void head_backward_kernel(const float* __restrict__ dy, int ldy, const float* __restrict__ h, int ldh,
                                      const float* __restrict__ W, float* __restrict__ dz, int ldz,
-                                     float* __restrict__ dW, float* __restrict__ db, int M, int K, int rows,
-                                     int dtanh) {
+                                     uint16_t* __restrict__ dz_split, float* __restrict__ dW, float* __restrict__ db,
+                                     int M, int K, int rows, int dtanh) {
     const int k = blockIdx.y * blockDim.x + threadIdx.x;
     const int m_begin = blockIdx.x * rows, m_end = min(M, m_begin + rows);
     float w[NOUT], accw[NOUT], accb = 0.0f;
 #pragma unroll
     for (int j = 0; j < NOUT; ++j) { w[j] = (k < K) ? W[j * K + k] : 0.0f; accw[j] = 0.0f; }
-    for (int m = m_begin; m < m_end; ++m) {
-        float g[NOUT];
+    constexpr int U = 4;
+    for (int m0 = m_begin; m0 < m_end; m0 += U) {
+        float g[U][NOUT], hv[U];
 #pragma unroll
-        for (int j = 0; j < NOUT; ++j) g[j] = dy[(size_t)m * ldy + j];
-        if (k < K) {
-            float hv = h[(size_t)m * ldh + k];
-            float s = 0.0f;
+        for (int u = 0; u < U; ++u) {
+            const int m = m0 + u;
+            const bool in = m < m_end;
 #pragma unroll
-            for (int j = 0; j < NOUT; ++j) { s = fmaf(g[j], w[j], s); accw[j] = fmaf(g[j], hv, accw[j]); }
-            if (dz) dz[(size_t)m * ldz + k] = dtanh ? s * (1.0f - hv * hv) : s;
+            for (int j = 0; j < NOUT; ++j) g[u][j] = in ? dy[(size_t)m * ldy + j] : 0.0f;
+            hv[u] = (in && k < K) ? h[(size_t)m * ldh + k] : 0.0f;
         }
-        if (blockIdx.y == 0 && threadIdx.x < NOUT) accb += g[threadIdx.x];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int m = m0 + u;
+            if (m < m_end && k < K) {
+                float s = 0.0f;
+#pragma unroll
+                for (int j = 0; j < NOUT; ++j) { s = fmaf(g[u][j], w[j], s); accw[j] = fmaf(g[u][j], hv[u], accw[j]); }
+                const float z = dtanh ? s * (1.0f - hv[u] * hv[u]) : s;
+                if (dz) dz[(size_t)m * ldz + k] = z;
+                if (dz_split) {
+                    __nv_bfloat16 hi = __float2bfloat16_rn(z);
+                    __nv_bfloat16 lo = __float2bfloat16_rn(z - __bfloat162float(hi));
+                    dz_split[(size_t)m * 2 * K + k] = __bfloat16_as_ushort(hi);
+                    dz_split[(size_t)m * 2 * K + K + k] = __bfloat16_as_ushort(lo);
+                }
+            }
+            if (blockIdx.y == 0 && threadIdx.x < NOUT && m < m_end) accb += g[u][threadIdx.x];
+        }
     }
     if (k < K && dW) {
 #pragma unroll
@@ -218,9 +237,9 @@ extern "C" {
 
 int b2c_head_forward(const float* h, int ldh, const float* W, const float* b, float* y, int ldy, int M, int K, int N,
                      void* stream) {
+    if (M == 0) return B2C_OK;
     if (!h || !W || !y || N < 1 || N > HEAD_MAX_N || K < 1 || K > 4096)
         return b2c_set_error(B2C_ERR_ARG, "b2c_head_forward: N must be in [1, 8], K in [1, 4096]");
-    if (M == 0) return B2C_OK;
     int grid = (M + 7) / 8;
     if (grid > 148 * 16) grid = 148 * 16;
     size_t smem = (size_t)N * K * sizeof(float);
@@ -234,12 +253,18 @@ int b2c_head_forward(const float* h, int ldh, const float* W, const float* b, fl
 
 int b2c_head_backward(const float* dy, int ldy, const float* h, int ldh, const float* W, float* dz, int ldz, float* dW,
                       float* db, int M, int K, int N, int dtanh, void* stream) {
-    if (!dy || !h || !W || N < 1 || N > HEAD_MAX_N) return b2c_set_error(B2C_ERR_ARG, "b2c_head_backward: bad argument");
+    return b2c_head_backward_split(dy, ldy, h, ldh, W, dz, ldz, nullptr, dW, db, M, K, N, dtanh, stream);
+}
+
+int b2c_head_backward_split(const float* dy, int ldy, const float* h, int ldh, const float* W, float* dz, int ldz,
+                            uint16_t* dz_split, float* dW, float* db, int M, int K, int N, int dtanh, void* stream) {
     if (M == 0) return B2C_OK;
+    if (!dy || !h || !W || N < 1 || N > HEAD_MAX_N) return b2c_set_error(B2C_ERR_ARG, "b2c_head_backward: bad argument");
+    if (dz_split && (K % 64)) return b2c_set_error(B2C_ERR_ARG, "b2c_head_backward: dz_split needs K to be a multiple of 64");
     int rows = 256;
     dim3 grid((M + rows - 1) / rows, (K + 255) / 256);
     cudaStream_t s = (cudaStream_t)stream;
-#define B2C_HB(n) case n: head_backward_kernel<n><<<grid, 256, 0, s>>>(dy, ldy, h, ldh, W, dz, ldz, dW, db, M, K, rows, dtanh); break;
+#define B2C_HB(n) case n: head_backward_kernel<n><<<grid, 256, 0, s>>>(dy, ldy, h, ldh, W, dz, ldz, dz_split, dW, db, M, K, rows, dtanh); break;
     switch (N) { B2C_HB(1) B2C_HB(2) B2C_HB(3) B2C_HB(4) B2C_HB(5) B2C_HB(6) B2C_HB(7) B2C_HB(8) }
 #undef B2C_HB
     B2C_CUDA(cudaGetLastError());
@@ -248,8 +273,8 @@ int b2c_head_backward(const float* dy, int ldy, const float* h, int ldh, const f
 
 int b2c_gaussian_sample(const float* logits, const float* eps_in, float* actions, float* logp, float* eps_out, int M,
                         uint32_t seed, uint32_t step, int deterministic, void* stream) {
-    if (!logits || !actions) return b2c_set_error(B2C_ERR_ARG, "b2c_gaussian_sample: null argument");
     if (M == 0) return B2C_OK;
+    if (!logits || !actions) return b2c_set_error(B2C_ERR_ARG, "b2c_gaussian_sample: null argument");
     gaussian_sample_kernel<<<(M + 255) / 256, 256, 0, (cudaStream_t)stream>>>(logits, eps_in, actions, logp, eps_out, M,
                                                                               seed, step, deterministic);
     B2C_CUDA(cudaGetLastError());
@@ -257,12 +282,12 @@ int b2c_gaussian_sample(const float* logits, const float* eps_in, float* actions
 }
 
 int b2c_ppo_head(const b2c_ppo_head_args* p, void* stream) {
+    if (p && p->rows == 0) return B2C_OK;
     if (!p || !p->logits || !p->actions || !p->dlogits || p->n_heads < 0 || p->n_heads > 3)
         return b2c_set_error(B2C_ERR_ARG, "b2c_ppo_head: bad argument");
     if (p->mode == 0 && (!p->old_logp || !p->adv)) return b2c_set_error(B2C_ERR_ARG, "b2c_ppo_head: missing columns");
     if (p->mode == 0 && p->kl_coeff > 0.0f && !p->old_logits)
         return b2c_set_error(B2C_ERR_ARG, "b2c_ppo_head: kl_coeff > 0 needs the behaviour distribution inputs");
-    if (p->rows == 0) return B2C_OK;
     PpoHeadArgs a;
     a.logits = p->logits; a.actions = p->actions; a.old_logp = p->old_logp; a.old_logits = p->old_logits; a.adv = p->adv;
     for (int h = 0; h < 3; ++h) {
@@ -280,8 +305,8 @@ int b2c_ppo_head(const b2c_ppo_head_args* p, void* stream) {
 
 int b2c_lcf_meta_terms(const float* adv, const float* nei_adv, const float* eps, int rows, float lcf_mean, float lcf_std,
                        double* out3, void* stream) {
-    if (!adv || !nei_adv || !eps || !out3) return b2c_set_error(B2C_ERR_ARG, "b2c_lcf_meta_terms: null argument");
     if (rows == 0) return B2C_OK;
+    if (!adv || !nei_adv || !eps || !out3) return b2c_set_error(B2C_ERR_ARG, "b2c_lcf_meta_terms: null argument");
     lcf_meta_terms_kernel<<<(rows + 255) / 256, 256, 0, (cudaStream_t)stream>>>(adv, nei_adv, eps, rows, lcf_mean, lcf_std,
                                                                                out3);
     B2C_CUDA(cudaGetLastError());

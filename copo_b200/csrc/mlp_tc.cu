@@ -586,8 +586,8 @@ extern "C" {
 int b2c_tc_padded_k(int K) { return (K + BLOCK_K - 1) / BLOCK_K * BLOCK_K; }
 
 int b2c_tc_split_rows(const float* x, int ldx, uint16_t* out, int M, int K, int Kp, void* stream) {
-    if (!x || !out || K < 1 || Kp < K || Kp % BLOCK_K) return b2c_set_error(B2C_ERR_ARG, "b2c_tc_split_rows: bad argument");
     if (M == 0) return B2C_OK;
+    if (!x || !out || K < 1 || Kp < K || Kp % BLOCK_K) return b2c_set_error(B2C_ERR_ARG, "b2c_tc_split_rows: bad argument");
     size_t total = (size_t)M * Kp;
     int grid = (int)((total + 255) / 256 > 148 * 32 ? 148 * 32 : (total + 255) / 256);
     split_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, out, M, K, Kp);
@@ -610,6 +610,7 @@ static int tc_linear_launch(const uint16_t* a_split, const uint16_t* w_prep, con
 
 int b2c_tc_linear(const uint16_t* a_split, const uint16_t* w_prep, const float* bias, const float* dtanh_src, int ld_src,
                   float* out_f32, int ld_out, uint16_t* out_split, int M, int Kp, int act, void* stream) {
+    if (M == 0) return B2C_OK;
     if (!out_f32 && !out_split) return b2c_set_error(B2C_ERR_ARG, "b2c_tc_linear: no output requested");
     return tc_linear_launch(a_split, w_prep, bias, dtanh_src, ld_src, out_f32, ld_out, out_split, M, Kp, act, nullptr,
                             stream);
@@ -617,6 +618,7 @@ int b2c_tc_linear(const uint16_t* a_split, const uint16_t* w_prep, const float* 
 
 int b2c_tc_linear_head(const uint16_t* a_split, const uint16_t* w_prep, const float* bias, float* out_f32, int ld_out,
                        int M, int Kp, int act, const b2c_tc_head* head, void* stream) {
+    if (M == 0) return B2C_OK;
     if (!head || !head->weight || !head->bias || !head->out || (head->n != 1 && head->n != 4))
         return b2c_set_error(B2C_ERR_ARG, "b2c_tc_linear_head: the fused output layer needs weight, bias, out and n in {1, 4}");
     if (head->actions && head->n != 4) return b2c_set_error(B2C_ERR_ARG, "b2c_tc_linear_head: sampling needs the 4 policy logits");
@@ -628,13 +630,13 @@ int b2c_tc_linear_head(const uint16_t* a_split, const uint16_t* w_prep, const fl
 static int tc_linear_launch(const uint16_t* a_split, const uint16_t* w_prep, const float* bias, const float* dtanh_src,
                             int ld_src, float* out_f32, int ld_out, uint16_t* out_split, int M, int Kp, int act,
                             const b2c_tc_head* head, void* stream) {
+    if (M == 0) return B2C_OK;
     if (!a_split || !w_prep || Kp < BLOCK_K || Kp % BLOCK_K || M < 0)
         return b2c_set_error(B2C_ERR_ARG, "b2c_tc_linear: bad argument");
     if (((uintptr_t)a_split | (uintptr_t)w_prep | (uintptr_t)out_f32 | (uintptr_t)out_split | (uintptr_t)dtanh_src) & 15)
         return b2c_set_error(B2C_ERR_ARG, "b2c_tc_linear: pointers must be 16-byte aligned");
     if ((out_f32 && (ld_out & 3)) || (dtanh_src && (ld_src & 3)))
         return b2c_set_error(B2C_ERR_ARG, "b2c_tc_linear: row strides must be multiples of 4 floats");
-    if (M == 0) return B2C_OK;
     static int attr_set = 0;
     static int num_sms = 0;
     if (!attr_set) {
@@ -674,9 +676,9 @@ int b2c_tc_wgrad_parts(void) {
 
 int b2c_tc_wgrad(const uint16_t* dz_split, const uint16_t* x_split, float* workspace, float* dW, int M, int K, int Kp,
                  void* stream) {
+    if (M == 0) return B2C_OK;
     if (!dz_split || !x_split || !workspace || !dW || Kp < BLOCK_K || Kp > 256 || Kp % BLOCK_K || K > Kp || M < 0)
         return b2c_set_error(B2C_ERR_ARG, "b2c_tc_wgrad: bad argument (Kp must be 64..256)");
-    if (M == 0) return B2C_OK;
     static int attr_set = 0;
     static int num_sms = 0;
     if (!attr_set) {

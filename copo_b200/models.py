@@ -91,14 +91,18 @@ class _Net:
             h = ops.linear_forward(h, self.W[k], self.b[k], 0 if last else 1)
         return h
 
-    def forward_train(self, x, tc_version=None):
+    def forward_train(self, x, tc_version=None, x_split=None):
         if tc_version is not None and self.tc_ok():
             w1, w2, _ = self.tc_weights(tc_version)
-            s0 = ops.tc_split_rows(x)
+            s0 = x_split if x_split is not None else ops.tc_split_rows(x)
             h1, s1 = ops.tc_linear(s0, w1, self.b[0], act=1, want_f32=True, want_split=True)
-            h2, _ = ops.tc_linear(s1, w2, self.b[1], act=1)
+            if self.out_dim in (1, 4):   # output layer in the layer-2 epilogue; h2 is kept for the backward pass
+                out, _, _, h2 = ops.tc_linear_head(s1, w2, self.b[1], self.W[2], self.b[2], act=1, want_f32=True)
+            else:
+                h2, _ = ops.tc_linear(s1, w2, self.b[1], act=1)
+                out = ops.linear_forward(h2, self.W[2], self.b[2], 0)
             # the [hi | lo] operands are kept: the weight gradients read them again
-            return [x, h1, h2, ops.linear_forward(h2, self.W[2], self.b[2], 0), s0, s1]
+            return [x, h1, h2, out, s0, s1]
         acts = [x]
         for k in range(len(self.shapes)):
             last = k == len(self.shapes) - 1
@@ -109,9 +113,9 @@ class _Net:
         """Accumulates dW / db of every layer given d(loss)/d(out)."""
         if tc_version is not None and self.tc_ok():
             x, h1, h2, _, s0, s1 = acts
-            dz2 = ops.linear_backward(dout, h2, self.W[2], self.dW[2], self.db[2], h_prev_is_tanh=True)
+            # output layer backward also emits dz2 as the tensor-core operand
+            dz2, dz2s = ops.head_backward_split(dout, h2, self.W[2], self.dW[2], self.db[2])
             # layer 2: input gradient and weight gradient on the tensor cores from the same [hi | lo] operand
-            dz2s = ops.tc_split_rows(dz2)
             dz1, dz1s = ops.tc_linear(dz2s, self.tc_weights(tc_version)[2], None, act=0, dtanh_src=h1, want_split=True)
             ops.tc_wgrad(dz2s, s1, self.dW[1])
             ops.colsum(dz2, self.db[1])

@@ -66,6 +66,18 @@ def linear_forward(x, W, b, act, out=None):
     return y
 
 
+def head_backward_split(dy, h, W, dW, db):
+    """Backward of a narrow output layer on tanh activations h: returns (dz fp32, dz as [hi | lo] bf16)."""
+    lib = _lib_ready()
+    pdy, M, N, ldy = _rows2d(dy)
+    ph, _, K, ldh = _rows2d(h)
+    dz = torch.empty((M, K), dtype=torch.float32, device=dy.device)
+    dzs = torch.empty((M, 2 * K), dtype=torch.bfloat16, device=dy.device)
+    _lib.check(lib.b2c_head_backward_split(pdy, c_int(ldy), ph, c_int(ldh), P(W), P(dz), c_int(K), P(dzs), P(dW), P(db),
+                                           c_int(M), c_int(K), c_int(N), c_int(1), _lib.stream_ptr()))
+    return dz, dzs
+
+
 def linear_backward(dy, x, W, dW, db, h_prev_is_tanh, need_dx=True, dx_out=None):
     """Backward of y = x W^T + b given dy.  Accumulates dW / db; returns dz_prev = (dy W) * (1 - x^2) when x is a tanh
     output (h_prev_is_tanh), else dy W; None when need_dx is False."""

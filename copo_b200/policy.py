@@ -127,10 +127,21 @@ class IPPOPolicy:
         B = train_batch[OBS].shape[0]
         pol = model.nets["policy"]
         tc = model._tc()
-        acts_p = pol.forward_train(train_batch[OBS], tc)
+        # one [hi | lo] operand split per distinct input tensor (CoPO: obs is the critic input of all four networks)
+        splits = {}
+
+        def split_of(t):
+            if tc is None:
+                return None
+            key = (t.data_ptr(), tuple(t.shape))
+            if key not in splits:
+                splits[key] = ops.tc_split_rows(t)
+            return splits[key]
+
+        acts_p = pol.forward_train(train_batch[OBS], tc, split_of(train_batch[OBS]))
         head_acts, heads = [], []
         for net_name, in_col, old_col, tgt_col in self._heads(train_batch):
-            acts = model.nets[net_name].forward_train(train_batch[in_col], tc)
+            acts = model.nets[net_name].forward_train(train_batch[in_col], tc, split_of(train_batch[in_col]))
             head_acts.append((net_name, acts))
             heads.append((acts[3].reshape(-1), train_batch[old_col], train_batch[tgt_col]))
         dlogits, dvs, st = ops.ppo_head(acts_p[3], train_batch[ACTIONS], train_batch[ACTION_LOGP],

@@ -119,6 +119,9 @@ int b2c_head_forward(const float* h, int ldh, const float* W, const float* b, fl
 /* dz[M][K] = (dy W) * (dtanh ? 1 - h^2 : 1), dW += dy^T h, db += colsum(dy); dz / dW / db may be NULL */
 int b2c_head_backward(const float* dy, int ldy, const float* h, int ldh, const float* W, float* dz, int ldz, float* dW,
                       float* db, int M, int K, int N, int dtanh, void* stream);
+/* same, and dz also as the [hi | lo] bf16 operand of the tensor-core kernels (dz_split [M][2*K], K % 64 == 0) */
+int b2c_head_backward_split(const float* dy, int ldy, const float* h, int ldh, const float* W, float* dz, int ldz,
+                            uint16_t* dz_split, float* dW, float* db, int M, int K, int N, int dtanh, void* stream);
 /* TorchDiagGaussian (rllib): logits = (mean[2] | log_std[2]); action = mean + exp(log_std) * eps, logp(action).
  * eps_in NULL: standard normals from the counter-based generator keyed by (seed, step, row); eps_out optional. */
 int b2c_gaussian_sample(const float* logits, const float* eps_in, float* actions, float* logp, float* eps_out, int M,
