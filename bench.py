@@ -327,9 +327,12 @@ def run_gpu(args):
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get("dram_bytes_per_launch")
     env_roof = {"bound": "hbm", "achieved": env_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": env_gbs / hbm_peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": "env_step_kernel",
+                "traffic": traffic, "peak_source": peak_src,
+                "kernel": "scene step: env_step_kernel<state> + env_lidar_kernel (two launches, timed together)"
+                          if env.kernels_per_step == 2 else "env_step_kernel (fused)",
                 "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": env_ms,
-                "note": "issue-bound (72-laser lidar + neighbour search): see profiles/ for the instruction mix"}
+                "note": "issue-bound, not HBM-bound (72-laser lidar + neighbour search are ALU work): see profiles/ for the "
+                        "instruction mix and issue-slot utilisation"}
     mlp_roof = {"bound": "tensor", "achieved": l2_tf, "peak": tc_peak, "unit": "TFLOP/s", "frac": l2_tf / tc_peak,
                 "traffic": None, "peak_source": peak_src, "kernel": "tc_linear_kernel (256x256 layer, bf16_split)",
                 "algorithmic_flops_per_launch": l2_flops, "kernel_ms": l2_ms, "tensor_flops_issued": 4 * l2_flops,
@@ -348,8 +351,9 @@ def run_gpu(args):
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "CoPO Intersection 40 agents x %d scenes per GPU, one rollout step: policy MLP forward "
-                               "(92-256-256-4, tcgen05 bf16_split) + Gaussian sample + fused scene step (dynamics, "
-                               "crash/out/arrive, respawn, neighbours + nei/global reward, 72-laser lidar obs + LCF)"
+                               "(92-256-256-4, tcgen05 split-bf16, logits + Gaussian sample in the layer-2 epilogue) + "
+                               "scene step (dynamics, crash/out/arrive, respawn, neighbours + nei/global reward, "
+                               "72-laser lidar obs + LCF)"
                                % S, "map": MAP, "agents_per_scene": A, "scenes_per_gpu": S, "obs_dim": D,
                    "actions": "sampled from the randomly initialised policy (normc init, seed %d)" % args.seed,
                    "l2": "flushed between steps with a 256 MiB write, outside the timed events",
