@@ -91,6 +91,11 @@ class BatchedDrivingEnv:
         _lib.LAUNCHES += self.kernels_per_step - 1          # the launch counter counts kernels, not calls
         return out
 
+    def relaunch_lidar(self, out=None):
+        """Two-kernel mode: runs the lidar kernel again on the last step's poses / pairs (same result; for timing)."""
+        io = self._io(out if out is not None else self.out)
+        _lib.check(self.lib.b2c_env_relaunch_lidar(self._h, ctypes.byref(io), _lib.stream_ptr()))
+
     # -- host-buffer stepping (what a CPU-side caller of the reference's env.step sees) ---------------------
     HOST_KEYS = ("obs", "reward", "flags", "nei_mask", "nei_reward", "global_reward", "nei_list", "agent_id", "lcf",
                  "scene_done")

@@ -626,6 +626,21 @@ int b2c_env_destroy(b2c_env* e) {
     return B2C_OK;
 }
 
+static void launch_lidar(b2c_env* e, float* obs, uint32_t* obs_split, int kp, cudaStream_t st) {
+    const EnvConfig& cfg = e->cfg;
+    LidarIO li;
+    li.map = e->d_map; li.pose = e->d_pose; li.pairs = e->d_pairs; li.obs = obs; li.obs_split = obs_split;
+    li.pair_stride = e->pair_stride; li.kp = kp; li.group = e->lidar_group; li.S = cfg.S; li.A = cfg.A; li.D = cfg.D;
+    int lc = (int)(227 * 1024 / (e->lidar_smem + 1024));
+    int lt = 2048 / e->lidar_threads;
+    if (lc > lt) lc = lt;
+    if (lc < 1) lc = 1;
+    int lg = (cfg.S + e->lidar_group - 1) / e->lidar_group;
+    int lgrid = e->num_sms * lc;
+    if (lgrid > lg) lgrid = lg;
+    env_lidar_kernel<<<lgrid, e->lidar_threads, e->lidar_smem, st>>>(li);
+}
+
 static int launch_env(b2c_env* e, const float* actions, const b2c_env_io* o, int do_reset, int new_episode,
                       void* stream) {
     if (!e || !o || !o->obs || !o->reward || !o->flags)
@@ -656,17 +671,7 @@ static int launch_env(b2c_env* e, const float* actions, const b2c_env_io* o, int
     } else {
         env_step_kernel<true><<<grid, e->threads, e->smem, st>>>(cfg, io);
         B2C_CUDA(cudaGetLastError());
-        LidarIO li;
-        li.map = e->d_map; li.pose = e->d_pose; li.pairs = e->d_pairs; li.obs = o->obs; li.obs_split = io.obs_split;
-        li.pair_stride = e->pair_stride; li.kp = io.kp; li.group = e->lidar_group; li.S = cfg.S; li.A = cfg.A; li.D = cfg.D;
-        int lc = (int)(227 * 1024 / (e->lidar_smem + 1024));
-        int lt = 2048 / e->lidar_threads;
-        if (lc > lt) lc = lt;
-        if (lc < 1) lc = 1;
-        int lg = (cfg.S + e->lidar_group - 1) / e->lidar_group;
-        int lgrid = e->num_sms * lc;
-        if (lgrid > lg) lgrid = lg;
-        env_lidar_kernel<<<lgrid, e->lidar_threads, e->lidar_smem, st>>>(li);
+        launch_lidar(e, o->obs, io.obs_split, io.kp, st);
     }
     B2C_CUDA(cudaGetLastError());
     return B2C_OK;
@@ -694,6 +699,13 @@ int b2c_env_set_force_lcf(b2c_env* e, float v) {
 int b2c_env_set_num_agents(b2c_env* e, int n) {
     if (!e || n < 1 || n > e->cfg.A) return b2c_set_error(B2C_ERR_ARG, "set_num_agents: out of range");
     e->cfg.num_agents = n;
+    return B2C_OK;
+}
+int b2c_env_relaunch_lidar(b2c_env* e, const b2c_env_io* o, void* stream) {
+    if (!e || !o || !o->obs) return b2c_set_error(B2C_ERR_ARG, "b2c_env_relaunch_lidar: null argument");
+    if (!e->split) return b2c_set_error(B2C_ERR_STATE, "b2c_env_relaunch_lidar: the env runs the fused kernel");
+    launch_lidar(e, o->obs, (uint32_t*)o->obs_split, (e->cfg.D + 63) / 64 * 64, (cudaStream_t)stream);
+    B2C_CUDA(cudaGetLastError());
     return B2C_OK;
 }
 int b2c_env_obs_dim(const b2c_env* e) { return e ? e->cfg.D : -1; }

@@ -88,6 +88,8 @@ int b2c_env_step(b2c_env* env, const float* actions /* [S][A][2] */, const b2c_e
 int b2c_env_set_lcf_dist(b2c_env* env, float mean, float std);
 int b2c_env_set_force_lcf(b2c_env* env, float value);
 int b2c_env_set_num_agents(b2c_env* env, int num_agents);   /* curriculum: ChangeNEnv, env_wrappers.py:450 */
+/* two-kernel mode only: runs the lidar kernel again on the poses / pairs of the last step (idempotent; profiling) */
+int b2c_env_relaunch_lidar(b2c_env* env, const b2c_env_io* out, void* stream);
 int b2c_env_obs_dim(const b2c_env* env);
 int b2c_env_obs_split_width(const b2c_env* env);
 int b2c_env_kernels_per_step(const b2c_env* env);            /* 1: fused kernel, 2: state kernel + lidar kernel */
