@@ -262,8 +262,7 @@ def run_gpu(args):
     w1, w2, _ = net.tc_weights(pol.model.weights_version)
     a1 = ops.tc_split_rows(obs[0])
     _, s1 = ops.tc_linear(a1, w1, net.b[0], act=1, want_f32=False, want_split=True)
-    h2 = torch.empty((N, 256), device=dev)
-    l2_ms = time_kernel(lambda: ops.tc_linear(s1, w2, net.b[1], act=1, out_f32=h2))
+    l2_ms = time_kernel(lambda: ops.tc_linear_head(s1, w2, net.b[1], net.W[2], net.b[2], act=1, sample=(1, 1)))
     l1_ms = time_kernel(lambda: ops.tc_linear(a1, w1, net.b[0], act=1, want_f32=False, out_split=s1, want_split=True))
 
     # ---- end to end, host in the loop: pinned host actions -> device, scene step, every env output -> pinned host,
