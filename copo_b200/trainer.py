@@ -82,6 +82,15 @@ class IPPOTrainer:
         self.env.reset(out=first)
         self.ro[P.OBS][0].copy_(self.env.out["obs"].reshape(self.N, -1))
 
+    def reset_scenes(self):
+        """Restarts every scene (new episode) - used by the curriculum after a population change."""
+        first = dict(self.env.out)
+        if self._split:
+            first["obs_split"] = self._split[self._step_counter % 2]
+        self.env.reset(out=first, new_episode=True)
+        slot = self.T if self._iteration > 0 else 0
+        self.ro[P.OBS][slot].copy_(self.env.out["obs"].reshape(self.N, -1))
+
     def get_policy(self, policy_id="default"):
         return self.policy
 

@@ -139,3 +139,20 @@ def test_batched_evaluation_of_a_shipped_policy():
     total = res["success_rate"] + res["crash_rate"] + res["out_rate"] + res["max_step_rate"]
     assert 0.99 <= total <= 2.0              # an agent can crash and leave the road in the same step
     assert res["agent_steps"] > 16 * 20 * 100 and res["velocity_step_mean_episode_max"] > 1.0
+
+
+def test_curriculum_changes_the_population_by_slot_masking():
+    from copo_b200 import trainer as T
+    from copo_b200.curriculum import ChangeNCallback
+    tr = T.IPPOTrainer(dict(env="MultiAgentIntersectionEnv", num_scenes=8, rollout_fragment_length=10,
+                            sgd_minibatch_size=1024, num_sgd_iter=1, env_config={"num_agents": 20}, seed=0))
+    cb = ChangeNCallback(total_time_step=8 * 10 * 8, target_num_agents=20)
+    pops = []
+    for it in range(8):
+        res = tr.train()
+        cb.on_train_result(tr, res)
+        valid = (tr.ro["flags"] & 1) > 0
+        pops.append(int(valid.view(10, 8, 20).sum(2).max()))
+    assert [n for _, n in cb.history] == [5, 10, 15, 20]
+    assert pops[1] <= 5 and pops[3] <= 10 and pops[-1] > 10      # the next fragment runs with the new population
+    tr.stop()
