@@ -37,7 +37,9 @@ struct EnvIO {
     uint32_t* obs_split;   // [S][A][kp] bf16 pairs: the policy's tensor-core operand ([hi | lo], mlp_tc.cu), or null
     int kp;                // padded observation width (multiple of 64)
     // two-kernel mode: the state kernel hands these to the lidar kernel
-    float* pose;           // [S][4 * A + 4]: x[A], y[A], cos[A], sin[A], then {pair count, part mask lo, hi, 0}
+    float* pose;           // [S][rec_words]: x[A], y[A], cos[A], sin[A], {pair count, part mask lo, hi, 0}, then the
+                           // non-laser observation columns [D - n_ray][A]
+    int rec_words;
     uint16_t* pairs;       // [S][pair_stride]: queued (observer << 6 | box) lidar pairs
     int pair_stride;
     int map_words;
@@ -130,7 +132,8 @@ env_step_kernel(const __grid_constant__ EnvConfig cfg, const __grid_constant__ E
     auto view = [&](int sl) {
         SceneView v;
         v.map = s_map; v.st = s_st + sl * io.tile_words;
-        v.obs = SPLIT ? io.obs + (size_t)(scene_base + sl) * A * D : s_obs + (size_t)sl * A * D;
+        v.obs = SPLIT ? io.pose + (size_t)(scene_base + sl) * io.rec_words + 4 * A + 4 : s_obs + (size_t)sl * A * D;
+        v.obs_compact = SPLIT ? 1 : 0;
         float* f = s_f + sl * 6 * A;
         v.cs = f; v.sn = f + A; v.rew = f + 2 * A; v.long_last = f + 3 * A; v.loc_s = f + 4 * A; v.loc_l = f + 5 * A;
         int* q = s_i + sl * (4 * A + MAX_SPAWN);
@@ -310,9 +313,8 @@ env_step_kernel(const __grid_constant__ EnvConfig cfg, const __grid_constant__ E
                 bulk_s2g(g_tiles, s_st, (uint32_t)ng * tile_bytes);
                 bulk_commit();
             }
-            const int rec = 4 * A + 4;
             if (has_agent) {
-                float* pr = io.pose + (size_t)(scene0 + sl_a) * rec;
+                float* pr = io.pose + (size_t)(scene0 + sl_a) * io.rec_words;
                 pr[ia] = v.f(F_X, ia); pr[A + ia] = v.f(F_Y, ia); pr[2 * A + ia] = v.cs[ia]; pr[3 * A + ia] = v.sn[ia];
                 if (ia == 0) {
                     uint32_t* pi = reinterpret_cast<uint32_t*>(pr + 4 * A);
@@ -363,64 +365,111 @@ env_step_kernel(const __grid_constant__ EnvConfig cfg, const __grid_constant__ E
 }
 
 // ---- lidar half of the two-kernel mode ---------------------------------------------------------------------------
-// One CTA works on `G` scenes at a time: poses (x, y, cos, sin per slot) + pair count + participant mask arrive with
-// one bulk copy per group, the 72-laser tile of every slot lives in shared memory, queued pairs are read straight
-// from HBM (coalesced, 2 bytes each).  Same pair set-up / laser distribution as the fused kernel; the tile leaves
-// with coalesced stores into the observation rows, optionally again as the policy's bf16 [hi | lo] operand.
+// One CTA works on `G` scenes at a time.  Everything a scene needs arrives through bulk copies: first the record the
+// state kernel left (poses, pair count, participant mask, the non-laser observation columns), then - while the
+// observation tile is being initialised - exactly the queued pairs.  The tile holds whole observation rows [A][D] in
+// shared memory (non-laser columns transposed in from the record, lasers lowered by the pair pass, same pair set-up /
+// laser distribution as the fused kernel) and leaves as one bulk store, plus once more as the policy's bf16 [hi | lo]
+// operand through 8-byte coalesced stores.  Nothing on this path waits on a dependent global load.
 struct LidarIO {
     const uint32_t* map;
     const float* pose;
     const uint16_t* pairs;
     float* obs;
     uint32_t* obs_split;
-    int pair_stride, kp, group, S, A, D;
+    int pair_stride, rec_words, kp, group, S, A, D, n_ray, ray_off;
 };
 
-__global__ void __launch_bounds__(ENV_MAX_THREADS, 3)
+struct LidarPlan {
+    int ray, rec, pairs, tile, total;
+};
+__host__ __device__ inline LidarPlan lidar_plan(int G, int A, int D, int n_ray, int rec_words, int pair_stride) {
+    LidarPlan p;
+    int o = 16;                                           // two mbarriers
+    p.ray = o;   o += (n_ray * 8 + 15) & ~15;
+    p.rec = o;   o += G * rec_words * 4;                  // rec_words is a multiple of 4
+    p.pairs = o; o += G * pair_stride * 2;                // pair_stride is a multiple of 8
+    p.tile = o;  o += ((G * A * D + 3) & ~3) * 4;
+    p.total = o;
+    return p;
+}
+
+__global__ void __launch_bounds__(ENV_MAX_THREADS)
 env_lidar_kernel(const __grid_constant__ LidarIO io) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int A = io.A, D = io.D, G = io.group;
     const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, n_warps = NT >> 5;
-    const int n_ray = (int)io.map[M_NRAY];
-    const int rec = 4 * A + 4;                                    // floats per scene record
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
-    float2* s_ray = reinterpret_cast<float2*>(smem_raw + 16);
-    float* s_pose = reinterpret_cast<float*>(smem_raw + 16 + ((n_ray * 8 + 15) & ~15));
-    float* s_tile = s_pose + ((G * rec + 3) & ~3);                // [G][A][n_ray]
-    {
-        const float2* gr = reinterpret_cast<const float2*>(io.map + io.map[M_OFF_RAY]);
-        for (int k = tid; k < n_ray; k += NT) s_ray[k] = gr[k];
-    }
-    uint32_t parity = 0;
-    if (tid == 0) mbar_init(bar, 1);
-    __syncthreads();
+    const int n_ray = io.n_ray;
+    const int rec = io.rec_words;
+    const LidarPlan pl = lidar_plan(G, A, D, n_ray, rec, io.pair_stride);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);          // record arrivals
+    uint64_t* bar_q = bar + 1;                                      // pair-list arrivals
+    float2* s_ray = reinterpret_cast<float2*>(smem_raw + pl.ray);
+    float* s_rec = reinterpret_cast<float*>(smem_raw + pl.rec);
+    uint16_t* s_pairs = reinterpret_cast<uint16_t*>(smem_raw + pl.pairs);
+    float* s_tile = reinterpret_cast<float*>(smem_raw + pl.tile);     // [G][A][D]
     const int n_groups = (io.S + G - 1) / G;
     const int lid0 = EGO_DIM + NAVI_DIM;
+    const int n_ego = D - n_ray;                                  // non-laser columns
+    auto fetch_record = [&](int grp) {                            // thread 0 only
+        const int scene0 = grp * G;
+        const int ng = (io.S - scene0 < G) ? io.S - scene0 : G;
+        mbar_expect_tx(bar, (uint32_t)(ng * rec * 4));
+        bulk_g2s(s_rec, io.pose + (size_t)scene0 * rec, (uint32_t)(ng * rec * 4), bar);
+    };
+    uint32_t parity = 0;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_init(bar_q, 1);
+        if ((int)blockIdx.x < n_groups) fetch_record(blockIdx.x);  // in flight while the laser table loads
+    }
+    {
+        const float2* gr = reinterpret_cast<const float2*>(io.map + io.ray_off);
+        for (int k = tid; k < n_ray; k += NT) s_ray[k] = gr[k];
+    }
+    __syncthreads();
     for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
         const int scene0 = grp * G;
         const int ng = (io.S - scene0 < G) ? io.S - scene0 : G;
-        if (tid == 0) {
-            mbar_expect_tx(bar, (uint32_t)(ng * rec * 4));
-            bulk_g2s(s_pose, io.pose + (size_t)scene0 * rec, (uint32_t)(ng * rec * 4), bar);
-        }
         mbar_wait(bar, parity);
-        parity ^= 1u;
-        // laser entries start at "nothing within range" for participants, 0 for empty rows (one warp per row)
-        for (int sl = 0; sl < ng; ++sl) {
-            const uint32_t* hd = reinterpret_cast<const uint32_t*>(s_pose + sl * rec + 4 * A);
-            const unsigned long long pm = (unsigned long long)hd[1] | ((unsigned long long)hd[2] << 32);
-            for (int i = warp; i < A; i += n_warps) {
-                const float val = ((pm >> i) & 1ull) ? 1.0f : 0.0f;
-                float* trow = s_tile + (size_t)(sl * A + i) * n_ray;
-                for (int k = lane; k < n_ray; k += 32) trow[k] = val;
+        if (tid == 0) {
+            // the queued pairs of the group, rounded up to the bulk copy's 16-byte granule (inside the scene's stride)
+            uint32_t bytes = 0;
+            for (int sl = 0; sl < ng; ++sl)
+                bytes += ((reinterpret_cast<const uint32_t*>(s_rec + sl * rec + 4 * A)[0] * 2u) + 15u) & ~15u;
+            mbar_expect_tx(bar_q, bytes);
+            for (int sl = 0; sl < ng; ++sl) {
+                uint32_t b = ((reinterpret_cast<const uint32_t*>(s_rec + sl * rec + 4 * A)[0] * 2u) + 15u) & ~15u;
+                if (b) bulk_g2s(s_pairs + (size_t)sl * io.pair_stride,
+                                io.pairs + (size_t)(scene0 + sl) * io.pair_stride, b, bar_q);
             }
         }
+        // observation rows: lasers start at "nothing within range" for participants (0 for empty rows), the other
+        // columns come out of the record (stored slot-fastest by the state kernel)
+        for (int sl = 0; sl < ng; ++sl) {
+            const float* ps = s_rec + sl * rec;
+            const uint32_t* hd = reinterpret_cast<const uint32_t*>(ps + 4 * A);
+            const unsigned long long pm = (unsigned long long)hd[1] | ((unsigned long long)hd[2] << 32);
+            float* tile = s_tile + (size_t)sl * A * D;
+            for (int i = warp; i < A; i += n_warps) {
+                const float val = ((pm >> i) & 1ull) ? 1.0f : 0.0f;
+                float* trow = tile + (size_t)i * D + lid0;
+                for (int k = lane; k < n_ray; k += 32) trow[k] = val;
+            }
+            const float* eg = ps + 4 * A + 4;
+            for (int idx = tid; idx < n_ego * A; idx += NT) {
+                const int c = idx / A, i = idx - c * A;
+                tile[(size_t)i * D + (c < lid0 ? c : c + n_ray)] = eg[idx];
+            }
+        }
+        mbar_wait(bar_q, parity);                                 // pairs have landed
+        parity ^= 1u;                                             // both barriers complete one phase per group
         __syncthreads();
         for (int sl = 0; sl < ng; ++sl) {
-            const float* ps = s_pose + sl * rec;
+            const float* ps = s_rec + sl * rec;
             const int nq = (int)reinterpret_cast<const uint32_t*>(ps + 4 * A)[0];
-            const uint16_t* gq = io.pairs + (size_t)(scene0 + sl) * io.pair_stride;
-            float* tile = s_tile + (size_t)sl * A * n_ray;
+            const uint16_t* gq = s_pairs + (size_t)sl * io.pair_stride;
+            float* tile = s_tile + (size_t)sl * A * D + lid0;
             for (int base = warp * 32; base < nq; base += n_warps * 32) {
                 const int e = base + lane;
                 PairGeom g;
@@ -431,7 +480,7 @@ env_lidar_kernel(const __grid_constant__ LidarIO io) {
                     int oi = (code >> 6) & 63, oj = code & 63;
                     lidar_pair_geom(ps[oi], ps[A + oi], ps[2 * A + oi], ps[3 * A + oi], ps[oj], ps[A + oj], ps[2 * A + oj],
                                     ps[3 * A + oj], n_ray, g);
-                    lid_off = oi * n_ray;
+                    lid_off = oi * D;
                 }
                 int incl = g.cnt;
 #pragma unroll
@@ -466,48 +515,71 @@ env_lidar_kernel(const __grid_constant__ LidarIO io) {
                 }
             }
         }
+        fence_async_smem();
         __syncthreads();
-        // laser part of the observation rows, one warp per row (coalesced along the lasers)
+        // the group's observation rows are one contiguous block of HBM
         float* g_obs = io.obs + (size_t)scene0 * A * D;
         const int n_rows = ng * A;
-        for (int row = warp; row < n_rows; row += n_warps) {
-            const float* trow = s_tile + (size_t)row * n_ray;
-            float* orow = g_obs + (size_t)row * D + lid0;
-            for (int k = lane; k < n_ray; k += 32) orow[k] = trow[k];
+        const uint32_t obs_bytes = (uint32_t)(n_rows * D * 4);
+        const bool obs_bulk = ((obs_bytes | (uint32_t)(A * D * 4)) & 15u) == 0u &&
+                              (reinterpret_cast<uintptr_t>(io.obs) & 15u) == 0u;
+        if (obs_bulk) {
+            if (tid == 0) {
+                bulk_s2g(g_obs, s_tile, obs_bytes);
+                bulk_commit();
+            }
+        } else {
+            for (int idx = tid; idx < n_rows * D; idx += NT) g_obs[idx] = s_tile[idx];
         }
         if (io.obs_split) {
-            // whole rows as the policy's [hi | lo] bf16 operand: lasers from the tile, the rest from the rows the state
-            // kernel wrote
-            const int half = io.kp >> 1;
+            // whole rows as the policy's [hi | lo] bf16 operand
+            const int half = io.kp >> 1;                          // 32-bit words per half row (2 columns each)
             uint32_t* g_sp = io.obs_split + (size_t)scene0 * A * io.kp;
-            for (int row = warp; row < n_rows; row += n_warps) {
-                const float* trow = s_tile + (size_t)row * n_ray;
-                const float* orow = g_obs + (size_t)row * D;
-                uint32_t* srow = g_sp + (size_t)row * io.kp;
-                for (int c2 = lane; c2 < half; c2 += 32) {
-                    float v2[2];
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        int k = 2 * c2 + u;
-                        float x = 0.0f;
-                        if (k < D) x = (k >= lid0 && k < lid0 + n_ray) ? trow[k - lid0] : orow[k];
-                        v2[u] = x;
+            if ((D & 3) == 0 && (half & 1) == 0) {
+                // four columns per lane: one 16-byte shared load, one 8-byte store into each half
+                for (int row = warp; row < n_rows; row += n_warps) {
+                    const float4* trow = reinterpret_cast<const float4*>(s_tile + (size_t)row * D);
+                    uint2* srow = reinterpret_cast<uint2*>(g_sp + (size_t)row * io.kp);
+                    for (int q = lane; q < (half >> 1); q += 32) {
+                        float4 x = (4 * q < D) ? trow[q] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                        __nv_bfloat16 h0 = __float2bfloat16_rn(x.x), h1 = __float2bfloat16_rn(x.y);
+                        __nv_bfloat16 h2 = __float2bfloat16_rn(x.z), h3 = __float2bfloat16_rn(x.w);
+                        __nv_bfloat16 l0 = __float2bfloat16_rn(x.x - __bfloat162float(h0));
+                        __nv_bfloat16 l1 = __float2bfloat16_rn(x.y - __bfloat162float(h1));
+                        __nv_bfloat16 l2 = __float2bfloat16_rn(x.z - __bfloat162float(h2));
+                        __nv_bfloat16 l3 = __float2bfloat16_rn(x.w - __bfloat162float(h3));
+                        uint2 hi, lo;
+                        hi.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                        hi.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
+                        lo.x = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                        lo.y = (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16);
+                        srow[q] = hi;
+                        srow[(half >> 1) + q] = lo;
                     }
-                    __nv_bfloat16 h0 = __float2bfloat16_rn(v2[0]), h1 = __float2bfloat16_rn(v2[1]);
-                    __nv_bfloat16 l0 = __float2bfloat16_rn(v2[0] - __bfloat162float(h0));
-                    __nv_bfloat16 l1 = __float2bfloat16_rn(v2[1] - __bfloat162float(h1));
-                    srow[c2] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                    srow[half + c2] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                }
+            } else {
+                for (int row = warp; row < n_rows; row += n_warps) {
+                    const float* trow = s_tile + (size_t)row * D;
+                    uint32_t* srow = g_sp + (size_t)row * io.kp;
+                    for (int c2 = lane; c2 < half; c2 += 32) {
+                        const int k = 2 * c2;
+                        const float v0 = (k < D) ? trow[k] : 0.0f;
+                        const float v1 = (k + 1 < D) ? trow[k + 1] : 0.0f;
+                        __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+                        __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0));
+                        __nv_bfloat16 l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
+                        srow[c2] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                        srow[half + c2] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                    }
                 }
             }
         }
         __syncthreads();
+        if (tid == 0) {
+            bulk_wait_read0();                                    // the tile has left shared memory
+            if (grp + (int)gridDim.x < n_groups) fetch_record(grp + gridDim.x);
+        }
     }
-}
-
-static size_t lidar_smem_bytes(int G, int A, int n_ray) {
-    size_t rec = 4 * A + 4;
-    return 16 + ((n_ray * 8 + 15) & ~15) + (((size_t)G * rec + 3) & ~(size_t)3) * 4 + (size_t)G * A * n_ray * 4 + 16;
 }
 
 }  // namespace b2c
@@ -520,11 +592,11 @@ struct b2c_env {
     int group;
     int threads;
     int split;               // 1: two-kernel mode (state kernel + lidar kernel)
-    int lidar_group, lidar_threads;
+    int lidar_group, lidar_threads, lidar_ctas, ray_off;
     size_t lidar_smem;
     float* d_pose;
     uint16_t* d_pairs;
-    int pair_stride, n_ray;
+    int pair_stride, n_ray, rec_words;
     uint32_t* d_map;
     uint32_t* d_state;
     int map_words;
@@ -594,15 +666,20 @@ int b2c_env_create(const b2c_env_config* c, const uint32_t* map_blob, int map_wo
         e->lidar_threads = 128;
         if (const char* t = getenv("B2C_LIDAR_THREADS")) e->lidar_threads = atoi(t);
         if (e->lidar_threads < 32 || e->lidar_threads > ENV_MAX_THREADS || (e->lidar_threads & 31)) e->lidar_threads = 128;
+        e->lidar_ctas = 64;
+        if (const char* t = getenv("B2C_LIDAR_CTAS")) e->lidar_ctas = atoi(t) > 0 ? atoi(t) : 64;
+        e->ray_off = (int)map_blob[M_OFF_RAY];
         e->lidar_group = 1;
         if (const char* g = getenv("B2C_LIDAR_GROUP")) e->lidar_group = atoi(g) > 0 ? atoi(g) : 1;
-        while (e->lidar_group > 1 && lidar_smem_bytes(e->lidar_group, k.A, e->n_ray) > 100 * 1024) e->lidar_group -= 1;
+        e->pair_stride = (k.A * k.A + 7) & ~7;
+        e->rec_words = (4 * k.A + 4 + (k.D - e->n_ray) * k.A + 3) & ~3;
+        auto lsm = [&](int g) { return (size_t)lidar_plan(g, k.A, k.D, e->n_ray, e->rec_words, e->pair_stride).total; };
+        while (e->lidar_group > 1 && lsm(e->lidar_group) > 100 * 1024) e->lidar_group -= 1;
         if (e->lidar_group > k.S) e->lidar_group = k.S;
-        e->lidar_smem = lidar_smem_bytes(e->lidar_group, k.A, e->n_ray);
+        e->lidar_smem = lsm(e->lidar_group);
         B2C_CUDA_OR(cudaFuncSetAttribute(env_lidar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->lidar_smem),
                     delete e);
-        e->pair_stride = (k.A * k.A + 7) & ~7;
-        B2C_CUDA_OR(cudaMalloc(&e->d_pose, (size_t)k.S * (4 * k.A + 4) * 4), delete e);
+        B2C_CUDA_OR(cudaMalloc(&e->d_pose, (size_t)k.S * e->rec_words * 4), delete e);
         B2C_CUDA_OR(cudaMalloc(&e->d_pairs, (size_t)k.S * e->pair_stride * 2), delete e);
     } else {
         B2C_CUDA_OR(cudaFuncSetAttribute(env_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem),
@@ -630,13 +707,11 @@ static void launch_lidar(b2c_env* e, float* obs, uint32_t* obs_split, int kp, cu
     const EnvConfig& cfg = e->cfg;
     LidarIO li;
     li.map = e->d_map; li.pose = e->d_pose; li.pairs = e->d_pairs; li.obs = obs; li.obs_split = obs_split;
-    li.pair_stride = e->pair_stride; li.kp = kp; li.group = e->lidar_group; li.S = cfg.S; li.A = cfg.A; li.D = cfg.D;
-    int lc = (int)(227 * 1024 / (e->lidar_smem + 1024));
-    int lt = 2048 / e->lidar_threads;
-    if (lc > lt) lc = lt;
-    if (lc < 1) lc = 1;
+    li.pair_stride = e->pair_stride; li.rec_words = e->rec_words; li.n_ray = e->n_ray; li.ray_off = e->ray_off;
+    li.kp = kp; li.group = e->lidar_group; li.S = cfg.S; li.A = cfg.A; li.D = cfg.D;
+    // one CTA per group of scenes (the hardware scheduler balances the uneven pair counts); very large batches loop
     int lg = (cfg.S + e->lidar_group - 1) / e->lidar_group;
-    int lgrid = e->num_sms * lc;
+    int lgrid = e->num_sms * e->lidar_ctas;
     if (lgrid > lg) lgrid = lg;
     env_lidar_kernel<<<lgrid, e->lidar_threads, e->lidar_smem, st>>>(li);
 }
@@ -657,7 +732,7 @@ static int launch_env(b2c_env* e, const float* actions, const b2c_env_io* o, int
     io.map_words = e->map_words; io.tile_words = e->tile_words;
     io.obs_bulk = ((((size_t)cfg.A * cfg.D * 4) % 16 == 0) && (((uintptr_t)o->obs) % 16 == 0)) ? 1 : 0;
     io.group = e->group;
-    io.pose = e->d_pose; io.pairs = e->d_pairs; io.pair_stride = e->pair_stride;
+    io.pose = e->d_pose; io.pairs = e->d_pairs; io.pair_stride = e->pair_stride; io.rec_words = e->rec_words;
     int ctas_per_sm = (int)(227 * 1024 / (e->smem + 1024));
     int by_threads = 2048 / e->threads;
     if (ctas_per_sm > by_threads) ctas_per_sm = by_threads;

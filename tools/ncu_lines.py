@@ -1,24 +1,28 @@
 """Aggregates an ncu report's per-SASS-instruction counters by CUDA source line (needs -lineinfo + --import-source).
-usage: python tools/ncu_lines.py report.ncu-rep [top_n]"""
+usage: python tools/ncu_lines.py report.ncu-rep [top_n] [kernel-name substring]"""
 import collections
 import csv
 import subprocess
 import sys
 
 
-def main(rep, top=40):
+def main(rep, top=40, kernel=None):
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     agg = collections.OrderedDict()
     cur_file = cur = None
+    skip = False
     for r in rows:
         if not r:
             continue
         if r[0] == "File Path":
             cur_file = r[1].split("/")[-1]
             continue
-        if r[0] in ("Function Name", "Line No"):
+        if r[0] == "Function Name":
+            skip = kernel is not None and kernel not in r[1]
+            continue
+        if r[0] == "Line No" or skip:
             continue
         if r[0] != "":
             cur = (cur_file, r[0], r[1][:100])
@@ -42,4 +46,4 @@ def main(rep, top=40):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 40)
+    main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 40, sys.argv[3] if len(sys.argv) > 3 else None)
