@@ -267,17 +267,17 @@ def run_gpu(args):
 
     # ---- end to end, host in the loop: pinned host actions -> device, scene step, every env output -> pinned host,
     # policy forward + sample on the new observations, sampled actions -> pinned host (they are the next step's input)
-    e2e_out = dict(env.out)
-    e2e_out["obs_split"] = split[0]
-    env.out = e2e_out
     host_act = torch.zeros((S, A, 2)).pin_memory()
 
     def e2e_step(t):
-        env.step_host(host_act)
-        lg, a, lp = pol.model.forward_sample(env.out["obs"].view(N, D), args.seed + rank * 7919, 100000 + t,
+        # the scene step's outputs start crossing PCIe (one copy of the output arena, on the env's copy stream) as soon
+        # as its kernels end; the policy forward on the new observations is queued behind the scene step meanwhile
+        env.step_host(host_act, obs_split=split[0], wait=False)
+        lg, a, lp = pol.model.forward_sample(env.host_step_out["obs"].view(N, D), args.seed + rank * 7919, 100000 + t,
                                              obs_split=split[0].view(N, -1))
         host_act.copy_(a.view(S, A, 2), non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        env.wait_host()                                  # every env output is in pinned host memory
+        torch.cuda.current_stream().synchronize()        # ... and so are the next step's actions
 
     for t in range(3):
         e2e_step(t)
@@ -368,8 +368,9 @@ def run_gpu(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": env.h2d_bytes_per_step * world,
                 "d2h_bytes_per_step": (env.d2h_bytes_per_step + env.h2d_bytes_per_step) * world, "steps": e2e_steps,
                 "api": "host-in-the-loop rollout step: BatchedDrivingEnv.step_host (pinned host actions in, every env "
-                       "output back to pinned host) + CoPOModel.forward_sample on the device, sampled actions back to "
-                       "pinned host"},
+                       "output back to pinned host as one arena copy on a copy stream) + CoPOModel.forward_sample on "
+                       "the device meanwhile, sampled actions back to pinned host; the step ends when both have "
+                       "landed"},
         "gpu_launches": launches,
         "clocks": clk,
         "train": train,

@@ -99,31 +99,71 @@ class BatchedDrivingEnv:
     # -- host-buffer stepping (what a CPU-side caller of the reference's env.step sees) ---------------------
     HOST_KEYS = ("obs", "reward", "flags", "nei_mask", "nei_reward", "global_reward", "nei_list", "agent_id", "lcf",
                  "scene_done")
+    _host = None
 
     def _host_buffers(self):
-        if getattr(self, "_host", None) is None:
-            self._host = {k: torch.empty(self.out[k].shape, dtype=self.out[k].dtype).pin_memory()
-                          for k in self.HOST_KEYS}
-            self._host_act = torch.empty((self.S, self.A, 2), dtype=torch.float32).pin_memory()
+        """One device arena and one pinned host arena hold every output of a host-facing step, so a step's results
+        cross PCIe as ONE copy on a dedicated copy stream (the kernels write straight into the device arena)."""
+        if self._host is None:
+            offs, size = {}, 0
+            for k in self.HOST_KEYS:
+                t = self.out[k]
+                offs[k] = size
+                size += (t.numel() * t.element_size() + 255) & ~255
+            self._arena_dev = torch.zeros(size, dtype=torch.uint8, device=self.device)
+            self._arena_host = torch.zeros(size, dtype=torch.uint8).pin_memory()
+
+            def views(arena):
+                d = {}
+                for k in self.HOST_KEYS:
+                    t = self.out[k]
+                    n = t.numel() * t.element_size()
+                    d[k] = arena[offs[k]:offs[k] + n].view(t.dtype).view(t.shape)
+                return d
+            self._host = views(self._arena_host)
+            self.host_step_out = dict(self.out)          # device side of the same step (arena views + mf_mask)
+            self.host_step_out.update(views(self._arena_dev))
             self._dev_act = torch.empty((self.S, self.A, 2), dtype=torch.float32, device=self.device)
-            self.h2d_bytes_per_step = self._host_act.numel() * 4
+            self._pin_act = torch.empty((self.S, self.A, 2), dtype=torch.float32).pin_memory()
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._ev_step = torch.cuda.Event()
+            self._ev_copy = torch.cuda.Event()
+            self._copy_pending = False
+            self.h2d_bytes_per_step = self._dev_act.numel() * 4
             self.d2h_bytes_per_step = sum(v.numel() * v.element_size() for v in self._host.values())
         return self._host
 
-    def step_host(self, actions_host):
-        """actions_host: float32 [S, A, 2] numpy array or CPU tensor.  Copies it to the device, steps every scene
-        and returns pinned host tensors of every output (valid until the next call)."""
+    def step_host(self, actions_host, obs_split=None, wait=True):
+        """actions_host: float32 [S, A, 2] numpy array or CPU tensor (pinned tensors are read in place).  Copies it
+        to the device, steps every scene and returns pinned host tensors of every output (valid until the next call).
+        With wait=False the call returns as soon as the work is enqueued - the outputs travel on the copy stream
+        while the caller queues more device work on `host_step_out` - and are valid after `wait_host()`."""
         host = self._host_buffers()
         a = torch.as_tensor(actions_host, dtype=torch.float32)
         assert tuple(a.shape) == (self.S, self.A, 2), a.shape
-        if a.data_ptr() != self._host_act.data_ptr():
-            self._host_act.copy_(a)
-        self._dev_act.copy_(self._host_act, non_blocking=True)
-        self.step(self._dev_act)
-        for k in self.HOST_KEYS:
-            host[k].copy_(self.out[k], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        if not (a.is_pinned() and a.is_contiguous()):
+            a = self._pin_act.copy_(a)
+        cur = torch.cuda.current_stream(self.device)
+        if self._copy_pending:                               # a forgotten wait_host() must not race the arena
+            cur.wait_event(self._ev_copy)
+        self._dev_act.copy_(a, non_blocking=True)
+        self.host_step_out["obs_split"] = obs_split
+        self.step(self._dev_act, out=self.host_step_out)
+        self._ev_step.record(cur)
+        self._copy_stream.wait_event(self._ev_step)
+        with torch.cuda.stream(self._copy_stream):
+            self._arena_host.copy_(self._arena_dev, non_blocking=True)
+            self._ev_copy.record(self._copy_stream)
+        self._copy_pending = True
+        if wait:
+            self.wait_host()
         return host
+
+    def wait_host(self):
+        """Blocks until the outputs of the last `step_host(..., wait=False)` are in the pinned host tensors."""
+        if self._host is not None and self._copy_pending:
+            self._ev_copy.synchronize()
+            self._copy_pending = False
 
     def agent_steps(self):
         """Running count of agent-env-steps (agents that received an action), summed over scenes."""

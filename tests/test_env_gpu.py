@@ -130,3 +130,37 @@ def test_env_emits_the_policy_operand(split, monkeypatch):
         assert env.split_width == want.shape[1]
         assert torch.equal(out["obs_split"].reshape(37 * A, -1).view(torch.int16), want.view(torch.int16))
         env.close()
+
+
+def test_step_host_matches_device_step():
+    """The host-buffer step (one arena copy on the copy stream, blocking or overlapped with later device work) returns
+    exactly what the device step leaves in HBM."""
+    from copo_b200.batched_env import BatchedDrivingEnv
+    S, A = 50, 40
+    e_dev = BatchedDrivingEnv("intersection", num_scenes=S, num_slots=A, num_agents=A, seed=4)
+    e_host = BatchedDrivingEnv("intersection", num_scenes=S, num_slots=A, num_agents=A, seed=4)
+    e_dev.reset()
+    e_host.reset()
+    rng = np.random.default_rng(0)
+    pinned = torch.zeros((S, A, 2)).pin_memory()
+    for t in range(12):
+        act = rng.uniform(-1, 1, (S, A, 2)).astype(np.float32)
+        want = e_dev.step(torch.from_numpy(act).cuda())
+        if t % 3 == 0:
+            got = e_host.step_host(act)                              # numpy in, blocking
+        elif t % 3 == 1:
+            got = e_host.step_host(torch.from_numpy(act))            # pageable tensor in, blocking
+        else:
+            pinned.copy_(torch.from_numpy(act))
+            got = e_host.step_host(pinned, wait=False)               # pinned in place, overlapped
+            busy = e_host.host_step_out["obs"].sum()                 # device work queued behind the step
+            e_host.wait_host()
+            assert torch.isfinite(busy)
+        for k in BatchedDrivingEnv.HOST_KEYS:
+            assert not got[k].is_cuda and got[k].is_pinned()
+            assert torch.equal(got[k], want[k].cpu()), (t, k)
+            assert torch.equal(e_host.host_step_out[k], want[k]), (t, k)
+    assert e_host.d2h_bytes_per_step == sum(want[k].numel() * want[k].element_size()
+                                            for k in BatchedDrivingEnv.HOST_KEYS)
+    e_dev.close()
+    e_host.close()
