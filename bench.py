@@ -292,6 +292,16 @@ def run_gpu(args):
     barrier()
     e2e_ms = e0.elapsed_time(e1)
     e2e_agent_steps = env.agent_steps() - m0
+    # what the PCIe link alone takes for one step's outputs (the arena copy, nothing else in flight)
+    pc = []
+    for _ in range(5):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        env._arena_host.copy_(env._arena_dev, non_blocking=True)
+        b.record(stream)
+        torch.cuda.synchronize()
+        pc.append(a.elapsed_time(b))
+    pcie_ms = float(np.median(pc))
 
     stats = torch.tensor([total_ms, e2e_ms, float(agent_steps), float(e2e_agent_steps)], dtype=torch.float64,
                          device=dev)
@@ -367,6 +377,8 @@ def run_gpu(args):
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": env.h2d_bytes_per_step * world,
                 "d2h_bytes_per_step": (env.d2h_bytes_per_step + env.h2d_bytes_per_step) * world, "steps": e2e_steps,
+                "ms_per_step": e2e_ms / e2e_steps, "output_copy_alone_ms": pcie_ms,
+                "output_copy_GBps": env.d2h_bytes_per_step / (pcie_ms * 1e-3) / 1e9,
                 "api": "host-in-the-loop rollout step: BatchedDrivingEnv.step_host (pinned host actions in, every env "
                        "output back to pinned host as one arena copy on a copy stream) + CoPOModel.forward_sample on "
                        "the device meanwhile, sampled actions back to pinned host; the step ends when both have "
