@@ -26,6 +26,7 @@ struct GaeArgs {
     int T, N, heads, g_div;        // g_div: slots per scene when the global reward is stored per scene, else 1
     int g_ld;                      // row length of rew[2]
     float gamma, lambda_;
+    const float* boot[3];          // optional [N]: value of the observation after the fragment's last row
 };
 
 __global__ void gae3_kernel(const GaeArgs a) {
@@ -47,7 +48,10 @@ __global__ void gae3_kernel(const GaeArgs a) {
             const double v = (double)a.val[h][idx];
             double next_v = nv[h], next_adv = nadv[h];
             if (done) { next_v = 0.0; next_adv = 0.0; }
-            else if (!has_next) { next_v = v; next_adv = 0.0; }            // fragment cut: bootstrap with own value
+            else if (!has_next) {                                            // fragment cut: bootstrap with own value
+                next_v = (a.boot[h] && t == a.T - 1) ? (double)a.boot[h][n] : v;   // (IPPO: value of the next obs)
+                next_adv = 0.0;
+            }
             const double delta = (double)r + g * next_v - v;
             const double adv = delta + g * (double)a.lambda_ * next_adv;
             a.adv[h][idx] = (float)adv;
@@ -202,6 +206,7 @@ int b2c_gae3(const b2c_gae_args* p, void* stream) {
     a.g_ld = p->global_reward_per_scene > 0 ? p->N / p->global_reward_per_scene : p->N;
     for (int h = 0; h < 3; ++h) {
         a.rew[h] = p->rewards[h]; a.val[h] = p->values[h]; a.adv[h] = p->advantages[h]; a.tgt[h] = p->targets[h];
+        a.boot[h] = (h < p->heads) ? p->bootstrap[h] : nullptr;
         if (h < p->heads && (!a.rew[h] || !a.val[h] || !a.adv[h] || !a.tgt[h]))
             return b2c_set_error(B2C_ERR_ARG, "b2c_gae3: head %d has a null column", h);
     }

@@ -36,7 +36,7 @@ class GaeArgs(ctypes.Structure):
     _fields_ = [("flags", ctypes.c_void_p), ("rewards", ctypes.c_void_p * 3), ("values", ctypes.c_void_p * 3),
                 ("advantages", ctypes.c_void_p * 3), ("targets", ctypes.c_void_p * 3), ("T", ctypes.c_int32),
                 ("N", ctypes.c_int32), ("heads", ctypes.c_int32), ("global_reward_per_scene", ctypes.c_int32),
-                ("gamma", ctypes.c_float), ("lambda_", ctypes.c_float)]
+                ("gamma", ctypes.c_float), ("lambda_", ctypes.c_float), ("bootstrap", ctypes.c_void_p * 3)]
 
 
 def _lib_ready():
@@ -148,9 +148,12 @@ def lcf_meta_terms(adv, nei_adv, eps, lcf_mean, lcf_std):
 
 
 # ---- rollout bookkeeping ------------------------------------------------------------------------------------------
-def gae3(flags, rewards, values, gamma, lambda_, global_reward_per_scene=0):
+def gae3(flags, rewards, values, gamma, lambda_, global_reward_per_scene=0, bootstrap=None):
     """flags uint8 [T, N]; rewards / values: lists of 1 or 3 float32 [T, N] tensors (the global reward may be [T, S]
-    with global_reward_per_scene = slots per scene).  Returns (advantages, targets) lists."""
+    with global_reward_per_scene = slots per scene).  bootstrap: optional list of [N] tensors (or None) per head - the
+    value of the observation after the last row, used for trajectories the fragment end cuts (stock rllib rule);
+    without it such a trajectory bootstraps with the value of its own last row (the CCPPO / CoPO rule).
+    Returns (advantages, targets) lists."""
     lib = _lib_ready()
     T, N = flags.shape
     heads = len(values)
@@ -162,6 +165,10 @@ def gae3(flags, rewards, values, gamma, lambda_, global_reward_per_scene=0):
         assert rewards[h].is_contiguous() and values[h].is_contiguous()
         a.rewards[h], a.values[h] = rewards[h].data_ptr(), values[h].data_ptr()
         a.advantages[h], a.targets[h] = adv[h].data_ptr(), tgt[h].data_ptr()
+        if bootstrap is not None and bootstrap[h] is not None:
+            b = bootstrap[h]
+            assert b.dtype == torch.float32 and b.is_contiguous() and b.numel() == N
+            a.bootstrap[h] = b.data_ptr()
     a.T, a.N, a.heads, a.global_reward_per_scene = T, N, heads, global_reward_per_scene
     a.gamma, a.lambda_ = gamma, lambda_
     _lib.check(lib.b2c_gae3(ctypes.byref(a), _lib.stream_ptr()))

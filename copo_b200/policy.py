@@ -195,14 +195,21 @@ class IPPOPolicy:
     def _critic_obs(self, ro):
         return ro[OBS].reshape(-1, ro[OBS].shape[-1])
 
+    def _bootstrap_values(self, ro):
+        """Stock rllib PPO postprocessing (IPPOPolicy overrides only `loss`, algo_ippo.py:78-79): a trajectory the
+        fragment end cuts bootstraps with the value of its NEXT observation."""
+        nxt = ro.get("next_obs")
+        return None if nxt is None else [self.model.central_value_function(nxt).reshape(-1).contiguous()]
+
     def postprocess_rollout(self, ro):
-        """ro: dict of [T, N, ...] rollout columns (obs, actions, rewards, flags, ...).  Adds vf_preds, advantages,
-        value_targets (GAE; IPPO bootstraps like CCPPO here: value of the last observed state)."""
+        """ro: dict of [T, N, ...] rollout columns (obs, actions, rewards, flags, ...; `next_obs` [N, D] = the
+        observation after the last row).  Adds vf_preds, advantages, value_targets (GAE)."""
         T, N = ro["flags"].shape
         cobs = self._critic_obs(ro)
         ro[CENTRALIZED_CRITIC_OBS] = cobs.reshape(T, N, -1)
         ro[VF_PREDS] = self.model.central_value_function(cobs).reshape(T, N)
-        adv, tgt = ops.gae3(ro["flags"], [ro[REWARDS]], [ro[VF_PREDS]], self.config["gamma"], self.config["lambda_"])
+        adv, tgt = ops.gae3(ro["flags"], [ro[REWARDS]], [ro[VF_PREDS]], self.config["gamma"], self.config["lambda_"],
+                            bootstrap=self._bootstrap_values(ro))
         ro[ADVANTAGES], ro[VALUE_TARGETS] = adv[0], tgt[0]
         return ro
 
@@ -234,6 +241,9 @@ class CCPPOPolicy(IPPOPolicy):
 
     def _heads(self, train_batch):
         return [("value", CENTRALIZED_CRITIC_OBS, VF_PREDS, VALUE_TARGETS)]
+
+    def _bootstrap_values(self, ro):
+        return None      # last_r = VF_PREDS[-1]: the value of the LAST OBSERVED state (algo_ccppo.py:362-365)
 
     def _critic_obs(self, ro):
         T, N, D = ro[OBS].shape

@@ -136,6 +136,7 @@ class IPPOTrainer:
             self.env.step(ro[P.ACTIONS][t].view(self.env.S, self.env.A, 2), out=out)
             self._step_counter += 1
         view = {k: (v[:self.T] if k == P.OBS else v) for k, v in ro.items()}
+        view["next_obs"] = ro[P.OBS][self.T]             # the observation after the fragment's last row
         view["slots"] = self.env.A
         return view
 

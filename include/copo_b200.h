@@ -170,6 +170,9 @@ typedef struct {
     int32_t T, N, heads;          /* heads = 1 (IPPO / CCPPO) or 3 (CoPO) */
     int32_t global_reward_per_scene;  /* 0: rewards[2] is [T][N]; A > 0: it is [T][N / A], one value per scene */
     float gamma, lambda_;         /* the global head always uses gamma = 1 (algo_copo.py:498-500) */
+    const float* bootstrap[3];    /* optional [N] per head: value of the observation AFTER row T-1 (stock rllib PPO,
+                                     used by IPPO: last_r = V(NEXT_OBS), algo_ippo.py inherits PPOTorchPolicy's
+                                     postprocessing); NULL = the CCPPO / CoPO rule below */
 } b2c_gae_args;
 /* compute_advantages x3 (rllib postprocessing; algo_copo.py:189-204, 473-502): per (scene, slot) column, consecutive
  * valid rows up to a done row are one trajectory; a trajectory cut by the fragment end bootstraps with the value

@@ -61,9 +61,12 @@ def trajectories(flags_col):
 
 
 def rollout_gae3(flags, rewards, values, nei_rewards, nei_values, glob_rewards, glob_values, gamma=0.99,
-                 lambda_=0.95, heads=3):
+                 lambda_=0.95, heads=3, next_values=None):
     """All inputs [T, N] (flags uint8, the rest float32).  Returns dict of [T, N] float32 arrays, zero where the
-    row is not valid.  heads=1 computes only the native advantage (IPPO / CCPPO)."""
+    row is not valid.  heads=1 computes only the native advantage (IPPO / CCPPO).
+    next_values ([N], heads=1 only): the value of the observation after the fragment's last row - stock rllib PPO
+    (`compute_gae_for_sample_batch`, which IPPOPolicy inherits: algo_ippo.py:79 subclasses PPOTorchPolicy without
+    overriding postprocess_trajectory) bootstraps a trajectory that is not done with V(NEXT_OBS of its last row)."""
     T, N = flags.shape
     names = ["advantages", "value_targets", "nei_advantage", "nei_target", "global_advantages", "global_target"]
     out = {k: np.zeros((T, N), np.float32) for k in names[:2 * heads]}
@@ -73,6 +76,8 @@ def rollout_gae3(flags, rewards, values, nei_rewards, nei_values, glob_rewards, 
             done = bool(flags[rows[-1], n] & FLAG_DONE)
             v = values[rows, n]
             last_r = 0.0 if done else v[-1]                                  # algo_ccppo.py:362-365
+            if next_values is not None and not done and rows[-1] == T - 1:
+                last_r = next_values[n]                                      # stock rllib: V(NEXT_OBS)
             a, tg = compute_advantages(rewards[rows, n], v, last_r, gamma, lambda_)
             out["advantages"][rows, n], out["value_targets"][rows, n] = a, tg
             if heads == 3:

@@ -73,7 +73,8 @@ def test_ctypes_structs_match_the_header(tmp_path):
     fields = {"b2c_env_config": ["num_scenes", "seed", "neighbours_distance", "force_lcf"],
               "b2c_env_io": ["obs", "scene_done", "obs_split"],
               "b2c_ppo_head_args": ["logits", "v_cur", "dlogits", "dv", "stats", "rows", "mode", "clip_param", "kl_coeff"],
-              "b2c_gae_args": ["flags", "rewards", "targets", "T", "global_reward_per_scene", "gamma", "lambda_"],
+              "b2c_gae_args": ["flags", "rewards", "targets", "T", "global_reward_per_scene", "gamma", "lambda_",
+                               "bootstrap"],
               "b2c_tc_head": ["weight", "out", "n", "actions", "logp", "seed", "step"]}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "copo_b200.h"', 'int main(void) {']
     for s, fs in fields.items():

@@ -63,6 +63,35 @@ def test_rollout_columns_are_cut_into_trajectories():
     assert (out["advantages"][3:5, 0] == 0).all() and (out["nei_advantage"][:, 2] == 0).all()
 
 
+def test_ippo_bootstraps_with_the_next_observation():
+    """Stock rllib PPO (IPPOPolicy inherits its postprocessing): a trajectory that is not done bootstraps with
+    V(NEXT_OBS of its last row); done trajectories and trajectories that end before the fragment does are untouched."""
+    V, D = og.FLAG_VALID, og.FLAG_VALID | og.FLAG_DONE
+    T, N = 6, 4
+    flags = np.stack([np.full(T, V, np.uint8),                       # alive throughout: cut by the fragment end
+                      np.array([V, V, D, 0, V, V], np.uint8),        # second trajectory is cut
+                      np.array([0, V, V, V, V, D], np.uint8),        # ends done on the last row: last_r = 0
+                      np.zeros(T, np.uint8)], 1)
+    rng = np.random.default_rng(5)
+    r, v = rng.normal(size=(T, N)).astype(np.float32), rng.normal(size=(T, N)).astype(np.float32)
+    nxt = rng.normal(size=N).astype(np.float32)
+    z = np.zeros((T, N), np.float32)
+    out = og.rollout_gae3(flags, r, v, z, z, z, z, heads=1, next_values=nxt)
+    a, t = og.compute_advantages(r[:, 0], v[:, 0], nxt[0])
+    assert np.array_equal(out["advantages"][:, 0], a) and np.array_equal(out["value_targets"][:, 0], t)
+    a, _ = og.compute_advantages(r[[4, 5], 1], v[[4, 5], 1], nxt[1])
+    assert np.array_equal(out["advantages"][[4, 5], 1], a)
+    a, _ = og.compute_advantages(r[[0, 1, 2], 1], v[[0, 1, 2], 1], 0.0)
+    assert np.array_equal(out["advantages"][[0, 1, 2], 1], a)
+    a, _ = og.compute_advantages(r[1:, 2], v[1:, 2], 0.0)
+    assert np.array_equal(out["advantages"][1:, 2], a)
+    # the last delta is r + gamma * V(next) - V(last)
+    assert np.isclose(out["advantages"][5, 0], r[5, 0] + 0.99 * nxt[0] - v[5, 0], rtol=1e-6)
+    own = og.rollout_gae3(flags, r, v, z, z, z, z, heads=1)
+    assert not np.array_equal(own["advantages"][:, 0], out["advantages"][:, 0])      # the CCPPO / CoPO rule differs
+    assert np.array_equal(own["advantages"][:, 2], out["advantages"][:, 2])
+
+
 def test_lcf_mix_standardize():
     rng = np.random.default_rng(2)
     adv, nei, gadv = (rng.normal(size=1000).astype(np.float32) for _ in range(3))

@@ -136,6 +136,13 @@ def test_gae3_matches_reference_restatement():
         close(tgt[k], want[t], 1e-4, 1e-5)
     adv1, _ = ops.gae3(c(flags), [c(r)], [c(v)], 0.99, 0.95)
     close(adv1[0], want["advantages"], 1e-4, 1e-5)
+    # IPPO: trajectories the fragment end cuts bootstrap with the value of the next observation (stock rllib)
+    nxt = f(N) * 3
+    want_ippo = og.rollout_gae3(flags, r, v, nr, nv, gr, gv, 0.99, 0.95, heads=1, next_values=nxt)
+    adv_i, tgt_i = ops.gae3(c(flags), [c(r)], [c(v)], 0.99, 0.95, bootstrap=[c(nxt)])
+    close(adv_i[0], want_ippo["advantages"], 1e-4, 1e-5)
+    close(tgt_i[0], want_ippo["value_targets"], 1e-4, 1e-5)
+    assert not torch.equal(adv_i[0], adv1[0])
     # full-size property: linearity in the rewards (GAE is linear for fixed values / flags)
     T2, N2 = 50, 40 * 512
     fl = c(_random_flags(T2, 64, rng)).repeat(1, N2 // 64).contiguous()
