@@ -37,11 +37,10 @@ struct EnvIO {
     uint32_t* obs_split;   // [S][A][kp] bf16 pairs: the policy's tensor-core operand ([hi | lo], mlp_tc.cu), or null
     int kp;                // padded observation width (multiple of 64)
     // two-kernel mode: the state kernel hands these to the lidar kernel
-    float* pose;           // [S][rec_words]: x[A], y[A], cos[A], sin[A], {pair count, part mask lo, hi, 0}, then the
-                           // non-laser observation columns [D - n_ray][A]
+    float* pose;           // [S][rec_words]: x[A], y[A], cos[A], sin[A], {0, part mask lo, hi, 0}, the slots' lidar
+                           // broad-phase masks lo[A], hi[A] (boxes a laser of the slot can reach), then the non-laser
+                           // observation columns [D - n_ray][A]
     int rec_words;
-    uint16_t* pairs;       // [S][pair_stride]: queued (observer << 6 | box) lidar pairs
-    int pair_stride;
     int map_words;
     int tile_words;
     int obs_bulk;   // 1 when the obs tiles can leave through a bulk store (16-byte aligned base)
@@ -98,11 +97,63 @@ __host__ __device__ inline SmemPlan smem_plan(int G, int A, int D, int map_words
     p.f = o;     o += ((G * 6 * A + 3) & ~3) * 4;
     p.i = o;     o += ((G * (4 * A + MAX_SPAWN) + 3) & ~3) * 4;
     p.need = o;  o += ((3 * G + 4 + 3) & ~3) * 4;        // need[G], scene_done[G], queue fill (1 or per scene)
-    p.masks = o; o += G * 2 * 8;                         // per scene: participant / present slot masks
-    p.queue = o; o += ((G * A * A + 7) & ~7) * 2;
+    p.masks = o; o += G * 4 * 8;                         // per scene: four slot masks (SceneView::masks)
+    p.queue = o; o += split ? 0 : ((G * A * A + 7) & ~7) * 2;    // two-kernel mode: the lidar kernel builds the pair list
     p.geom = o;  (void)n_warps;
     p.total = o;
     return p;
+}
+
+// two fp32 values -> packed bf16 pairs: hi = bf16(x), lo = bf16(x - hi) (one packed conversion each; the same
+// bits as tc::split_rows_kernel produces, tests/test_env_gpu.py::test_env_emits_the_policy_operand)
+__device__ __forceinline__ void split_pair(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
+    hi = *reinterpret_cast<uint32_t*>(&h2);
+    float r0 = v0 - __uint_as_float(hi << 16);
+    float r1 = v1 - __uint_as_float(hi & 0xffff0000u);
+    __nv_bfloat162 l2 = __floats2bfloat162_rn(r0, r1);
+    lo = *reinterpret_cast<uint32_t*>(&l2);
+}
+
+// One warp holds up to 32 (observer, box) pairs, set up one per lane (PairGeom + the observer's laser row offset).
+// Their lasers are spread evenly over the lanes: laser r of the warp (0 <= r < total) belongs to the pair whose
+// [excl, excl + cnt) holds r.  Every live pair gets cnt >= 1 (an extra laser outside the window is harmless: the
+// slab test is exact) and dead lanes only trail the live ones, so the owner changes exactly at the set bits of
+// `starts` - the pair starts inside the current batch of 32 lasers, OR-reduced over the warp (REDUX) - and
+// owner lane = (pairs started before the batch) + popc(starts up to my laser) - 1.  No search.
+__device__ __forceinline__ void lidar_spread(const PairGeom& g, int lid_off, bool live, int n_ray, const float2* ray,
+                                             float* lasers) {
+    const int lane = threadIdx.x & 31;
+    const int cnt = live ? (g.cnt > 0 ? g.cnt : 1) : 0;
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int nb = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += nb;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    const int excl = incl - cnt;
+    const unsigned upto = 0xffffffffu >> (31 - lane);
+    int before = 0;
+    for (int r0 = 0; r0 < total; r0 += 32) {
+        const int pos = excl - r0;
+        const unsigned starts = __reduce_or_sync(0xffffffffu, (cnt > 0 && pos >= 0 && pos < 32) ? (1u << pos) : 0u);
+        const int lo = before + __popc(starts & upto) - 1;
+        before += __popc(starts);
+        const bool act = r0 + lane < total;
+        const int ex0 = __shfl_sync(0xffffffffu, excl, lo);
+        const int k0 = __shfl_sync(0xffffffffu, g.k0, lo);
+        const int off = __shfl_sync(0xffffffffu, lid_off, lo);
+        const float nx1 = __shfl_sync(0xffffffffu, g.nx1, lo), nx2 = __shfl_sync(0xffffffffu, g.nx2, lo);
+        const float ny1 = __shfl_sync(0xffffffffu, g.ny1, lo), ny2 = __shfl_sync(0xffffffffu, g.ny2, lo);
+        const float cc = __shfl_sync(0xffffffffu, g.cc, lo), ss = __shfl_sync(0xffffffffu, g.ss, lo);
+        if (act) {
+            int k = k0 + (r0 + lane - ex0);
+            k = (k >= n_ray) ? k - n_ray : k;
+            float2 rd = ray[k];
+            lidar_ray(nx1, nx2, ny1, ny2, cc, ss, rd.x, rd.y, lasers + off + k);
+        }
+    }
 }
 
 // SPLIT = false: the whole step in one kernel (observation tile in shared memory, lidar included).
@@ -132,14 +183,14 @@ env_step_kernel(const __grid_constant__ EnvConfig cfg, const __grid_constant__ E
     auto view = [&](int sl) {
         SceneView v;
         v.map = s_map; v.st = s_st + sl * io.tile_words;
-        v.obs = SPLIT ? io.pose + (size_t)(scene_base + sl) * io.rec_words + 4 * A + 4 : s_obs + (size_t)sl * A * D;
+        v.obs = SPLIT ? io.pose + (size_t)(scene_base + sl) * io.rec_words + 6 * A + 4 : s_obs + (size_t)sl * A * D;
         v.obs_compact = SPLIT ? 1 : 0;
         float* f = s_f + sl * 6 * A;
         v.cs = f; v.sn = f + A; v.rew = f + 2 * A; v.long_last = f + 3 * A; v.loc_s = f + 4 * A; v.loc_l = f + 5 * A;
         int* q = s_i + sl * (4 * A + MAX_SPAWN);
         v.flags = q; v.crash = q + A; v.acted = q + 2 * A; v.linger = q + 3 * A; v.place_free = q + 4 * A;
-        v.nqueue = SPLIT ? s_nq + sl : s_nq; v.queue = SPLIT ? s_queue + sl * A * A : s_queue;
-        v.scene_local = SPLIT ? 0 : sl; v.masks = s_masks + 2 * sl;
+        v.nqueue = s_nq; v.queue = s_queue;                  // fused mode only
+        v.scene_local = SPLIT ? 0 : sl; v.masks = s_masks + 4 * sl;
         v.A = A; v.AP = AP; v.D = D;
         return v;
     };
@@ -148,6 +199,7 @@ env_step_kernel(const __grid_constant__ EnvConfig cfg, const __grid_constant__ E
     const uint32_t map_bytes = (uint32_t)io.map_words * 4u;
     uint32_t parity = 0;
     if (tid == 0) mbar_init(bar, 1);
+    for (int k = tid; k < 4 * G; k += NT) s_masks[k] = 0ull;
     __syncthreads();
     bool first = true;
     const int sl_a = tid / A, ia = tid - sl_a * A;       // this thread's (scene in group, slot)
@@ -168,7 +220,6 @@ env_step_kernel(const __grid_constant__ EnvConfig cfg, const __grid_constant__ E
             bulk_g2s(s_st, g_tiles, (uint32_t)ng * tile_bytes, bar);
             *s_nq = 0;
         }
-        if (SPLIT && tid < G) s_nq[tid] = 0;
         float act0 = 0.0f, act1 = 0.0f;
         if (has_agent && !cfg.do_reset) {
             float2 a = reinterpret_cast<const float2*>(io.actions)[(size_t)scene0 * A + tid];
@@ -196,6 +247,7 @@ env_step_kernel(const __grid_constant__ EnvConfig cfg, const __grid_constant__ E
         // ---- P3: reward / termination (thread = slot) ----------------------------------------------------
         if (has_agent) {
             phase_outcome(v, cfg, ia);
+            if (ia == 0) { v.masks[2] = 0ull; v.masks[3] = 0ull; }      // the overlap phase is done with them
             if (v.status(ia) == ST_EMPTY || v.hdr(H_EP_STEP) >= cfg.horizon) s_need[sl_a] = 1;
         }
         __syncthreads();
@@ -226,6 +278,12 @@ env_step_kernel(const __grid_constant__ EnvConfig cfg, const __grid_constant__ E
         const bool spare = (NT - ng * A) >= ng;          // idle threads take the per-scene reductions
         if (has_agent) {
             NeiOut n = phase_neighbours(v, cfg, ia);
+            if constexpr (SPLIT) {
+                uint32_t* pm = reinterpret_cast<uint32_t*>(io.pose + (size_t)(scene0 + sl_a) * io.rec_words + 4 * A + 4);
+                pm[ia] = (uint32_t)n.cull_mask; pm[A + ia] = (uint32_t)(n.cull_mask >> 32);
+            } else {
+                queue_push_mask(v, ia, n.cull_mask);
+            }
             size_t g = (size_t)scene0 * A + tid;
             if (io.nei_mask) io.nei_mask[g] = n.nei_mask;
             if (io.mf_mask) io.mf_mask[g] = n.mf_mask;
@@ -253,7 +311,7 @@ env_step_kernel(const __grid_constant__ EnvConfig cfg, const __grid_constant__ E
         __syncthreads();
         if constexpr (!SPLIT) {
         // ---- P7: lidar.  Each warp takes 32 queued (observer, box) pairs, sets them up one per lane, then
-        // spreads the pairs' lasers evenly over its lanes (prefix sum + search through shuffles) -------------
+        // spreads the pairs' lasers evenly over its lanes (lidar_spread) ---------------------------------------
         {
             const int nq = *s_nq;
             const int lane = tid & 31, warp = tid >> 5;
@@ -270,37 +328,7 @@ env_step_kernel(const __grid_constant__ EnvConfig cfg, const __grid_constant__ E
                     lidar_pair_setup(view(sl), oi, oj, g);
                     lid_off = (sl * A + oi) * D + EGO_DIM + NAVI_DIM;
                 }
-                int incl = g.cnt;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    int nb = __shfl_up_sync(0xffffffffu, incl, d);
-                    if (lane >= d) incl += nb;
-                }
-                const int total = __shfl_sync(0xffffffffu, incl, 31);
-                const int excl = incl - g.cnt;
-                for (int r0 = 0; r0 < total; r0 += 32) {
-                    const int r = r0 + lane;
-                    const bool act = r < total;
-                    const int rr = act ? r : 0;
-                    int lo = 0;
-#pragma unroll
-                    for (int step = 16; step >= 1; step >>= 1) {
-                        int ex = __shfl_sync(0xffffffffu, excl, lo + step);
-                        if (ex <= rr) lo += step;
-                    }
-                    const int ex0 = __shfl_sync(0xffffffffu, excl, lo);
-                    const int k0 = __shfl_sync(0xffffffffu, g.k0, lo);
-                    const int off = __shfl_sync(0xffffffffu, lid_off, lo);
-                    const float nx1 = __shfl_sync(0xffffffffu, g.nx1, lo), nx2 = __shfl_sync(0xffffffffu, g.nx2, lo);
-                    const float ny1 = __shfl_sync(0xffffffffu, g.ny1, lo), ny2 = __shfl_sync(0xffffffffu, g.ny2, lo);
-                    const float cc = __shfl_sync(0xffffffffu, g.cc, lo), ss = __shfl_sync(0xffffffffu, g.ss, lo);
-                    if (act) {
-                        int k = k0 + (rr - ex0);
-                        k = (k >= n_ray) ? k - n_ray : k;
-                        float2 rd = ray2[k];
-                        lidar_ray(nx1, nx2, ny1, ny2, cc, ss, rd.x, rd.y, s_obs + off + k);
-                    }
-                }
+                lidar_spread(g, lid_off, e < nq, n_ray, ray2, s_obs);
             }
         }
         }
@@ -308,7 +336,7 @@ env_step_kernel(const __grid_constant__ EnvConfig cfg, const __grid_constant__ E
         __syncthreads();
         // ---- write back ------------------------------------------------------------------------------------
         if constexpr (SPLIT) {
-            // state tiles through a bulk store; poses, participant mask and the queued pairs to the scratch buffer
+            // state tiles through a bulk store; poses and the participant mask to the scratch buffer
             if (tid == 0) {
                 bulk_s2g(g_tiles, s_st, (uint32_t)ng * tile_bytes);
                 bulk_commit();
@@ -319,13 +347,8 @@ env_step_kernel(const __grid_constant__ EnvConfig cfg, const __grid_constant__ E
                 if (ia == 0) {
                     uint32_t* pi = reinterpret_cast<uint32_t*>(pr + 4 * A);
                     unsigned long long pm = v.masks[0];
-                    pi[0] = (uint32_t)s_nq[sl_a]; pi[1] = (uint32_t)pm; pi[2] = (uint32_t)(pm >> 32); pi[3] = 0u;
+                    pi[0] = 0u; pi[1] = (uint32_t)pm; pi[2] = (uint32_t)(pm >> 32); pi[3] = 0u;
                 }
-            }
-            for (int sl = 0; sl < ng; ++sl) {
-                const int nq = s_nq[sl];
-                uint16_t* gq = io.pairs + (size_t)(scene0 + sl) * io.pair_stride;
-                for (int e = tid; e < nq; e += NT) gq[e] = s_queue[sl * A * A + e];
             }
         } else {
         float* g_obs = io.obs + (size_t)scene0 * A * D;
@@ -365,30 +388,31 @@ env_step_kernel(const __grid_constant__ EnvConfig cfg, const __grid_constant__ E
 }
 
 // ---- lidar half of the two-kernel mode ---------------------------------------------------------------------------
-// One CTA works on `G` scenes at a time.  Everything a scene needs arrives through bulk copies: first the record the
-// state kernel left (poses, pair count, participant mask, the non-laser observation columns), then - while the
-// observation tile is being initialised - exactly the queued pairs.  The tile holds whole observation rows [A][D] in
-// shared memory (non-laser columns transposed in from the record, lasers lowered by the pair pass, same pair set-up /
-// laser distribution as the fused kernel) and leaves as one bulk store, plus once more as the policy's bf16 [hi | lo]
-// operand through 8-byte coalesced stores.  Nothing on this path waits on a dependent global load.
+// One CTA works on `G` scenes at a time.  Everything a scene needs arrives in ONE bulk copy: the record the state
+// kernel left (poses, participant mask, per-slot broad-phase masks, the non-laser observation columns).  Warp 0 turns
+// the masks into the (observer, box) pair list in shared memory (prefix sum of the mask populations) while the other
+// warps lay out the observation tile: whole rows [A][D] - lasers preset to "nothing within range", non-laser columns
+// transposed in from the record.  The pair pass lowers the lasers (same pair set-up / laser distribution as the fused
+// kernel), the tile leaves as one bulk store, plus once more as the policy's bf16 [hi | lo] operand through 8-byte
+// coalesced stores.  Nothing on this path waits on a dependent global load.
 struct LidarIO {
     const uint32_t* map;
     const float* pose;
-    const uint16_t* pairs;
     float* obs;
     uint32_t* obs_split;
     int pair_stride, rec_words, kp, group, S, A, D, n_ray, ray_off;
 };
 
 struct LidarPlan {
-    int ray, rec, pairs, tile, total;
+    int ray, rec, pairs, nq, tile, total;
 };
 __host__ __device__ inline LidarPlan lidar_plan(int G, int A, int D, int n_ray, int rec_words, int pair_stride) {
     LidarPlan p;
-    int o = 16;                                           // two mbarriers
+    int o = 16;                                           // mbarrier
     p.ray = o;   o += (n_ray * 8 + 15) & ~15;
     p.rec = o;   o += G * rec_words * 4;                  // rec_words is a multiple of 4
     p.pairs = o; o += G * pair_stride * 2;                // pair_stride is a multiple of 8
+    p.nq = o;    o += ((G + 3) & ~3) * 4;
     p.tile = o;  o += ((G * A * D + 3) & ~3) * 4;
     p.total = o;
     return p;
@@ -403,10 +427,10 @@ env_lidar_kernel(const __grid_constant__ LidarIO io) {
     const int rec = io.rec_words;
     const LidarPlan pl = lidar_plan(G, A, D, n_ray, rec, io.pair_stride);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);          // record arrivals
-    uint64_t* bar_q = bar + 1;                                      // pair-list arrivals
     float2* s_ray = reinterpret_cast<float2*>(smem_raw + pl.ray);
     float* s_rec = reinterpret_cast<float*>(smem_raw + pl.rec);
     uint16_t* s_pairs = reinterpret_cast<uint16_t*>(smem_raw + pl.pairs);
+    int* s_nq = reinterpret_cast<int*>(smem_raw + pl.nq);
     float* s_tile = reinterpret_cast<float*>(smem_raw + pl.tile);     // [G][A][D]
     const int n_groups = (io.S + G - 1) / G;
     const int lid0 = EGO_DIM + NAVI_DIM;
@@ -420,7 +444,6 @@ env_lidar_kernel(const __grid_constant__ LidarIO io) {
     uint32_t parity = 0;
     if (tid == 0) {
         mbar_init(bar, 1);
-        mbar_init(bar_q, 1);
         if ((int)blockIdx.x < n_groups) fetch_record(blockIdx.x);  // in flight while the laser table loads
     }
     {
@@ -428,46 +451,70 @@ env_lidar_kernel(const __grid_constant__ LidarIO io) {
         for (int k = tid; k < n_ray; k += NT) s_ray[k] = gr[k];
     }
     __syncthreads();
+    // warp 0 builds the pair lists, the other warps (all of them when there is only one) lay out the tile
+    const bool lays_out = (n_warps == 1) || (warp > 0);
+    const int lw = (n_warps == 1) ? 0 : warp - 1, n_lw = (n_warps == 1) ? 1 : n_warps - 1;
+    const bool rows_vec = ((D & 3) == 0);                         // rows start 16-byte aligned
     for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
         const int scene0 = grp * G;
         const int ng = (io.S - scene0 < G) ? io.S - scene0 : G;
         mbar_wait(bar, parity);
-        if (tid == 0) {
-            // the queued pairs of the group, rounded up to the bulk copy's 16-byte granule (inside the scene's stride)
-            uint32_t bytes = 0;
-            for (int sl = 0; sl < ng; ++sl)
-                bytes += ((reinterpret_cast<const uint32_t*>(s_rec + sl * rec + 4 * A)[0] * 2u) + 15u) & ~15u;
-            mbar_expect_tx(bar_q, bytes);
-            for (int sl = 0; sl < ng; ++sl) {
-                uint32_t b = ((reinterpret_cast<const uint32_t*>(s_rec + sl * rec + 4 * A)[0] * 2u) + 15u) & ~15u;
-                if (b) bulk_g2s(s_pairs + (size_t)sl * io.pair_stride,
-                                io.pairs + (size_t)(scene0 + sl) * io.pair_stride, b, bar_q);
-            }
-        }
-        // observation rows: lasers start at "nothing within range" for participants (0 for empty rows), the other
-        // columns come out of the record (stored slot-fastest by the state kernel)
+        parity ^= 1u;
         for (int sl = 0; sl < ng; ++sl) {
             const float* ps = s_rec + sl * rec;
             const uint32_t* hd = reinterpret_cast<const uint32_t*>(ps + 4 * A);
-            const unsigned long long pm = (unsigned long long)hd[1] | ((unsigned long long)hd[2] << 32);
-            float* tile = s_tile + (size_t)sl * A * D;
-            for (int i = warp; i < A; i += n_warps) {
-                const float val = ((pm >> i) & 1ull) ? 1.0f : 0.0f;
-                float* trow = tile + (size_t)i * D + lid0;
-                for (int k = lane; k < n_ray; k += 32) trow[k] = val;
+            if (warp == 0) {
+                // pair list: observer `o` owns popc(mask[o]) consecutive entries; each lane expands observers
+                // `lane` and `lane + 32` (A <= 64)
+                const uint32_t* cl = hd + 4;
+                const uint32_t* ch = cl + A;
+                const int o0 = lane, o1 = lane + 32;
+                unsigned long long m0 = (o0 < A) ? ((unsigned long long)cl[o0] | ((unsigned long long)ch[o0] << 32)) : 0ull;
+                unsigned long long m1 = (o1 < A) ? ((unsigned long long)cl[o1] | ((unsigned long long)ch[o1] << 32)) : 0ull;
+                const int c0 = __popcll(m0), c1 = __popcll(m1);
+                int i0 = c0, i1 = c1;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    int n0 = __shfl_up_sync(0xffffffffu, i0, d), n1 = __shfl_up_sync(0xffffffffu, i1, d);
+                    if (lane >= d) { i0 += n0; i1 += n1; }
+                }
+                const int t0 = __shfl_sync(0xffffffffu, i0, 31), t1 = __shfl_sync(0xffffffffu, i1, 31);
+                uint16_t* q = s_pairs + (size_t)sl * io.pair_stride;
+                int w0 = i0 - c0, w1 = t0 + i1 - c1;
+#pragma unroll 1
+                while (m0 | m1) {
+                    if (m0) { const int j = __ffsll((long long)m0) - 1; m0 &= m0 - 1ull; q[w0++] = (uint16_t)((o0 << 6) | j); }
+                    if (m1) { const int j = __ffsll((long long)m1) - 1; m1 &= m1 - 1ull; q[w1++] = (uint16_t)((o1 << 6) | j); }
+                }
+                if (lane == 0) s_nq[sl] = t0 + t1;
             }
-            const float* eg = ps + 4 * A + 4;
-            for (int idx = tid; idx < n_ego * A; idx += NT) {
-                const int c = idx / A, i = idx - c * A;
-                tile[(size_t)i * D + (c < lid0 ? c : c + n_ray)] = eg[idx];
+            if (lays_out) {
+                // observation rows: lasers start at "nothing within range" for participants (0 for empty rows), the
+                // other columns come out of the record (stored slot-fastest by the state kernel)
+                const unsigned long long pm = (unsigned long long)hd[1] | ((unsigned long long)hd[2] << 32);
+                float* tile = s_tile + (size_t)sl * A * D;
+                const float* eg = ps + 6 * A + 4;
+                for (int i = lw; i < A; i += n_lw) {
+                    const float val = ((pm >> i) & 1ull) ? 1.0f : 0.0f;
+                    float* trow = tile + (size_t)i * D;
+                    if (rows_vec) {
+                        float4* t4 = reinterpret_cast<float4*>(trow);
+#pragma unroll 1
+                        for (int k = lane; k < (D >> 2); k += 32) t4[k] = make_float4(val, val, val, val);
+                    } else {
+#pragma unroll 1
+                        for (int k = lane; k < D; k += 32) trow[k] = val;
+                    }
+                    __syncwarp();
+#pragma unroll 1
+                    for (int c = lane; c < n_ego; c += 32) trow[c < lid0 ? c : c + n_ray] = eg[c * A + i];
+                }
             }
         }
-        mbar_wait(bar_q, parity);                                 // pairs have landed
-        parity ^= 1u;                                             // both barriers complete one phase per group
         __syncthreads();
         for (int sl = 0; sl < ng; ++sl) {
             const float* ps = s_rec + sl * rec;
-            const int nq = (int)reinterpret_cast<const uint32_t*>(ps + 4 * A)[0];
+            const int nq = s_nq[sl];
             const uint16_t* gq = s_pairs + (size_t)sl * io.pair_stride;
             float* tile = s_tile + (size_t)sl * A * D + lid0;
             for (int base = warp * 32; base < nq; base += n_warps * 32) {
@@ -482,37 +529,7 @@ env_lidar_kernel(const __grid_constant__ LidarIO io) {
                                     ps[3 * A + oj], n_ray, g);
                     lid_off = oi * D;
                 }
-                int incl = g.cnt;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    int nb = __shfl_up_sync(0xffffffffu, incl, d);
-                    if (lane >= d) incl += nb;
-                }
-                const int total = __shfl_sync(0xffffffffu, incl, 31);
-                const int excl = incl - g.cnt;
-                for (int r0 = 0; r0 < total; r0 += 32) {
-                    const int r = r0 + lane;
-                    const bool act = r < total;
-                    const int rr = act ? r : 0;
-                    int lo = 0;
-#pragma unroll
-                    for (int step = 16; step >= 1; step >>= 1) {
-                        int ex = __shfl_sync(0xffffffffu, excl, lo + step);
-                        if (ex <= rr) lo += step;
-                    }
-                    const int ex0 = __shfl_sync(0xffffffffu, excl, lo);
-                    const int k0 = __shfl_sync(0xffffffffu, g.k0, lo);
-                    const int off = __shfl_sync(0xffffffffu, lid_off, lo);
-                    const float nx1 = __shfl_sync(0xffffffffu, g.nx1, lo), nx2 = __shfl_sync(0xffffffffu, g.nx2, lo);
-                    const float ny1 = __shfl_sync(0xffffffffu, g.ny1, lo), ny2 = __shfl_sync(0xffffffffu, g.ny2, lo);
-                    const float cc = __shfl_sync(0xffffffffu, g.cc, lo), ss = __shfl_sync(0xffffffffu, g.ss, lo);
-                    if (act) {
-                        int k = k0 + (rr - ex0);
-                        k = (k >= n_ray) ? k - n_ray : k;
-                        float2 rd = s_ray[k];
-                        lidar_ray(nx1, nx2, ny1, ny2, cc, ss, rd.x, rd.y, tile + off + k);
-                    }
-                }
+                lidar_spread(g, lid_off, e < nq, n_ray, s_ray, tile);
             }
         }
         fence_async_smem();
@@ -540,19 +557,12 @@ env_lidar_kernel(const __grid_constant__ LidarIO io) {
                 for (int row = warp; row < n_rows; row += n_warps) {
                     const float4* trow = reinterpret_cast<const float4*>(s_tile + (size_t)row * D);
                     uint2* srow = reinterpret_cast<uint2*>(g_sp + (size_t)row * io.kp);
+#pragma unroll 1
                     for (int q = lane; q < (half >> 1); q += 32) {
                         float4 x = (4 * q < D) ? trow[q] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                        __nv_bfloat16 h0 = __float2bfloat16_rn(x.x), h1 = __float2bfloat16_rn(x.y);
-                        __nv_bfloat16 h2 = __float2bfloat16_rn(x.z), h3 = __float2bfloat16_rn(x.w);
-                        __nv_bfloat16 l0 = __float2bfloat16_rn(x.x - __bfloat162float(h0));
-                        __nv_bfloat16 l1 = __float2bfloat16_rn(x.y - __bfloat162float(h1));
-                        __nv_bfloat16 l2 = __float2bfloat16_rn(x.z - __bfloat162float(h2));
-                        __nv_bfloat16 l3 = __float2bfloat16_rn(x.w - __bfloat162float(h3));
                         uint2 hi, lo;
-                        hi.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                        hi.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
-                        lo.x = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-                        lo.y = (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16);
+                        split_pair(x.x, x.y, hi.x, lo.x);
+                        split_pair(x.z, x.w, hi.y, lo.y);
                         srow[q] = hi;
                         srow[(half >> 1) + q] = lo;
                     }
@@ -595,7 +605,6 @@ struct b2c_env {
     int lidar_group, lidar_threads, lidar_ctas, ray_off;
     size_t lidar_smem;
     float* d_pose;
-    uint16_t* d_pairs;
     int pair_stride, n_ray, rec_words;
     uint32_t* d_map;
     uint32_t* d_state;
@@ -659,7 +668,7 @@ int b2c_env_create(const b2c_env_config* c, const uint32_t* map_blob, int map_wo
     }
     e->smem = (size_t)smem_plan(e->group, k.A, k.D, map_words, e->tile_words, e->threads / 32, e->split).total;
     e->n_ray = (int)map_blob[M_NRAY];
-    e->d_pose = nullptr; e->d_pairs = nullptr;
+    e->d_pose = nullptr;
     if (e->split) {
         B2C_CUDA_OR(cudaFuncSetAttribute(env_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem),
                     delete e);
@@ -672,7 +681,7 @@ int b2c_env_create(const b2c_env_config* c, const uint32_t* map_blob, int map_wo
         e->lidar_group = 1;
         if (const char* g = getenv("B2C_LIDAR_GROUP")) e->lidar_group = atoi(g) > 0 ? atoi(g) : 1;
         e->pair_stride = (k.A * k.A + 7) & ~7;
-        e->rec_words = (4 * k.A + 4 + (k.D - e->n_ray) * k.A + 3) & ~3;
+        e->rec_words = (6 * k.A + 4 + (k.D - e->n_ray) * k.A + 3) & ~3;
         auto lsm = [&](int g) { return (size_t)lidar_plan(g, k.A, k.D, e->n_ray, e->rec_words, e->pair_stride).total; };
         while (e->lidar_group > 1 && lsm(e->lidar_group) > 100 * 1024) e->lidar_group -= 1;
         if (e->lidar_group > k.S) e->lidar_group = k.S;
@@ -680,7 +689,6 @@ int b2c_env_create(const b2c_env_config* c, const uint32_t* map_blob, int map_wo
         B2C_CUDA_OR(cudaFuncSetAttribute(env_lidar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->lidar_smem),
                     delete e);
         B2C_CUDA_OR(cudaMalloc(&e->d_pose, (size_t)k.S * e->rec_words * 4), delete e);
-        B2C_CUDA_OR(cudaMalloc(&e->d_pairs, (size_t)k.S * e->pair_stride * 2), delete e);
     } else {
         B2C_CUDA_OR(cudaFuncSetAttribute(env_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem),
                     delete e);
@@ -698,7 +706,6 @@ int b2c_env_destroy(b2c_env* e) {
     cudaFree(e->d_map);
     cudaFree(e->d_state);
     cudaFree(e->d_pose);
-    cudaFree(e->d_pairs);
     delete e;
     return B2C_OK;
 }
@@ -706,7 +713,7 @@ int b2c_env_destroy(b2c_env* e) {
 static void launch_lidar(b2c_env* e, float* obs, uint32_t* obs_split, int kp, cudaStream_t st) {
     const EnvConfig& cfg = e->cfg;
     LidarIO li;
-    li.map = e->d_map; li.pose = e->d_pose; li.pairs = e->d_pairs; li.obs = obs; li.obs_split = obs_split;
+    li.map = e->d_map; li.pose = e->d_pose; li.obs = obs; li.obs_split = obs_split;
     li.pair_stride = e->pair_stride; li.rec_words = e->rec_words; li.n_ray = e->n_ray; li.ray_off = e->ray_off;
     li.kp = kp; li.group = e->lidar_group; li.S = cfg.S; li.A = cfg.A; li.D = cfg.D;
     // one CTA per group of scenes (the hardware scheduler balances the uneven pair counts); very large batches loop
@@ -732,7 +739,7 @@ static int launch_env(b2c_env* e, const float* actions, const b2c_env_io* o, int
     io.map_words = e->map_words; io.tile_words = e->tile_words;
     io.obs_bulk = ((((size_t)cfg.A * cfg.D * 4) % 16 == 0) && (((uintptr_t)o->obs) % 16 == 0)) ? 1 : 0;
     io.group = e->group;
-    io.pose = e->d_pose; io.pairs = e->d_pairs; io.pair_stride = e->pair_stride; io.rec_words = e->rec_words;
+    io.pose = e->d_pose; io.rec_words = e->rec_words;
     int ctas_per_sm = (int)(227 * 1024 / (e->smem + 1024));
     int by_threads = 2048 / e->threads;
     if (ctas_per_sm > by_threads) ctas_per_sm = by_threads;

@@ -23,6 +23,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include "b2c_internal.h"
 #include "rng.cuh"
 
@@ -119,6 +120,14 @@ __device__ __forceinline__ float fast_tanh(float x) {
     q = fmaf(q, x2, 4.89352518554385e-03f);
     return __fdividef(p, q);
 }
+// 32-byte global store (sm_100: STG.256): one thread fills a whole 32-byte sector, so the row-per-thread epilogue
+// writes full sectors instead of two half-filled ones per 16-byte store pair
+__device__ __forceinline__ void st_global_256(void* p, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4,
+                                              uint32_t a5, uint32_t a6, uint32_t a7) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a0), "r"(a1), "r"(a2), "r"(a3),
+                 "r"(a4), "r"(a5), "r"(a6), "r"(a7)
+                 : "memory");
+}
 __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
     return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
@@ -130,6 +139,7 @@ struct LinearArgs {
     uint16_t* out_split;      // [M][512] bf16 (hi | lo) or null
     int M, kp_blocks;         // kp_blocks = Kp / 64 reduction blocks, four products each
     int ld_out, ld_src, act;  // act: 0 none, 1 tanh
+    int wide_f32, wide_split; // 1: the output rows are 32-byte aligned (256-bit stores)
     // fused narrow output layer on the activated result: head_out[m][j] = head_b[j] + sum_n y[m][n] head_w[j][n]
     const float* head_w;      // [head_n][256] or null
     const float* head_b;      // [head_n] or null
@@ -284,9 +294,19 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         }
                     }
                     if (args.out_f32) {
-                        float4* o = reinterpret_cast<float4*>(args.out_f32 + (size_t)row * args.ld_out + c * 32);
+                        float* op = args.out_f32 + (size_t)row * args.ld_out + c * 32;
+                        if (args.wide_f32) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                            for (int j = 0; j < 4; ++j)
+                                st_global_256(op + 8 * j, __float_as_uint(v[8 * j]), __float_as_uint(v[8 * j + 1]),
+                                              __float_as_uint(v[8 * j + 2]), __float_as_uint(v[8 * j + 3]),
+                                              __float_as_uint(v[8 * j + 4]), __float_as_uint(v[8 * j + 5]),
+                                              __float_as_uint(v[8 * j + 6]), __float_as_uint(v[8 * j + 7]));
+                        } else {
+                            float4* o = reinterpret_cast<float4*>(op);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        }
                     }
                     if (args.out_split) {
                         uint32_t hi[16], lo[16];
@@ -299,12 +319,23 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                             __nv_bfloat162 l2 = __floats2bfloat162_rn(r0, r1);
                             hi[j] = hb; lo[j] = *reinterpret_cast<uint32_t*>(&l2);
                         }
-                        uint4* oh = reinterpret_cast<uint4*>(args.out_split + (size_t)row * 512 + c * 32);
-                        uint4* ol = reinterpret_cast<uint4*>(args.out_split + (size_t)row * 512 + 256 + c * 32);
+                        uint16_t* ohp = args.out_split + (size_t)row * 512 + c * 32;
+                        if (args.wide_split) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            oh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-                            ol[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                            for (int j = 0; j < 2; ++j) {
+                                st_global_256(ohp + 16 * j, hi[8 * j], hi[8 * j + 1], hi[8 * j + 2], hi[8 * j + 3],
+                                              hi[8 * j + 4], hi[8 * j + 5], hi[8 * j + 6], hi[8 * j + 7]);
+                                st_global_256(ohp + 256 + 16 * j, lo[8 * j], lo[8 * j + 1], lo[8 * j + 2], lo[8 * j + 3],
+                                              lo[8 * j + 4], lo[8 * j + 5], lo[8 * j + 6], lo[8 * j + 7]);
+                            }
+                        } else {
+                            uint4* oh = reinterpret_cast<uint4*>(ohp);
+                            uint4* ol = reinterpret_cast<uint4*>(ohp + 256);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                oh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                                ol[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                            }
                         }
                     }
                 }
@@ -654,6 +685,10 @@ static int tc_linear_launch(const uint16_t* a_split, const uint16_t* w_prep, con
     LinearArgs a;
     a.bias = bias; a.dtanh_src = dtanh_src; a.out_f32 = out_f32; a.out_split = out_split; a.M = M;
     a.kp_blocks = Kp / BLOCK_K; a.ld_out = ld_out; a.ld_src = ld_src; a.act = act;
+    a.wide_f32 = (out_f32 && ((uintptr_t)out_f32 & 31) == 0 && (ld_out & 7) == 0) ? 1 : 0;
+    a.wide_split = (out_split && ((uintptr_t)out_split & 31) == 0) ? 1 : 0;
+    static const bool narrow = getenv("B2C_TC_NARROW_STORES") != nullptr;    // A/B switch for measurements
+    if (narrow) a.wide_f32 = a.wide_split = 0;
     a.head_w = nullptr; a.head_b = nullptr; a.head_out = nullptr; a.head_n = 0; a.actions = nullptr; a.logp = nullptr;
     a.seed = 0; a.step = 0;
     if (head) {

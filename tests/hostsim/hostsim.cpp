@@ -21,7 +21,7 @@ extern "C" int hostsim_step(const EnvConfig* cfgp, const uint32_t* map, int map_
     const int tile_words = NUM_FIELDS * AP + HEADER_WORDS;
     std::vector<float> fbuf(6 * A), obs((size_t)A * D);
     std::vector<int> ibuf(4 * A + MAX_SPAWN + 1);
-    unsigned long long masks[2];
+    unsigned long long masks[4];
     std::vector<uint16_t> queue((size_t)A * A);
     for (int scene = 0; scene < cfg.S; ++scene) {
         SceneView v;
@@ -31,7 +31,7 @@ extern "C" int hostsim_step(const EnvConfig* cfgp, const uint32_t* map, int map_
         v.loc_l = s_f + 5 * A;
         v.flags = s_i; v.crash = s_i + A; v.acted = s_i + 2 * A; v.linger = s_i + 3 * A;
         v.place_free = s_i + 4 * A; v.nqueue = s_i + 4 * A + MAX_SPAWN; v.queue = queue.data(); v.scene_local = 0;
-        v.masks = masks; masks[0] = masks[1] = 0ull;
+        v.masks = masks; masks[0] = masks[1] = masks[2] = masks[3] = 0ull;
         v.A = A; v.AP = AP; v.D = D;
         *v.nqueue = 0;
         if (cfg.do_reset) {
@@ -53,6 +53,7 @@ extern "C" int hostsim_step(const EnvConfig* cfgp, const uint32_t* map, int map_
         for (int i = 0; i < A; ++i) { phase_pose_refresh(v, i); phase_masks(v, i); }
         for (int i = 0; i < A; ++i) {
             NeiOut n = phase_neighbours(v, cfg, i);
+            queue_push_mask(v, i, n.cull_mask);
             size_t g = (size_t)scene * A + i;
             io->nei_mask[g] = n.nei_mask; io->mf_mask[g] = n.mf_mask; io->nei_reward[g] = n.nei_reward;
             for (int k = 0; k < NEI_K; ++k) io->nei_list[g * NEI_K + k] = n.list[k];
@@ -78,7 +79,7 @@ extern "C" int hostsim_lidar_window_audit(const uint32_t* map, int n_cases, unsi
     std::vector<float> fbuf(6 * A), obs((size_t)A * D), ref((size_t)A * D);
     std::vector<int> ibuf(4 * A + MAX_SPAWN + 1, 0);
     std::vector<uint16_t> queue(4);
-    unsigned long long masks[2] = {3ull, 3ull};
+    unsigned long long masks[4] = {3ull, 3ull, 0ull, 0ull};
     SceneView v;
     v.masks = masks;
     v.map = map; v.st = st.data(); v.obs = obs.data();
