@@ -37,6 +37,17 @@ constexpr int STAGE_BYTES = 2 * A_STAGE_BYTES + 2 * B_STAGE_BYTES;     // A_hi, 
 constexpr int HEAD_MAX = 4;                               // fused narrow output layer: up to 4 outputs
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 1024 /*bias*/ +
                            HEAD_MAX * BLOCK_N * 4 /*head weights*/ + 2 * BLOCK_M * HEAD_MAX * 4 /*head partials*/;
+// "resident weights" mode (reduction length <= 128, no fused output layer - the first layer of every network): the
+// whole prepared weight matrix (hi | lo, 64 KB per reduction block) stays in shared memory for the life of the CTA and
+// only the A blocks (32 KB) stream through a deeper ring, so the weights cross L2 -> shared memory once per CTA instead
+// of once per 128-row tile.
+constexpr int MAX_STAGES = 4;
+constexpr int A_PAIR_BYTES = 2 * A_STAGE_BYTES;           // A_hi + A_lo of one reduction block: 32 KB
+constexpr int W_PAIR_BYTES = 2 * B_STAGE_BYTES;           // W_hi + W_lo of one reduction block: 64 KB
+constexpr int SMEM_MAX_OPTIN = 232448;
+__host__ __device__ constexpr int resident_smem_bytes(int kp_blocks, int a_stages) {
+    return kp_blocks * W_PAIR_BYTES + a_stages * A_PAIR_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 1024 /*bias*/;
+}
 constexpr int TMEM_COLS = 512;
 constexpr int EPI_WARPS = 8;
 constexpr int NUM_THREADS = 128 + EPI_WARPS * 32;
@@ -140,6 +151,7 @@ struct LinearArgs {
     int M, kp_blocks;         // kp_blocks = Kp / 64 reduction blocks, four products each
     int ld_out, ld_src, act;  // act: 0 none, 1 tanh
     int wide_f32, wide_split; // 1: the output rows are 32-byte aligned (256-bit stores)
+    int resident, stages;     // resident weights mode; ring depth
     // fused narrow output layer on the activated result: head_out[m][j] = head_b[j] + sum_n y[m][n] head_w[j][n]
     const float* head_w;      // [head_n][256] or null
     const float* head_b;      // [head_n] or null
@@ -156,12 +168,19 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                  const __grid_constant__ LinearArgs args) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-    uint64_t* empty = full + STAGES;
-    uint64_t* tmem_full = empty + STAGES;
+    const bool resident = args.resident != 0;
+    const int n_stages = args.stages;
+    const int stage_bytes = resident ? A_PAIR_BYTES : STAGE_BYTES;
+    uint8_t* s_w = smem;                                         // resident mode: [kp_blocks][W_hi | W_lo]
+    uint8_t* ring = smem + (resident ? args.kp_blocks * W_PAIR_BYTES : 0);
+    uint8_t* misc = ring + n_stages * stage_bytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(misc);
+    uint64_t* empty = full + MAX_STAGES;
+    uint64_t* tmem_full = empty + MAX_STAGES;
     uint64_t* tmem_empty = tmem_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-    float* s_bias = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);
+    uint64_t* w_full = tmem_empty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
+    float* s_bias = reinterpret_cast<float*>(misc + 256);
     float* s_head_w = s_bias + BLOCK_N;                          // [HEAD_MAX][256]
     float* s_part = s_head_w + HEAD_MAX * BLOCK_N;               // [2 halves... upper half's partials][128][HEAD_MAX]
 
@@ -175,8 +194,9 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < n_stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], EPI_WARPS); }
+        mbar_init(w_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -196,16 +216,25 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         // ===== TMA producer =====
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
+            if (resident) {
+                mbar_expect_tx(w_full, (uint32_t)(num_kb * W_PAIR_BYTES));
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    tma_load_2d(s_w + kb * W_PAIR_BYTES, &map_w, kb * BLOCK_K, 0, w_full);                       // W_hi
+                    tma_load_2d(s_w + kb * W_PAIR_BYTES + B_STAGE_BYTES, &map_w, kp + kb * BLOCK_K, 0, w_full);  // W_lo
+                }
+            }
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1u);
-                    uint8_t* st = smem + stage * STAGE_BYTES;
-                    mbar_expect_tx(&full[stage], STAGE_BYTES);
+                    uint8_t* st = ring + stage * stage_bytes;
+                    mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
                     tma_load_2d(st, &map_a, kb * BLOCK_K, tile * BLOCK_M, &full[stage]);                       // A_hi
                     tma_load_2d(st + A_STAGE_BYTES, &map_a, kp + kb * BLOCK_K, tile * BLOCK_M, &full[stage]);  // A_lo
-                    tma_load_2d(st + 2 * A_STAGE_BYTES, &map_w, kb * BLOCK_K, 0, &full[stage]);                // W_hi
-                    tma_load_2d(st + 2 * A_STAGE_BYTES + B_STAGE_BYTES, &map_w, kp + kb * BLOCK_K, 0, &full[stage]);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                    if (!resident) {
+                        tma_load_2d(st + 2 * A_STAGE_BYTES, &map_w, kb * BLOCK_K, 0, &full[stage]);            // W_hi
+                        tma_load_2d(st + 2 * A_STAGE_BYTES + B_STAGE_BYTES, &map_w, kp + kb * BLOCK_K, 0, &full[stage]);
+                    }
+                    if (++stage == n_stages) { stage = 0; phase ^= 1u; }
                 }
             }
         }
@@ -214,6 +243,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
+            if (resident) mbar_wait(w_full, 0u);                 // the weights have landed (once per CTA)
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
                 tc_fence_after();
@@ -221,10 +251,11 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                    const uint32_t sa = smem_u32(ring + stage * stage_bytes);
+                    const uint32_t sw = resident ? smem_u32(s_w + kb * W_PAIR_BYTES) : sa + 2 * A_STAGE_BYTES;
                     const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + A_STAGE_BYTES);
-                    const uint64_t w_hi = make_desc(sa + 2 * A_STAGE_BYTES);
-                    const uint64_t w_lo = make_desc(sa + 2 * A_STAGE_BYTES + B_STAGE_BYTES);
+                    const uint64_t w_hi = make_desc(sw);
+                    const uint64_t w_lo = make_desc(sw + B_STAGE_BYTES);
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                         // advance the start address by 32 B (16 bf16) inside the 128 B swizzle row
@@ -236,7 +267,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     }
                     umma_commit(&empty[stage]);                  // frees the smem slot when these MMAs retire
                     if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                    if (++stage == n_stages) { stage = 0; phase ^= 1u; }
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
@@ -671,7 +702,7 @@ static int tc_linear_launch(const uint16_t* a_split, const uint16_t* w_prep, con
     static int attr_set = 0;
     static int num_sms = 0;
     if (!attr_set) {
-        B2C_CUDA(cudaFuncSetAttribute(tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        B2C_CUDA(cudaFuncSetAttribute(tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX_OPTIN));
         int dev = 0;
         B2C_CUDA(cudaGetDevice(&dev));
         B2C_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -687,8 +718,17 @@ static int tc_linear_launch(const uint16_t* a_split, const uint16_t* w_prep, con
     a.kp_blocks = Kp / BLOCK_K; a.ld_out = ld_out; a.ld_src = ld_src; a.act = act;
     a.wide_f32 = (out_f32 && ((uintptr_t)out_f32 & 31) == 0 && (ld_out & 7) == 0) ? 1 : 0;
     a.wide_split = (out_split && ((uintptr_t)out_split & 31) == 0) ? 1 : 0;
-    static const bool narrow = getenv("B2C_TC_NARROW_STORES") != nullptr;    // A/B switch for measurements
+    static const bool narrow = getenv("B2C_TC_NARROW_STORES") != nullptr;    // A/B switches for measurements
+    static const bool streamed = getenv("B2C_TC_STREAM_WEIGHTS") != nullptr;
     if (narrow) a.wide_f32 = a.wide_split = 0;
+    a.resident = 0; a.stages = STAGES;
+    int smem_bytes = SMEM_BYTES;
+    if (!head && a.kp_blocks <= 2 && !streamed) {
+        a.resident = 1;
+        a.stages = MAX_STAGES;
+        while (a.stages > 2 && resident_smem_bytes(a.kp_blocks, a.stages) > SMEM_MAX_OPTIN) a.stages -= 1;
+        smem_bytes = resident_smem_bytes(a.kp_blocks, a.stages);
+    }
     a.head_w = nullptr; a.head_b = nullptr; a.head_out = nullptr; a.head_n = 0; a.actions = nullptr; a.logp = nullptr;
     a.seed = 0; a.step = 0;
     if (head) {
@@ -697,7 +737,7 @@ static int tc_linear_launch(const uint16_t* a_split, const uint16_t* w_prep, con
     }
     int tiles = (M + BLOCK_M - 1) / BLOCK_M;
     int grid = tiles < num_sms ? tiles : num_sms;
-    tc_linear_kernel<<<grid, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(map_a, map_w, a);
+    tc_linear_kernel<<<grid, NUM_THREADS, smem_bytes, (cudaStream_t)stream>>>(map_a, map_w, a);
     B2C_CUDA(cudaGetLastError());
     return B2C_OK;
 }

@@ -14,8 +14,10 @@ def _ref(x, W, b, act):
 
 
 @pytest.mark.parametrize("M,K", [(128, 64), (1000, 92), (4096 + 37, 256), (300, 157), (129, 184), (77, 463), (1, 92),
-                                 (40000, 92)])
+                                 (40000, 92), (148 * 128 * 3 + 77, 92), (148 * 128 * 5, 40)])
 def test_tc_linear_forward(M, K):
+    """Reduction lengths up to 128 run with the weights resident in shared memory (several tiles per CTA in the two
+    largest cases: the A ring wraps), longer ones stream the weights with the activations."""
     from copo_b200 import ops
     g = torch.Generator().manual_seed(M * 7 + K)
     x = torch.rand(M, K, generator=g)
