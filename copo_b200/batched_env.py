@@ -81,13 +81,23 @@ class BatchedDrivingEnv:
         _lib.check(self.lib.b2c_env_reset(self._h, ctypes.byref(io), int(new_episode), _lib.stream_ptr()))
         return out
 
-    def step(self, actions, out=None):
-        """actions: float32 device tensor [S, A, 2]; returns the dict of output tensors (views, not copies)."""
+    def step(self, actions, out=None, scenes=None):
+        """actions: float32 device tensor [S, A, 2]; returns the dict of output tensors (views, not copies).
+        scenes=(first, count) steps only that range of scenes: `actions` and every tensor of `out` then hold just
+        those scenes ([count, A, ...]); stepping the ranges of a partition equals one full step."""
         out = out if out is not None else self.out
         assert actions.dtype == torch.float32 and actions.is_cuda and actions.is_contiguous()
-        assert tuple(actions.shape) == (self.S, self.A, 2), actions.shape
-        io = self._io(out)
-        _lib.check(self.lib.b2c_env_step(self._h, _lib.ptr(actions), ctypes.byref(io), _lib.stream_ptr()))
+        if scenes is None:
+            assert tuple(actions.shape) == (self.S, self.A, 2), actions.shape
+            io = self._io(out)
+            _lib.check(self.lib.b2c_env_step(self._h, _lib.ptr(actions), ctypes.byref(io), _lib.stream_ptr()))
+        else:
+            first, count = int(scenes[0]), int(scenes[1])
+            assert tuple(actions.shape) == (count, self.A, 2), actions.shape
+            assert all(v is None or v.shape[0] == count for v in out.values()), "outputs must hold the scene range"
+            io = self._io(out)
+            _lib.check(self.lib.b2c_env_step_scenes(self._h, _lib.ptr(actions), ctypes.byref(io), first, count,
+                                                    _lib.stream_ptr()))
         _lib.LAUNCHES += self.kernels_per_step - 1          # the launch counter counts kernels, not calls
         return out
 
@@ -102,8 +112,10 @@ class BatchedDrivingEnv:
     _host = None
 
     def _host_buffers(self):
-        """One device arena and one pinned host arena hold every output of a host-facing step, so a step's results
-        cross PCIe as ONE copy on a dedicated copy stream (the kernels write straight into the device arena)."""
+        """One device arena and one pinned host arena hold every output of a host-facing step (the kernels write
+        straight into the device arena; observations first, everything else behind them).  The scenes are stepped in
+        `host_chunks` ranges: a range's observations start crossing PCIe on a dedicated copy stream while the next
+        range is still being computed; the small outputs follow as one last copy."""
         if self._host is None:
             offs, size = {}, 0
             for k in self.HOST_KEYS:
@@ -112,6 +124,7 @@ class BatchedDrivingEnv:
                 size += (t.numel() * t.element_size() + 255) & ~255
             self._arena_dev = torch.zeros(size, dtype=torch.uint8, device=self.device)
             self._arena_host = torch.zeros(size, dtype=torch.uint8).pin_memory()
+            self._rest_off = offs[self.HOST_KEYS[1]]
 
             def views(arena):
                 d = {}
@@ -123,10 +136,16 @@ class BatchedDrivingEnv:
             self._host = views(self._arena_host)
             self.host_step_out = dict(self.out)          # device side of the same step (arena views + mf_mask)
             self.host_step_out.update(views(self._arena_dev))
+            self.host_step_out["obs_split"] = None
+            K = max(1, min(int(getattr(self, "host_chunks", 4)), self.S // 64 if self.S >= 128 else 1))
+            per = (self.S + K - 1) // K
+            self._chunks = [(f, min(per, self.S - f)) for f in range(0, self.S, per)]
+            self._chunk_out = [{k: (v[f:f + n] if v is not None else None) for k, v in self.host_step_out.items()}
+                               for f, n in self._chunks]
             self._dev_act = torch.empty((self.S, self.A, 2), dtype=torch.float32, device=self.device)
             self._pin_act = torch.empty((self.S, self.A, 2), dtype=torch.float32).pin_memory()
             self._copy_stream = torch.cuda.Stream(device=self.device)
-            self._ev_step = torch.cuda.Event()
+            self._ev_chunk = [torch.cuda.Event() for _ in self._chunks]
             self._ev_copy = torch.cuda.Event()
             self._copy_pending = False
             self.h2d_bytes_per_step = self._dev_act.numel() * 4
@@ -148,11 +167,17 @@ class BatchedDrivingEnv:
             cur.wait_event(self._ev_copy)
         self._dev_act.copy_(a, non_blocking=True)
         self.host_step_out["obs_split"] = obs_split
-        self.step(self._dev_act, out=self.host_step_out)
-        self._ev_step.record(cur)
-        self._copy_stream.wait_event(self._ev_step)
+        dev_obs, host_obs = self.host_step_out["obs"], host["obs"]
+        for c, (f, n) in enumerate(self._chunks):
+            out = self._chunk_out[c]
+            out["obs_split"] = obs_split[f:f + n] if obs_split is not None else None
+            self.step(self._dev_act[f:f + n], out=out, scenes=(f, n))
+            self._ev_chunk[c].record(cur)
+            self._copy_stream.wait_event(self._ev_chunk[c])
+            with torch.cuda.stream(self._copy_stream):
+                host_obs[f:f + n].copy_(dev_obs[f:f + n], non_blocking=True)
         with torch.cuda.stream(self._copy_stream):
-            self._arena_host.copy_(self._arena_dev, non_blocking=True)
+            self._arena_host[self._rest_off:].copy_(self._arena_dev[self._rest_off:], non_blocking=True)
             self._ev_copy.record(self._copy_stream)
         self._copy_pending = True
         if wait:

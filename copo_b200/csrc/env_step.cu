@@ -668,7 +668,7 @@ int b2c_env_create(const b2c_env_config* c, const uint32_t* map_blob, int map_wo
     }
     e->smem = (size_t)smem_plan(e->group, k.A, k.D, map_words, e->tile_words, e->threads / 32, e->split).total;
     e->n_ray = (int)map_blob[M_NRAY];
-    e->d_pose = nullptr;
+    e->d_pose = nullptr; e->rec_words = 0; e->pair_stride = 0;
     if (e->split) {
         B2C_CUDA_OR(cudaFuncSetAttribute(env_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem),
                     delete e);
@@ -710,10 +710,12 @@ int b2c_env_destroy(b2c_env* e) {
     return B2C_OK;
 }
 
-static void launch_lidar(b2c_env* e, float* obs, uint32_t* obs_split, int kp, cudaStream_t st) {
-    const EnvConfig& cfg = e->cfg;
+static void launch_lidar(b2c_env* e, float* obs, uint32_t* obs_split, int kp, cudaStream_t st, int first = 0,
+                         int count = -1) {
+    EnvConfig cfg = e->cfg;
+    if (count >= 0) cfg.S = count;
     LidarIO li;
-    li.map = e->d_map; li.pose = e->d_pose; li.obs = obs; li.obs_split = obs_split;
+    li.map = e->d_map; li.pose = e->d_pose ? e->d_pose + (size_t)first * e->rec_words : nullptr; li.obs = obs; li.obs_split = obs_split;
     li.pair_stride = e->pair_stride; li.rec_words = e->rec_words; li.n_ray = e->n_ray; li.ray_off = e->ray_off;
     li.kp = kp; li.group = e->lidar_group; li.S = cfg.S; li.A = cfg.A; li.D = cfg.D;
     // one CTA per group of scenes (the hardware scheduler balances the uneven pair counts); very large batches loop
@@ -724,14 +726,19 @@ static void launch_lidar(b2c_env* e, float* obs, uint32_t* obs_split, int kp, cu
 }
 
 static int launch_env(b2c_env* e, const float* actions, const b2c_env_io* o, int do_reset, int new_episode,
-                      void* stream) {
+                      void* stream, int first = 0, int count = -1) {
     if (!e || !o || !o->obs || !o->reward || !o->flags)
         return b2c_set_error(B2C_ERR_ARG, "b2c_env_step: obs, reward and flags outputs are required");
     if (!do_reset && !actions) return b2c_set_error(B2C_ERR_ARG, "b2c_env_step: actions is null");
+    if (count < 0) count = e->cfg.S;
+    if (first < 0 || count < 1 || first + count > e->cfg.S)
+        return b2c_set_error(B2C_ERR_ARG, "b2c_env_step_scenes: scene range out of bounds");
     EnvConfig cfg = e->cfg;
     cfg.do_reset = do_reset; cfg.new_episode = new_episode;
+    cfg.S = count; cfg.scene_offset += first;            // the kernels index scenes from the start of the range
     EnvIO io;
-    io.map = e->d_map; io.state = e->d_state; io.actions = actions; io.obs = o->obs; io.reward = o->reward;
+    io.map = e->d_map; io.state = e->d_state + (size_t)first * e->tile_words; io.actions = actions; io.obs = o->obs;
+    io.reward = o->reward;
     io.flags = o->flags; io.nei_mask = (unsigned long long*)o->nei_mask; io.mf_mask = (unsigned long long*)o->mf_mask;
     io.nei_reward = o->nei_reward; io.global_reward = o->global_reward; io.nei_list = o->nei_list;
     io.agent_id = o->agent_id; io.lcf = o->lcf; io.scene_done = o->scene_done;
@@ -739,7 +746,7 @@ static int launch_env(b2c_env* e, const float* actions, const b2c_env_io* o, int
     io.map_words = e->map_words; io.tile_words = e->tile_words;
     io.obs_bulk = ((((size_t)cfg.A * cfg.D * 4) % 16 == 0) && (((uintptr_t)o->obs) % 16 == 0)) ? 1 : 0;
     io.group = e->group;
-    io.pose = e->d_pose; io.rec_words = e->rec_words;
+    io.pose = e->d_pose ? e->d_pose + (size_t)first * e->rec_words : nullptr; io.rec_words = e->rec_words;
     int ctas_per_sm = (int)(227 * 1024 / (e->smem + 1024));
     int by_threads = 2048 / e->threads;
     if (ctas_per_sm > by_threads) ctas_per_sm = by_threads;
@@ -753,7 +760,7 @@ static int launch_env(b2c_env* e, const float* actions, const b2c_env_io* o, int
     } else {
         env_step_kernel<true><<<grid, e->threads, e->smem, st>>>(cfg, io);
         B2C_CUDA(cudaGetLastError());
-        launch_lidar(e, o->obs, io.obs_split, io.kp, st);
+        launch_lidar(e, o->obs, io.obs_split, io.kp, st, first, count);
     }
     B2C_CUDA(cudaGetLastError());
     return B2C_OK;
@@ -764,6 +771,10 @@ int b2c_env_reset(b2c_env* e, const b2c_env_io* out, int new_episode, void* stre
 }
 int b2c_env_step(b2c_env* e, const float* actions, const b2c_env_io* out, void* stream) {
     return launch_env(e, actions, out, 0, 0, stream);
+}
+int b2c_env_step_scenes(b2c_env* e, const float* actions, const b2c_env_io* out, int first_scene, int num_scenes,
+                        void* stream) {
+    return launch_env(e, actions, out, 0, 0, stream, first_scene, num_scenes);
 }
 int b2c_env_set_lcf_dist(b2c_env* e, float mean, float std) {
     if (!e) return b2c_set_error(B2C_ERR_ARG, "null env");

@@ -85,6 +85,12 @@ int b2c_env_create(const b2c_env_config* cfg, const uint32_t* map_blob_host, int
 int b2c_env_destroy(b2c_env* env);
 int b2c_env_reset(b2c_env* env, const b2c_env_io* out, int new_episode, void* stream);
 int b2c_env_step(b2c_env* env, const float* actions /* [S][A][2] */, const b2c_env_io* out, void* stream);
+/* Steps only scenes [first_scene, first_scene + num_scenes): `actions` and every buffer of `out` hold just those scenes
+ * (the caller passes the sub-range of its arrays).  Scenes are independent, so stepping the ranges of a partition one
+ * after the other equals b2c_env_step; a host-facing caller uses it to start copying a range's results while the next
+ * range is still being computed. */
+int b2c_env_step_scenes(b2c_env* env, const float* actions, const b2c_env_io* out, int first_scene, int num_scenes,
+                        void* stream);
 int b2c_env_set_lcf_dist(b2c_env* env, float mean, float std);
 int b2c_env_set_force_lcf(b2c_env* env, float value);
 int b2c_env_set_num_agents(b2c_env* env, int num_agents);   /* curriculum: ChangeNEnv, env_wrappers.py:450 */

@@ -132,34 +132,43 @@ def test_env_emits_the_policy_operand(split, monkeypatch):
         env.close()
 
 
-def test_step_host_matches_device_step():
-    """The host-buffer step (one arena copy on the copy stream, blocking or overlapped with later device work) returns
-    exactly what the device step leaves in HBM."""
+@pytest.mark.parametrize("S,chunks", [(50, 1), (300, 4), (200, 3)])
+def test_step_host_matches_device_step(S, chunks):
+    """The host-buffer step (scenes stepped in ranges, each range's observations copied on the copy stream while the
+    next range is computed; blocking or overlapped with later device work) returns exactly what the one-launch device
+    step leaves in HBM."""
     from copo_b200.batched_env import BatchedDrivingEnv
-    S, A = 50, 40
+    A = 40
     e_dev = BatchedDrivingEnv("intersection", num_scenes=S, num_slots=A, num_agents=A, seed=4)
     e_host = BatchedDrivingEnv("intersection", num_scenes=S, num_slots=A, num_agents=A, seed=4)
+    e_host.host_chunks = chunks
     e_dev.reset()
     e_host.reset()
     rng = np.random.default_rng(0)
     pinned = torch.zeros((S, A, 2)).pin_memory()
+    split = e_host.alloc_obs_split()
     for t in range(12):
         act = rng.uniform(-1, 1, (S, A, 2)).astype(np.float32)
         want = e_dev.step(torch.from_numpy(act).cuda())
         if t % 3 == 0:
             got = e_host.step_host(act)                              # numpy in, blocking
         elif t % 3 == 1:
-            got = e_host.step_host(torch.from_numpy(act))            # pageable tensor in, blocking
+            got = e_host.step_host(torch.from_numpy(act), obs_split=split)     # pageable tensor in, blocking
         else:
             pinned.copy_(torch.from_numpy(act))
             got = e_host.step_host(pinned, wait=False)               # pinned in place, overlapped
             busy = e_host.host_step_out["obs"].sum()                 # device work queued behind the step
             e_host.wait_host()
             assert torch.isfinite(busy)
+        assert len(e_host._chunks) == chunks
         for k in BatchedDrivingEnv.HOST_KEYS:
             assert not got[k].is_cuda
             assert torch.equal(got[k], want[k].cpu()), (t, k)
             assert torch.equal(e_host.host_step_out[k], want[k]), (t, k)
+        if t % 3 == 1:
+            from copo_b200 import ops
+            ws = ops.tc_split_rows(want["obs"].reshape(S * A, -1))
+            assert torch.equal(split.reshape(S * A, -1).view(torch.int16), ws.view(torch.int16))
     assert e_host.d2h_bytes_per_step == sum(want[k].numel() * want[k].element_size()
                                             for k in BatchedDrivingEnv.HOST_KEYS)
     e_dev.close()
