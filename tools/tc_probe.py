@@ -1,6 +1,6 @@
 """Where does a tc_linear launch spend its time?  Times the rollout shapes (M = 163 840 rows; K = 92 and K = 256) with
-the epilogue's pieces switched on one by one: no activation / no output, tanh only, tanh + split output, + fp32 output,
-and the fused head.  L2 is flushed before every launch."""
+the epilogue's pieces switched on one by one: split output without / with tanh, fp32 output, both, and the fused head
+(4 outputs per row: next to no stores) without / with tanh.  L2 is flushed before every launch."""
 import json, sys
 import torch
 sys.path.insert(0, ".")
@@ -33,8 +33,6 @@ for K in (92, 256):
     f32 = torch.empty((M, 256), device=dev)
     sp = torch.empty((M, 512), dtype=torch.bfloat16, device=dev)
     r = {}
-    r["mma_only(act0,no_out)"] = timed(lambda: ops.tc_linear(a, w, b, act=0, want_f32=False, want_split=False))
-    r["tanh,no_out"] = timed(lambda: ops.tc_linear(a, w, b, act=1, want_f32=False, want_split=False))
     r["act0,split"] = timed(lambda: ops.tc_linear(a, w, b, act=0, want_f32=False, out_split=sp, want_split=True))
     r["tanh,split"] = timed(lambda: ops.tc_linear(a, w, b, act=1, want_f32=False, out_split=sp, want_split=True))
     r["tanh,f32"] = timed(lambda: ops.tc_linear(a, w, b, act=1, out_f32=f32, want_f32=True))
