@@ -24,7 +24,7 @@ def timed(fn, reps=15):
 
 
 out = {}
-for K in (92, 256):
+for K in (64, 92, 256):
     x = torch.rand(M, K, device=dev)
     W = torch.randn(256, K, device=dev) / K ** 0.5
     b = torch.zeros(256, device=dev)
