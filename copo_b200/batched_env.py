@@ -5,6 +5,7 @@ This is the native tensor API of the environment; the RLlib-style dict API of th
 thin host view over it in copo_b200/envs.py.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -137,7 +138,8 @@ class BatchedDrivingEnv:
             self.host_step_out = dict(self.out)          # device side of the same step (arena views + mf_mask)
             self.host_step_out.update(views(self._arena_dev))
             self.host_step_out["obs_split"] = None
-            K = max(1, min(int(getattr(self, "host_chunks", 4)), self.S // 64 if self.S >= 128 else 1))
+            want = getattr(self, "host_chunks", None) or int(os.environ.get("B2C_HOST_CHUNKS", "4"))
+            K = max(1, min(int(want), self.S // 64 if self.S >= 128 else 1))
             per = (self.S + K - 1) // K
             self._chunks = [(f, min(per, self.S - f)) for f in range(0, self.S, per)]
             self._chunk_out = [{k: (v[f:f + n] if v is not None else None) for k, v in self.host_step_out.items()}

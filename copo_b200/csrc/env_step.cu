@@ -161,7 +161,7 @@ __device__ __forceinline__ void lidar_spread(const PairGeom& g, int lid_off, boo
 // observation tile) so several times more scenes are resident per SM; ego / navigation features go straight to HBM,
 // poses + queued lidar pairs go to a scratch buffer for env_lidar_kernel.
 template <bool SPLIT>
-__global__ void __launch_bounds__(SPLIT ? 128 : ENV_MAX_THREADS, SPLIT ? 7 : 2)
+__global__ void __launch_bounds__(SPLIT ? 128 : ENV_MAX_THREADS, SPLIT ? 10 : 2)      // state kernel: 48 registers, 10 CTAs per SM
 env_step_kernel(const __grid_constant__ EnvConfig cfg, const __grid_constant__ EnvIO io) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int A = cfg.A, AP = cfg.AP, D = cfg.D, G = io.group;
