@@ -152,6 +152,7 @@ struct LinearArgs {
     int ld_out, ld_src, act;  // act: 0 none, 1 tanh
     int wide_f32, wide_split; // 1: the output rows are 32-byte aligned (256-bit stores)
     int resident, stages;     // resident weights mode; ring depth
+    int probe;                // measurements only (B2C_TC_PROBE): 1 = the epilogue stops after its tcgen05.ld
     // fused narrow output layer on the activated result: head_out[m][j] = head_b[j] + sum_n y[m][n] head_w[j][n]
     const float* head_w;      // [head_n][256] or null
     const float* head_b;      // [head_n] or null
@@ -289,6 +290,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 const int c = half * (BLOCK_N / 64) + cc;        // 32-column chunk index
                 uint32_t r[32];
                 tmem_ld32(taddr0 + (uint32_t)(c * 32), r);
+                if (args.probe == 1) { hacc[0] += __uint_as_float(r[0]) + __uint_as_float(r[31]); continue; }
                 float v[32];
                 const float4* b4 = reinterpret_cast<const float4*>(s_bias + c * 32);
 #pragma unroll
@@ -721,6 +723,8 @@ static int tc_linear_launch(const uint16_t* a_split, const uint16_t* w_prep, con
     static const bool narrow = getenv("B2C_TC_NARROW_STORES") != nullptr;    // A/B switches for measurements
     static const bool streamed = getenv("B2C_TC_STREAM_WEIGHTS") != nullptr;
     if (narrow) a.wide_f32 = a.wide_split = 0;
+    static const int probe = getenv("B2C_TC_PROBE") ? atoi(getenv("B2C_TC_PROBE")) : 0;
+    a.probe = probe;
     a.resident = 0; a.stages = STAGES;
     int smem_bytes = SMEM_BYTES;
     if (!head && a.kp_blocks <= 2 && !streamed) {
