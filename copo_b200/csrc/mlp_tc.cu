@@ -36,7 +36,7 @@ constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;      // 32 KB per half
 constexpr int STAGE_BYTES = 2 * A_STAGE_BYTES + 2 * B_STAGE_BYTES;     // A_hi, A_lo, W_hi, W_lo: 96 KB
 constexpr int HEAD_MAX = 4;                               // fused narrow output layer: up to 4 outputs
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 1024 /*bias*/ +
-                           HEAD_MAX * BLOCK_N * 4 /*head weights*/ + 2 * BLOCK_M * HEAD_MAX * 4 /*head partials*/;
+                           HEAD_MAX * BLOCK_N * 4 /*head weights*/ + 3 * BLOCK_M * HEAD_MAX * 4 /*head partials*/;
 // "resident weights" mode (reduction length <= 128, no fused output layer - the first layer of every network): the
 // whole prepared weight matrix (hi | lo, 64 KB per reduction block) stays in shared memory for the life of the CTA and
 // only the A blocks (32 KB) stream through a deeper ring, so the weights cross L2 -> shared memory once per CTA instead
@@ -153,6 +153,7 @@ struct LinearArgs {
     int wide_f32, wide_split; // 1: the output rows are 32-byte aligned (256-bit stores)
     int resident, stages;     // resident weights mode; ring depth
     int probe;                // measurements only (B2C_TC_PROBE): 1 = the epilogue stops after its tcgen05.ld
+    int products;             // 4: hi*hi + lo*hi + hi*lo + lo*lo; 3: without lo*lo (B2C_TC_PRODUCTS, measurements)
     // fused narrow output layer on the activated result: head_out[m][j] = head_b[j] + sum_n y[m][n] head_w[j][n]
     const float* head_w;      // [head_n][256] or null
     const float* head_b;      // [head_n] or null
@@ -164,9 +165,14 @@ struct LinearArgs {
     uint32_t seed, step;
 };
 
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+// EPI = epilogue warps (8, 12 or 16: two, three or four per scheduler).  The 8 column chunks of a tile are dealt to
+// EPI / 4 column groups; a warp reads the TMEM lanes of its quarter (warp % 4) and the chunks of its group.
+template <int EPI>
+__global__ void __launch_bounds__(128 + EPI * 32, 1)
 tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                  const __grid_constant__ LinearArgs args) {
+    constexpr int NT = 128 + EPI * 32;
+    constexpr int GROUPS = EPI / 4;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const bool resident = args.resident != 0;
@@ -196,7 +202,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < n_stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], EPI_WARPS); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], EPI); }
         mbar_init(w_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -205,9 +211,9 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                      "n"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < BLOCK_N; i += NUM_THREADS) s_bias[i] = args.bias ? args.bias[i] : 0.0f;
+    for (int i = threadIdx.x; i < BLOCK_N; i += NT) s_bias[i] = args.bias ? args.bias[i] : 0.0f;
     if (args.head_w)
-        for (int i = threadIdx.x; i < args.head_n * BLOCK_N; i += NUM_THREADS) s_head_w[i] = args.head_w[i];
+        for (int i = threadIdx.x; i < args.head_n * BLOCK_N; i += NT) s_head_w[i] = args.head_w[i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -264,7 +270,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         umma_bf16(tmem_d, a_hi + o, w_hi + o, IDESC, (kb | k) ? 1u : 0u);
                         umma_bf16(tmem_d, a_lo + o, w_hi + o, IDESC, 1u);
                         umma_bf16(tmem_d, a_hi + o, w_lo + o, IDESC, 1u);
-                        umma_bf16(tmem_d, a_lo + o, w_lo + o, IDESC, 1u);
+                        if (args.products == 4) umma_bf16(tmem_d, a_lo + o, w_lo + o, IDESC, 1u);
                     }
                     umma_commit(&empty[stage]);                  // frees the smem slot when these MMAs retire
                     if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);
@@ -276,7 +282,8 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     } else if (warp >= 4) {
         // ===== epilogue: warp w reads TMEM lanes 32*(w%4) .. +31 (one output row per thread), columns by half =====
         const int q = warp & 3;
-        const int half = (warp - 4) >> 2;                        // 0: columns 0..127, 1: columns 128..255
+        const int grp = (warp - 4) >> 2;                         // column group
+        const int c_begin = (8 * grp + GROUPS - 1) / GROUPS, c_end = (8 * (grp + 1) + GROUPS - 1) / GROUPS;
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             mbar_wait(&tmem_full[acc], acc_phase);
@@ -286,8 +293,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
             float hacc[HEAD_MAX] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll 1
-            for (int cc = 0; cc < BLOCK_N / 64; ++cc) {
-                const int c = half * (BLOCK_N / 64) + cc;        // 32-column chunk index
+            for (int c = c_begin; c < c_end; ++c) {              // 32-column chunks of this warp's group
                 uint32_t r[32];
                 tmem_ld32(taddr0 + (uint32_t)(c * 32), r);
                 if (args.probe == 1) { hacc[0] += __uint_as_float(r[0]) + __uint_as_float(r[31]); continue; }
@@ -377,19 +383,23 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
             if (args.head_w) {
-                // the two column halves of a row live in warps w and w + 4: the upper half hands its partial sums
-                // over through shared memory (named barrier 1 = the 8 epilogue warps)
+                // the column groups of a row live in warps w, w + 4, ...: groups 1.. hand their partial sums to group 0
+                // through shared memory (named barrier 1 = the epilogue warps); summed in group order
                 const int rloc = q * 32 + lane;
-                if (half == 1) {
+                if (grp > 0) {
 #pragma unroll
-                    for (int hj = 0; hj < HEAD_MAX; ++hj) s_part[rloc * HEAD_MAX + hj] = hacc[hj];
+                    for (int hj = 0; hj < HEAD_MAX; ++hj) s_part[((grp - 1) * BLOCK_M + rloc) * HEAD_MAX + hj] = hacc[hj];
                 }
-                asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
-                if (half == 0 && live) {
+                asm volatile("bar.sync 1, %0;" ::"n"(EPI * 32) : "memory");
+                if (grp == 0 && live) {
                     float o[HEAD_MAX];
 #pragma unroll
-                    for (int hj = 0; hj < HEAD_MAX; ++hj)
-                        o[hj] = (hj < args.head_n) ? hacc[hj] + s_part[rloc * HEAD_MAX + hj] + args.head_b[hj] : 0.0f;
+                    for (int hj = 0; hj < HEAD_MAX; ++hj) {
+                        float t = hacc[hj];
+#pragma unroll
+                        for (int g = 1; g < GROUPS; ++g) t += s_part[((g - 1) * BLOCK_M + rloc) * HEAD_MAX + hj];
+                        o[hj] = (hj < args.head_n) ? t + args.head_b[hj] : 0.0f;
+                    }
                     if (args.head_n == 4) {
                         reinterpret_cast<float4*>(args.head_out)[row] = make_float4(o[0], o[1], o[2], o[3]);
                         if (args.actions) {
@@ -405,7 +415,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         for (int hj = 0; hj < args.head_n; ++hj) args.head_out[(size_t)row * args.head_n + hj] = o[hj];
                     }
                 }
-                asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(EPI * 32) : "memory");
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
@@ -704,7 +714,9 @@ static int tc_linear_launch(const uint16_t* a_split, const uint16_t* w_prep, con
     static int attr_set = 0;
     static int num_sms = 0;
     if (!attr_set) {
-        B2C_CUDA(cudaFuncSetAttribute(tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX_OPTIN));
+        B2C_CUDA(cudaFuncSetAttribute(tc_linear_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX_OPTIN));
+        B2C_CUDA(cudaFuncSetAttribute(tc_linear_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX_OPTIN));
+        B2C_CUDA(cudaFuncSetAttribute(tc_linear_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX_OPTIN));
         int dev = 0;
         B2C_CUDA(cudaGetDevice(&dev));
         B2C_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -724,7 +736,10 @@ static int tc_linear_launch(const uint16_t* a_split, const uint16_t* w_prep, con
     static const bool streamed = getenv("B2C_TC_STREAM_WEIGHTS") != nullptr;
     if (narrow) a.wide_f32 = a.wide_split = 0;
     static const int probe = getenv("B2C_TC_PROBE") ? atoi(getenv("B2C_TC_PROBE")) : 0;
+    static const int products = getenv("B2C_TC_PRODUCTS") ? atoi(getenv("B2C_TC_PRODUCTS")) : 4;
+    static const int epi = getenv("B2C_TC_EPI_WARPS") ? atoi(getenv("B2C_TC_EPI_WARPS")) : 8;
     a.probe = probe;
+    a.products = products == 3 ? 3 : 4;
     a.resident = 0; a.stages = STAGES;
     int smem_bytes = SMEM_BYTES;
     if (!head && a.kp_blocks <= 2 && !streamed) {
@@ -741,7 +756,9 @@ static int tc_linear_launch(const uint16_t* a_split, const uint16_t* w_prep, con
     }
     int tiles = (M + BLOCK_M - 1) / BLOCK_M;
     int grid = tiles < num_sms ? tiles : num_sms;
-    tc_linear_kernel<<<grid, NUM_THREADS, smem_bytes, (cudaStream_t)stream>>>(map_a, map_w, a);
+    if (epi == 16) tc_linear_kernel<16><<<grid, 128 + 16 * 32, smem_bytes, (cudaStream_t)stream>>>(map_a, map_w, a);
+    else if (epi == 12) tc_linear_kernel<12><<<grid, 128 + 12 * 32, smem_bytes, (cudaStream_t)stream>>>(map_a, map_w, a);
+    else tc_linear_kernel<8><<<grid, 128 + 8 * 32, smem_bytes, (cudaStream_t)stream>>>(map_a, map_w, a);
     B2C_CUDA(cudaGetLastError());
     return B2C_OK;
 }
