@@ -240,6 +240,16 @@ def run_gpu(args):
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = float(sum(step_ms))
     agent_steps = n1 - n0
+    # the same steps back to back without the flush (secondary figure: a step touches ~450 MB, more than the 126 MB L2,
+    # so the flush mostly adds the write-back of its own dirty lines to the step)
+    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    b0.record(stream)
+    for t in range(args.steps):
+        rollout_step()
+    b1.record(stream)
+    barrier()
+    noflush_ms = b0.elapsed_time(b1) / args.steps
 
     # ---- per-kernel timing of the two heavy kernels (same inputs, L2 flushed before each) ---------------------
     def time_kernel(fn, reps=20):
@@ -357,7 +367,7 @@ def run_gpu(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": total_ms / args.steps, "ms_per_step_back_to_back_no_flush": noflush_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "CoPO Intersection 40 agents x %d scenes per GPU, one rollout step: policy MLP forward "
                                "(92-256-256-4, tcgen05 split-bf16, logits + Gaussian sample in the layer-2 epilogue) + "

@@ -737,7 +737,11 @@ static int tc_linear_launch(const uint16_t* a_split, const uint16_t* w_prep, con
     if (narrow) a.wide_f32 = a.wide_split = 0;
     static const int probe = getenv("B2C_TC_PROBE") ? atoi(getenv("B2C_TC_PROBE")) : 0;
     static const int products = getenv("B2C_TC_PRODUCTS") ? atoi(getenv("B2C_TC_PRODUCTS")) : 4;
-    static const int epi = getenv("B2C_TC_EPI_WARPS") ? atoi(getenv("B2C_TC_EPI_WARPS")) : 8;
+    // epilogue warps: with the fused output layer (next to no stores) four warps per scheduler hide the tcgen05.ld and
+    // FMA latencies best; with a full-width output two per scheduler are faster - more warps only spread the row-strided
+    // stores over more concurrent streams (profiles/r01_g_tc_probe_epi*.json)
+    static const int epi_env = getenv("B2C_TC_EPI_WARPS") ? atoi(getenv("B2C_TC_EPI_WARPS")) : 0;
+    const int epi = epi_env ? epi_env : (head ? 16 : 8);
     a.probe = probe;
     a.products = products == 3 ? 3 : 4;
     a.resident = 0; a.stages = STAGES;
