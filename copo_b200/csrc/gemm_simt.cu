@@ -147,9 +147,17 @@ __global__ void colsum_kernel(const float* __restrict__ dy, int ldy, float* __re
     int n = blockIdx.x * blockDim.x + threadIdx.x;
     int m_begin = blockIdx.y * rows, m_end = min(M, m_begin + rows);
     if (n >= N) return;
-    float s = 0.0f;
-    for (int m = m_begin; m < m_end; ++m) s += dy[(size_t)m * ldy + n];
-    atomicAdd(&db[n], s);
+    // four independent partial sums: four loads in flight per thread
+    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+    int m = m_begin;
+    for (; m + 3 < m_end; m += 4) {
+        s0 += dy[(size_t)m * ldy + n];
+        s1 += dy[(size_t)(m + 1) * ldy + n];
+        s2 += dy[(size_t)(m + 2) * ldy + n];
+        s3 += dy[(size_t)(m + 3) * ldy + n];
+    }
+    for (; m < m_end; ++m) s0 += dy[(size_t)m * ldy + n];
+    atomicAdd(&db[n], (s0 + s1) + (s2 + s3));
 }
 
 }  // namespace b2c
@@ -198,7 +206,7 @@ int b2c_linear_backward_weight(const float* dy, int ldy, const float* x, int ldx
     sgemm_kernel<true, false, EPI_ATOMIC><<<grid, NTHREADS, 0, s>>>(dy, ldy, x, ldx, dW, K, N, K, M, nullptr, nullptr, 0, chunk);
     B2C_CUDA(cudaGetLastError());
     if (db) {
-        int rows = 128;                                  // many short CTAs: the sum is bandwidth-bound
+        int rows = 64;                                   // many short CTAs: the sum is bandwidth-bound
         dim3 g2((N + 127) / 128, (M + rows - 1) / rows);
         colsum_kernel<<<g2, 128, 0, s>>>(dy, ldy, db, M, N, rows);
         B2C_CUDA(cudaGetLastError());
@@ -209,7 +217,7 @@ int b2c_linear_backward_weight(const float* dy, int ldy, const float* x, int ldx
 int b2c_colsum(const float* dy, int ldy, float* db, int M, int N, void* stream) {
     if (M == 0) return B2C_OK;
     if (!dy || !db || M < 0 || N < 1) return b2c_set_error(B2C_ERR_ARG, "b2c_colsum: bad argument");
-    int rows = 128;
+    int rows = 64;
     dim3 g2((N + 127) / 128, (M + rows - 1) / rows);
     colsum_kernel<<<g2, 128, 0, (cudaStream_t)stream>>>(dy, ldy, db, M, N, rows);
     B2C_CUDA(cudaGetLastError());

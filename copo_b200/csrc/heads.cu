@@ -261,7 +261,11 @@ int b2c_head_backward_split(const float* dy, int ldy, const float* h, int ldh, c
     if (M == 0) return B2C_OK;
     if (!dy || !h || !W || N < 1 || N > HEAD_MAX_N) return b2c_set_error(B2C_ERR_ARG, "b2c_head_backward: bad argument");
     if (dz_split && (K % 64)) return b2c_set_error(B2C_ERR_ARG, "b2c_head_backward: dz_split needs K to be a multiple of 64");
-    int rows = 256;
+    // row chunk per CTA: enough CTAs to fill the machine several times over (the kernel streams h in and dz out; with
+    // 256-row chunks a 65 536-row minibatch gave 1.7 CTAs per SM and the loads' latency was exposed)
+    int rows = (M + 148 * 8 - 1) / (148 * 8);
+    rows = (rows + 3) & ~3;
+    rows = rows < 32 ? 32 : (rows > 256 ? 256 : rows);
     dim3 grid((M + rows - 1) / rows, (K + 255) / 256);
     cudaStream_t s = (cudaStream_t)stream;
 #define B2C_HB(n) case n: head_backward_kernel<n><<<grid, 256, 0, s>>>(dy, ldy, h, ldh, W, dz, ldz, dz_split, dW, db, M, K, rows, dtanh); break;
