@@ -18,7 +18,13 @@ sys.path.insert(0, REF)
 from copo.eval import get_policy_function as ref  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-MODELS = {"copo_inter": 92, "ccppo_round": 91}       # TF-era naming with _1 suffix / torch-era naming
+# every naming scheme and every observation width the reference ships (best_checkpoints/*.npz):
+#   copo_*  TF-era naming with the _1 suffix (92 / 97 / 157 inputs: LCF appended)
+#   ippo_*, cl_*  TF-era naming without suffix (91 / 96 / 156)
+#   ccppo_*  torch-era naming
+MODELS = {"copo_inter": 92, "ccppo_round": 91, "ippo_tollgate": 156, "cl_bottle": 96, "copo_tollgate": 157,
+          "ccppo_parking": 91}
+ROWS = {"copo_inter": 48, "ccppo_round": 48}          # the others: 16 rows
 
 
 def main():
@@ -28,7 +34,7 @@ def main():
         path = os.path.join(REF, "copo", "best_checkpoints", name + ".npz")
         w = np.load(path)
         w = {k: w[k] for k in w.files}
-        obs = rng.uniform(0, 1, (48, odim)).astype(np.float32)
+        obs = rng.uniform(0, 1, (ROWS.get(name, 16), odim)).astype(np.float32)
         obs[0] = 0.0
         if name.startswith("ccppo"):
             mean = ref._compute_actions_for_torch_policy(w, obs, deterministic=True)
@@ -37,9 +43,10 @@ def main():
                 out["%s/%s.weight" % (name, n)] = w[n + ".weight"]
                 out["%s/%s.bias" % (name, n)] = w[n + ".bias"]
         else:
+            sfx = "_1" if name.startswith("copo") else ""
             mean = ref._compute_actions_for_tf_policy(w, obs, deterministic=True, policy_name="default",
-                                                      layer_name_suffix="_1")
-            for layer in ("fc_1_1", "fc_2_1", "fc_out_1"):
+                                                      layer_name_suffix=sfx)
+            for layer in ("fc_1" + sfx, "fc_2" + sfx, "fc_out" + sfx):
                 out["%s/default/%s/kernel" % (name, layer)] = w["default/%s/kernel" % layer]
                 out["%s/default/%s/bias" % (name, layer)] = w["default/%s/bias" % layer]
         out[name + "/obs"] = obs

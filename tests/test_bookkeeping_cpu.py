@@ -107,7 +107,10 @@ def test_lcf_mix_standardize():
     assert std0 == 1e-4
 
 
-@pytest.mark.parametrize("name", ["copo_inter", "ccppo_round"])
+GOLDEN_MODELS = ["copo_inter", "ccppo_round", "ippo_tollgate", "cl_bottle", "copo_tollgate", "ccppo_parking"]
+
+
+@pytest.mark.parametrize("name", GOLDEN_MODELS)
 def test_policy_forward_matches_reference_golden(name):
     z = np.load(GOLD)
     sub = {k[len(name) + 1:]: z[k] for k in z.files if k.startswith(name + "/")}
@@ -226,3 +229,43 @@ def test_adam_and_kl_controller():
         assert torch.allclose(p.detach(), q, atol=1e-7)
     assert om.update_kl(0.2, 0.03) == pytest.approx(0.3) and om.update_kl(0.2, 0.004) == pytest.approx(0.1)
     assert om.update_kl(0.2, 0.01) == 0.2
+
+
+REF_CKPT = "/root/reference/copo_code/copo/best_checkpoints"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_CKPT), reason="the reference tree is only mounted in the build container")
+def test_every_shipped_checkpoint_loads_and_matches_the_reference_forward():
+    """All 20 `best_checkpoints/*.npz` (three naming schemes, five observation widths): the wire-format reader of the
+    product (`copo_b200.checkpoint`, host-side) + the oracle forward reproduce the reference's own numpy forward
+    (`eval/get_policy_function.py:54-98`, imported from the reference tree)."""
+    import sys
+    sys.path.insert(0, "/root/reference/copo_code")
+    try:
+        from copo.eval import get_policy_function as ref
+    finally:
+        sys.path.pop(0)
+    from copo_b200 import checkpoint as ck
+    files = sorted(f for f in os.listdir(REF_CKPT) if f.endswith(".npz"))
+    assert len(files) == 20
+    rng = np.random.default_rng(7)
+    widths = set()
+    for f in files:
+        w = dict(np.load(os.path.join(REF_CKPT, f)))
+        sd = ck.state_dict_from_policy_npz(w)
+        odim = sd[ck.TORCH_POLICY[0] + ".weight"].shape[1]
+        widths.add(odim)
+        obs = rng.uniform(0, 1, (8, odim)).astype(np.float32)
+        if f.startswith("ccppo"):
+            want = ref._compute_actions_for_torch_policy(w, obs, deterministic=True)
+        else:
+            want = ref._compute_actions_for_tf_policy(w, obs, deterministic=True, policy_name="default",
+                                                      layer_name_suffix="_1" if f.startswith("copo") else "")
+        layers = [(sd[n + ".weight"].T, sd[n + ".bias"]) for n in ck.TORCH_POLICY]
+        got = om.mlp_forward_np(layers, obs)[:, :2]
+        assert np.allclose(got, want, rtol=1e-5, atol=1e-6), f
+        # and back out in both namings
+        for naming, sfx in (("torch", ""), ("tf", "_1")):
+            again = ck.state_dict_from_policy_npz(ck.policy_npz_from_state_dict(sd, naming, suffix=sfx))
+            assert all(np.array_equal(again[k], sd[k]) for k in sd), (f, naming)
+    assert widths == {91, 92, 96, 97, 156, 157}

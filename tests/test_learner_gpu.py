@@ -25,7 +25,8 @@ def close(a, b, rtol, atol):
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16_split"])
-@pytest.mark.parametrize("name", ["copo_inter", "ccppo_round"])
+@pytest.mark.parametrize("name", ["copo_inter", "ccppo_round", "ippo_tollgate", "cl_bottle", "copo_tollgate",
+                                  "ccppo_parking"])
 def test_policy_forward_golden(name, precision):
     from copo_b200.models import CCModel
     z = np.load(GOLD)
