@@ -1,9 +1,12 @@
-// env_step.cu - fused scene step kernel (K1 step_state + K2 raycast_obs + K3 neighbour of SURVEY.md 2.2).
+// env_step.cu - the scene step (K1 step_state + K2 raycast_obs + K3 neighbour of SURVEY.md 2.2) and its C ABI.
 //
-// One CTA works on one scene at a time (persistent loop over scenes).  The map blob and the scene's
-// agent-state tile ([16 fields][AP slots] + 8-word header) are staged into shared memory with 1-D TMA
-// bulk copies (cp.async.bulk + mbarrier, SASS UBLKCP); every phase of sim_core.cuh then runs on shared
-// memory, the assembled observation tile [A][D] and the updated state tile leave through bulk stores.
+// Two launch modes (b2c_env_create picks one; B2C_ENV_SPLIT overrides):
+//   * two kernels (scenes of 16 slots and more): env_step_kernel<true> runs the per-slot phases of sim_core.cuh for a
+//     group of scenes per CTA (thread = slot), then env_lidar_kernel casts the lasers, one scene per CTA;
+//   * one fused kernel (small scenes): env_step_kernel<false>, observation tile and lidar included.
+// The map blob and the group's agent-state tiles ([16 fields][AP slots] + 8-word header per scene) are staged into
+// shared memory with 1-D TMA bulk copies (cp.async.bulk + mbarrier, SASS UBLKCP); every phase then runs on shared
+// memory; the updated state tiles and the observation rows leave through bulk stores.
 // Algorithmic HBM bytes per agent-step: 8 (action) + 64 (state in) + 64 (state out) + 4*D (obs) + 4 + 4 + 1
 // + 8 = 4*D + 153.
 //
@@ -158,8 +161,8 @@ __device__ __forceinline__ void lidar_spread(const PairGeom& g, int lid_off, boo
 
 // SPLIT = false: the whole step in one kernel (observation tile in shared memory, lidar included).
 // SPLIT = true: the state half of the two-kernel mode - per-slot phases only, small shared-memory footprint (no
-// observation tile) so several times more scenes are resident per SM; ego / navigation features go straight to HBM,
-// poses + queued lidar pairs go to a scratch buffer for env_lidar_kernel.
+// observation tile) so several times more scenes are resident per SM; ego / navigation features, poses and the
+// slots' lidar broad-phase masks go to a scratch record for env_lidar_kernel.
 template <bool SPLIT>
 __global__ void __launch_bounds__(SPLIT ? 128 : ENV_MAX_THREADS, SPLIT ? 10 : 2)      // state kernel: 48 registers, 10 CTAs per SM
 env_step_kernel(const __grid_constant__ EnvConfig cfg, const __grid_constant__ EnvIO io) {
