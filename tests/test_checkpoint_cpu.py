@@ -71,3 +71,59 @@ def test_reference_loader_reads_our_files(tmp_path):
     act = fn({"agent%d" % i: obs[i] for i in range(7)}, {})
     got = np.stack([act["agent%d" % i] for i in range(7)])
     assert np.allclose(got, want, atol=1e-5)
+
+
+def test_tf_copo_state_round_trip():
+    torch.manual_seed(3)
+    m = om.CoPOModel(92)
+    sd = {k: v.detach().numpy() for k, v in m.state_dict().items()}
+    tf = ck.tf_copo_state_from_state_dict(sd)
+    assert len(tf) == 24 and tf["default/fc_value_nei_1_1/kernel"].shape == (92, 256)
+    back = ck.state_dict_from_tf_copo_state(dict(tf, _optimizer_variables=None))
+    assert set(back) == set(sd) - {"lcf_parameters"}
+    assert all(np.array_equal(back[k], sd[k]) for k in back)
+    with pytest.raises(KeyError):
+        ck.state_dict_from_tf_copo_state({k: v for k, v in tf.items() if "value_out_nei" not in k})
+    with pytest.raises(KeyError):
+        ck.state_dict_from_tf_copo_state(dict(tf, **{"default/extra/kernel": np.zeros(1)}))
+
+
+DEMO = os.path.join(REF, "copo", "eval", "demo_raw_checkpoints", "copo")
+
+
+@pytest.mark.skipif(not os.path.isdir(DEMO), reason="reference tree not present")
+@pytest.mark.parametrize("step", [490, 625])
+def test_shipped_full_copo_checkpoint_loads_into_the_four_networks(step):
+    """SURVEY.md 8c (ii): the shipped trial checkpoints hold the full TF-era CoPO state (24 arrays, 360 199 parameters);
+    they load - without ray - into the four networks of CoPOModel, and the policy part reproduces the reference's own
+    numpy forward on the very same arrays."""
+    import glob
+    path = glob.glob(os.path.join(DEMO, "*", "checkpoint_%d" % step, "checkpoint-%d" % step))[0]
+    state = ck.load_rllib_checkpoint(path, stub_ray=True)
+    assert len(state) == 24 and sum(v.size for v in state.values()) == 360199
+    sd = ck.state_dict_from_tf_copo_state(state)
+    m = om.CoPOModel(92)
+    missing = m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=False)
+    assert list(missing.missing_keys) == ["lcf_parameters"] and not missing.unexpected_keys
+    sys.path.insert(0, REF)
+    try:
+        from copo.eval import get_policy_function as gpf
+    finally:
+        sys.path.remove(REF)
+    obs = np.random.default_rng(step).random((9, 92)).astype(np.float32)
+    obs[0] = 0.0
+    want = gpf._compute_actions_for_tf_policy({k: v for k, v in state.items() if "value" not in k}, obs,
+                                              deterministic=True, policy_name="default", layer_name_suffix="_1")
+    with torch.no_grad():
+        got = m(torch.from_numpy(obs)).numpy()[:, :2]
+        values = [f(torch.from_numpy(obs)).numpy() for f in (m.central_value_function, m.get_nei_value, m.get_global_value)]
+    assert np.allclose(got, want, rtol=1e-4, atol=1e-5)
+    # the three value heads: restated forward on the shipped arrays ([in, out] kernels, tanh hidden layers)
+    for v, (h1, h2, out) in zip(values, (("fc_value_1", "fc_value_2", "value_out"),
+                                         ("fc_value_nei_1", "fc_value_nei_2", "value_out_nei"),
+                                         ("fc_value_global_1", "fc_value_global_2", "value_out_global"))):
+        x = obs.astype(np.float64)
+        for layer, act in ((h1, True), (h2, True), (out, False)):
+            x = x @ state["default/%s_1/kernel" % layer].astype(np.float64) + state["default/%s_1/bias" % layer]
+            x = np.tanh(x) if act else x
+        assert v.shape == (9,) and np.allclose(v, x[:, 0], rtol=1e-4, atol=1e-5)
