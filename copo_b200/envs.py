@@ -16,6 +16,8 @@ import torch
 from .batched_env import (BatchedDrivingEnv, DEFAULT_NUM_AGENTS, FLAG_ARRIVE, FLAG_CRASH, FLAG_DONE, FLAG_MAXSTEP,
                           FLAG_OUT, FLAG_SPAWNED, FLAG_VALID)
 
+COMM_CURRENT_OBS, COMM_METHOD, NEI_OBS = "comm_current_obs", "comm_method", "nei_obs"     # env_wrappers.py:17,24,26
+
 F_X, F_Y, F_H, F_V, F_STEER, F_THR, F_S, F_DONE_LEN, F_ROUTE, F_SEG, F_EPLEN, F_EPREW, F_LCF, F_STATUS, F_ID, F_YAW = range(16)
 VMAX = 22.22222137451172
 
@@ -54,15 +56,27 @@ class DictSpace:
 
 
 class _Vehicle:
-    def __init__(self, x, y, speed):
+    def __init__(self, x, y, speed, heading_theta=0.0):
         self.position = np.array([x, y], dtype=np.float64)
         self.speed = speed
+        self.heading_theta = float(heading_theta)
+
+    @property
+    def heading(self):
+        return np.array([np.cos(self.heading_theta), np.sin(self.heading_theta)])
+
+    def projection(self, vector):
+        """(forward, leftward) components of `vector` in the vehicle frame (MetaDrive's BaseVehicle.projection as
+        recalled - MetaDrive is not available to check; only the disabled-by-default `add_pos_in_comm` branch uses it)."""
+        h = self.heading
+        return np.array([h[0] * vector[0] + h[1] * vector[1], -h[1] * vector[0] + h[0] * vector[1]])
 
 
 class MultiAgentDrivingEnv:
     """One scene with the reference's multi-agent dict API (native MetaDrive-level view, no CoPO wrappers)."""
     MAP = "intersection"
     APPEND_LCF = False
+    SIM_FACTORY = None          # tests substitute a host simulator with BatchedDrivingEnv's interface here
 
     @classmethod
     def default_config(cls):
@@ -71,12 +85,17 @@ class MultiAgentDrivingEnv:
 
     def __init__(self, config=None):
         self.config = self.default_config()
-        self.config.update(config or {})
+        for k, v in (config or {}).items():                  # nested option groups ("communication") merge key-wise
+            if isinstance(v, dict) and isinstance(self.config.get(k), dict):
+                self.config[k] = dict(self.config[k], **v)
+            else:
+                self.config[k] = v
         self._build()
 
     def _build(self):
         c = self.config
-        self._sim = BatchedDrivingEnv(self.MAP, num_scenes=1, num_slots=int(c["num_agents"]),
+        make = type(self).SIM_FACTORY or BatchedDrivingEnv
+        self._sim = make(self.MAP, num_scenes=1, num_slots=int(c["num_agents"]),
                                       num_agents=int(c["num_agents"]), delay_done=int(c["delay_done"]),
                                       horizon=int(c["horizon"]), neighbours_distance=float(c["neighbours_distance"]),
                                       allow_respawn=bool(c["allow_respawn"]), auto_reset=False,
@@ -116,7 +135,8 @@ class MultiAgentDrivingEnv:
         o, r, d, info = {}, {}, {}, {}
         name = lambda i: "agent%d" % int(ids[i])
         part = [i for i in range(self.A) if flags[i] & (FLAG_VALID | FLAG_SPAWNED)]
-        self.vehicles_including_just_terminated = {name(i): _Vehicle(ff[F_X, i], ff[F_Y, i], ff[F_V, i]) for i in part}
+        self.vehicles_including_just_terminated = {name(i): _Vehicle(ff[F_X, i], ff[F_Y, i], ff[F_V, i], ff[F_H, i])
+                                                   for i in part}
         self.vehicles = {name(i): self.vehicles_including_just_terminated[name(i)] for i in part
                          if not (flags[i] & FLAG_DONE)}
         self._slot_of = {name(i): i for i in part if not (flags[i] & FLAG_DONE)}
@@ -196,7 +216,47 @@ def get_ccenv(env_class):
         def default_config(cls):
             c = super().default_config()
             c["neighbours_distance"] = 40
+            c.update(communication=dict(comm_method="none", comm_size=4, comm_neighbours=4, add_pos_in_comm=False),
+                     add_traffic_light=False, traffic_light_interval=30)          # env_wrappers.py:42-48
             return c
+
+        def __init__(self, config=None):
+            super().__init__(config)
+            comm = self.config["communication"]
+            self._comm_on = comm[COMM_METHOD] != "none"
+            self._comm_dim = comm["comm_size"] + (3 if comm["add_pos_in_comm"] else 0)      # :58-61
+
+        @property
+        def action_space(self):
+            old = super().action_space
+            if not self._comm_on:
+                return old
+            n = 2 + self.config["communication"]["comm_size"]                      # :70-87 (not _comm_dim)
+            return DictSpace({k: Box(-1.0, 1.0, (n,)) for k in old.keys()})
+
+        def step(self, actions):
+            """The message channel of CCEnv.step (env_wrappers.py:89-121; off unless `comm_method` is set): the
+            action carries `comm_size` extra entries that are handed to the nearest neighbours as observations."""
+            if not self._comm_on:
+                return super().step(actions)
+            comm = self.config["communication"]
+            comm_actions = {k: np.asarray(v)[2:] for k, v in actions.items()}
+            o, r, d, i = super().step({k: np.asarray(v)[:2] for k, v in actions.items()})
+            veh = self.vehicles_including_just_terminated
+            for k, inf in i.items():
+                cur = []
+                for n in inf["neighbours"][:comm["comm_neighbours"]]:
+                    if n not in comm_actions:
+                        cur.append(np.zeros((self._comm_dim,)))
+                    elif comm["add_pos_in_comm"]:
+                        rel = veh[k].projection(veh[n].position - veh[k].position)
+                        dis = np.linalg.norm(rel)
+                        extra = [dis / 20, ((rel[0] / dis) + 1) / 2, ((rel[1] / dis) + 1) / 2]
+                        cur.append(np.concatenate([comm_actions[n], np.clip(np.asarray(extra), 0, 1)]))
+                    else:
+                        cur.append(comm_actions[n])
+                inf[COMM_CURRENT_OBS] = cur
+            return o, r, d, i
 
     TMP.__name__ = TMP.__qualname__ = "CC" + name
     return TMP
@@ -224,10 +284,57 @@ def get_lcf_env(env_class):
             assert self.config["lcf_normal_std"] > 0.0
             self.force_lcf = self.config["force_lcf"]
             self.current_lcf_mean, self.current_lcf_std = 0.0, self.config["lcf_normal_std"]
+            self._last_obs = None
+            self._traffic_light_counter = 0
 
         @property
         def enable_copo(self):
             return self.config["enable_copo"]
+
+        # ---- disabled-by-default branches of LCFEnv: traffic-light message, message channel ---------------------
+        @property
+        def _extra_obs(self):
+            comm = self.config["communication"]
+            return (3 if self.config["add_traffic_light"] else 0) + \
+                (self._comm_dim * comm["comm_neighbours"] if self._comm_on else 0)
+
+        @property
+        def observation_space(self):
+            sp = super().observation_space
+            if not self._extra_obs:
+                return sp
+            return DictSpace({k: Box(-1.0, 1.0, (self.D + self._extra_obs,)) for k in sp.keys()})   # :227-246
+
+        @property
+        def _traffic_light_msg(self):
+            fix_interval = self.config["traffic_light_interval"]                   # env_wrappers.py:259-266
+            increment = (self._traffic_light_counter % fix_interval) / fix_interval * 0.1
+            if ((self._traffic_light_counter // fix_interval) % 2) == 1:
+                return 0 + increment
+            return 1 - increment
+
+        def get_agent_traffic_light_msg(self, pos):
+            b_box = self._sim.tables.bounding_box()                                # :268-272
+            pos0 = (pos[0] - b_box[0]) / (b_box[1] - b_box[0])
+            pos1 = (pos[1] - b_box[2]) / (b_box[3] - b_box[2])
+            return np.clip(np.array([self._traffic_light_msg, pos0, pos1]), 0, 1).astype(np.float32)
+
+        def _with_traffic_light(self, o):
+            """[obs | message, x, y | lcf]: the reference appends the message before `_add_lcf` (:277-296, :327-334)."""
+            veh = self.vehicles_including_just_terminated
+            return {k: np.concatenate([v[:-1], self.get_agent_traffic_light_msg(veh[k].position), v[-1:]])
+                    for k, v in o.items()}
+
+        def reset(self, force_seed=None):
+            o = super().reset(force_seed)
+            if self.config["add_traffic_light"]:
+                self._traffic_light_counter = 0
+                o = self._with_traffic_light(o)
+            if self._comm_on:                                                      # :296-302
+                pad = np.zeros((self._comm_dim * self.config["communication"]["comm_neighbours"],))
+                o = {k: np.concatenate([v, pad], axis=-1).astype(np.float32) for k, v in o.items()}
+            self._last_obs = o
+            return o
 
         def step(self, actions):
             o, r, d, i = super().step(actions)
@@ -249,6 +356,24 @@ def get_lcf_env(env_class):
                     cr = np.cos(rad) * r[k] + np.sin(rad) * inf["nei_rewards"]
                 inf["coordinated_rewards"], inf["native_rewards"] = cr, r[k]
                 new_r[k] = r[k] if self.config["return_native_reward"] else cr
+            if self.config["add_traffic_light"]:
+                self._traffic_light_counter += 1                                   # :315-316
+                o = self._with_traffic_light(o)
+            if self._comm_on:                                                      # :363-388
+                n_nei = self.config["communication"]["comm_neighbours"]
+                new_o = {}
+                for k, old_obs in o.items():
+                    comm_obs = i[k][COMM_CURRENT_OBS]
+                    if len(comm_obs) < n_nei:
+                        comm_obs.extend([np.zeros((self._comm_dim,))] * (n_nei - len(comm_obs)))
+                    new_o[k] = np.concatenate([old_obs] + comm_obs).astype(np.float32)
+                o = new_o
+                for k, inf in i.items():
+                    nei = inf["neighbours"]
+                    inf[NEI_OBS] = [self._last_obs[nei[j]] if j < len(nei) and nei[j] in self._last_obs else None
+                                    for j in range(n_nei)]
+                    inf[NEI_OBS].append(None)       # the reference's extra None ("to make sure np.array fails")
+            self._last_obs = o
             return o, new_r, d, i
 
         def set_lcf_dist(self, mean, std):

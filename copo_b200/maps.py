@@ -171,6 +171,24 @@ class MapTables:
     def obs_dim(self):
         return self.base_obs_dim
 
+    def bounding_box(self):
+        """(x_min, x_max, y_min, y_max) of the drivable surface - what the reference reads from
+        `road_network.get_bounding_box()` for the traffic-light message (env_wrappers.py:268-272).  Every segment's
+        centre line is sampled at 17 points and widened by its left / right widths."""
+        xs, ys = [], []
+        for x0, y0, h0, slen, kappa, wl, wr, c0, s0, cx, cy, r in self.seg.astype(np.float64):
+            for t in np.linspace(0.0, slen, 17):
+                if kappa == 0.0:
+                    x, y, h = x0 + t * c0, y0 + t * s0, h0
+                else:
+                    h = h0 + kappa * t
+                    sgn = 1.0 if kappa > 0.0 else -1.0
+                    x, y = cx + sgn * r * math.sin(h), cy - sgn * r * math.cos(h)
+                nx, ny = -math.sin(h), math.cos(h)                     # left normal
+                xs += [x + wl * nx, x - wr * nx]
+                ys += [y + wl * ny, y - wr * ny]
+        return float(min(xs)), float(max(xs)), float(min(ys)), float(max(ys))
+
 
 # ---------------------------------------------------------------------------------------------
 # Map builders.  Right-hand traffic; arm k points outward along angle k*90 deg.

@@ -104,3 +104,38 @@ def cc_step(positions, rewards, neighbours_distance=40):
         names, dists = find_in_range(dm, k, neighbours_distance)
         infos[k] = dict(all_agents=list(rewards.keys()), neighbours=names, neighbours_distance=dists)
     return infos
+
+
+# ---- disabled-by-default branches of CCEnv / LCFEnv ---------------------------------------
+def traffic_light_msg(counter, fix_interval=30):
+    """env_wrappers.py:259-266: a saw-tooth in [0.9, 1] / [0, 0.1] that flips every `fix_interval` steps."""
+    increment = (counter % fix_interval) / fix_interval * 0.1
+    if ((counter // fix_interval) % 2) == 1:
+        return 0 + increment
+    else:
+        return 1 - increment
+
+
+def agent_traffic_light_msg(msg, pos, b_box):
+    """env_wrappers.py:268-272: message + the agent's position normalised by the map's bounding box
+    (x_min, x_max, y_min, y_max), clipped to [0, 1], float32."""
+    pos0 = (pos[0] - b_box[0]) / (b_box[1] - b_box[0])
+    pos1 = (pos[1] - b_box[2]) / (b_box[3] - b_box[2])
+    return np.clip(np.array([msg, pos0, pos1]), 0, 1).astype(np.float32)
+
+
+def comm_current_obs(neighbours, comm_actions, comm_size=4, comm_neighbours=4):
+    """env_wrappers.py:104-121 without `add_pos_in_comm`: what agent k hears = the message part of the action of
+    each of its first `comm_neighbours` neighbours (zeros for a neighbour that did not act)."""
+    out = []
+    for n in neighbours[:comm_neighbours]:
+        out.append(comm_actions[n] if n in comm_actions else np.zeros((comm_size,)))
+    return out
+
+
+def lcf_comm_obs(old_obs, comm_obs, comm_size=4, comm_neighbours=4):
+    """env_wrappers.py:363-372: the heard messages, zero-padded to `comm_neighbours`, appended to the observation."""
+    comm_obs = list(comm_obs)
+    if len(comm_obs) < comm_neighbours:
+        comm_obs.extend([np.zeros((comm_size,))] * (comm_neighbours - len(comm_obs)))
+    return np.concatenate([old_obs] + comm_obs).astype(np.float32)
