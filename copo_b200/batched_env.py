@@ -19,8 +19,12 @@ MAP_OF_ENV = {
     "MultiAgentTollgateEnv": "tollgate",
     "MultiAgentBottleneckEnv": "bottleneck",
     "MultiAgentParkingLotEnv": "parking_lot",
+    "MultiAgentMetaDrive": "pg",
 }
-DEFAULT_NUM_AGENTS = {"intersection": 30, "roundabout": 40, "tollgate": 40, "bottleneck": 20, "parking_lot": 10}
+# the reference's eval script passes these explicitly (eval/evaluate_population.py:106-132); "pg" (MultiAgentMetaDrive's
+# own default) is recalled, not verifiable here
+DEFAULT_NUM_AGENTS = {"intersection": 30, "roundabout": 40, "tollgate": 40, "bottleneck": 20, "parking_lot": 10,
+                      "pg": 15}
 
 FLAG_VALID, FLAG_DONE, FLAG_ARRIVE, FLAG_CRASH, FLAG_OUT, FLAG_MAXSTEP, FLAG_SPAWNED, FLAG_ALIVE = (
     1 << k for k in range(8))

@@ -101,7 +101,7 @@ class MultiAgentDrivingEnv:
                                       allow_respawn=bool(c["allow_respawn"]), auto_reset=False,
                                       append_lcf=self.APPEND_LCF, lcf_uniform=(c.get("lcf_dist") == "uniform"),
                                       seed=int(c["start_seed"]), lcf_std=float(c.get("lcf_normal_std", 0.1)),
-                                      force_lcf=float(c.get("force_lcf", -100)))
+                                      force_lcf=float(c.get("force_lcf", -100)), map_kwargs=c.get("map_config"))
         self.A, self.D = self._sim.A, self._sim.D
         self._slot_of, self.vehicles, self.vehicles_including_just_terminated = {}, {}, {}
         self._agent_ids = set(["agent{}".format(i) for i in range(100)] + ["{}".format(i) for i in range(10000)])
@@ -204,6 +204,7 @@ MultiAgentRoundaboutEnv = _named("roundabout", "MultiAgentRoundaboutEnv")
 MultiAgentTollgateEnv = _named("tollgate", "MultiAgentTollgateEnv")
 MultiAgentBottleneckEnv = _named("bottleneck", "MultiAgentBottleneckEnv")
 MultiAgentParkingLotEnv = _named("parking_lot", "MultiAgentParkingLotEnv")
+MultiAgentMetaDrive = _named("pg", "MultiAgentMetaDrive")      # procedurally generated maps: config["map_config"]
 
 
 def get_ccenv(env_class):

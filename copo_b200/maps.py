@@ -373,7 +373,54 @@ def build_parking_lot(parking_space_num=8, road_len=60.0, slot_depth=8.0, spawn_
     return b.pack("parking_lot")
 
 
+def build_pg(seed=0, num_blocks=3, straight=50.0, radius=35.0, spawn_spacing=10.0, spawn_first=5.0,
+             spawns_per_lane=4):
+    """Procedurally generated two-way road (the reference's `MultiAgentMetaDrive` runs on MetaDrive's PG maps): a
+    straight entry, `num_blocks` blocks drawn from the map seed - straight, left curve, right curve of 30 to 90
+    degrees - and a straight exit; two lanes per direction, every lane one route, spawn places on the entry straight
+    of each direction."""
+    assert 0 <= num_blocks <= ROUTE_MAX_SEGS - 2, "a route holds at most %d segments" % ROUTE_MAX_SEGS
+    rng = np.random.default_rng(int(seed))
+    blocks = []
+    for _ in range(num_blocks):
+        kind = int(rng.integers(0, 3))
+        if kind == 0:
+            blocks.append(("s", straight))
+        else:
+            ang = float(rng.uniform(math.pi / 6.0, math.pi / 2.0)) * (1.0 if kind == 1 else -1.0)
+            blocks.append(("a", radius, ang))
+    centre = [("s", straight)] + blocks + [("s", straight)]
+    # end pose of the centre line (the reverse carriageway starts there, facing back)
+    x, y, h = 0.0, 0.0, 0.0
+    for p in centre:
+        if p[0] == "s":
+            x, y, h = _Builder._end_pose(x, y, h, p[1], 0.0)
+        else:
+            x, y, h = _Builder._end_pose(x, y, h, abs(p[2]) * p[1], (1.0 if p[2] > 0 else -1.0) / p[1])
+    b = _Builder()
+    w = LANE_WIDTH
+    for direction, (sx, sy, sh, pieces) in enumerate(((0.0, 0.0, 0.0, centre),
+                                                      (x, y, h + math.pi, [q if q[0] == "s" else ("a", q[1], -q[2])
+                                                                           for q in reversed(centre)]))):
+        for lane in range(2):
+            off = (lane + 0.5) * w                     # to the right of the centre line in the travel direction
+            wl, wr = _lane_bounds(lane)
+            start = (sx + off * math.sin(sh), sy - off * math.cos(sh), sh)
+            lane_pieces = []
+            for q in pieces:
+                if q[0] == "s":
+                    lane_pieces.append(("s", q[1], wl, wr))
+                else:                                  # a lane right of the centre line: wider on left curves
+                    lane_pieces.append(("a", q[1] + off if q[2] > 0 else q[1] - off, q[2], wl, wr))
+            ids = b.chain(start, lane_pieces)
+            rid = b.add_route(ids)
+            for k in range(spawns_per_lane):
+                b.add_spawn(ids[0], spawn_first + k * spawn_spacing, [rid])
+    return b.pack("pg")
+
+
 _BUILDERS = {
+    "pg": build_pg,
     "intersection": build_intersection,
     "roundabout": build_roundabout,
     "tollgate": build_tollgate,

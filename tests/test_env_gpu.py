@@ -36,6 +36,8 @@ def _to_np(out):
     ("intersection", 5, 64, 50, dict()),                      # maximum slot count (more slots than spawn places)
     ("parking_lot", 33, 1, 40, dict()),                       # single-slot scenes, ragged last CTA group
     ("roundabout", 1, 3, 30, dict(force_lcf=0.5, delay_done=1)),
+    ("pg", 4, 15, 150, dict()),                               # procedurally generated map (fused kernel: < 16 slots)
+    ("pg", 3, 20, 100, dict()),
 ])
 @pytest.mark.parametrize("split", [0, 1])
 def test_env_step_bit_exact(map_name, S, A, T, kw, split, monkeypatch):

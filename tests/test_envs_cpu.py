@@ -164,3 +164,17 @@ def test_message_channel_branch():
         o, r, d, i = env2.step({k: np.concatenate([[0.0, 0.7], np.full(4, 0.25)]).astype(np.float32) for k in env2.vehicles})
     full = [c for inf in i.values() for c in inf["comm_current_obs"] if c.any()]
     assert full and all(c.shape == (7,) and (c[4:] >= 0).all() and (c[4:] <= 1).all() for c in full)
+
+
+def test_procedural_map_env():
+    """`MultiAgentMetaDrive` (the reference's PG-map environment, train_all_cl.py:23): `map_config` picks the map."""
+    cls = envs.get_lcf_env(envs.MultiAgentMetaDrive)
+    assert cls.__name__ == "LCFMultiAgentMetaDrive" and cls.default_config()["num_agents"] == 15
+    a = cls({"start_seed": 1, "map_config": {"seed": 5, "num_blocks": 2}})
+    b = cls({"start_seed": 1, "map_config": {"seed": 6, "num_blocks": 2}})
+    oa, ob = a.reset(), b.reset()
+    assert len(oa) == 15 and all(v.shape == (92,) for v in oa.values())
+    assert a._sim.tables.bounding_box() != b._sim.tables.bounding_box()
+    for t in range(30):
+        oa, r, d, i = a.step({k: np.array([0.0, 0.8], np.float32) for k in a.vehicles})
+    assert all("neighbours" in inf and 0.0 <= inf["route_completion"] <= 1.05 for inf in i.values())

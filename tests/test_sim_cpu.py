@@ -34,6 +34,7 @@ def _policy(obs, rng, S, A):
     ("intersection", 2, 64, 25, dict()),
     ("parking_lot", 5, 1, 30, dict()),
     ("roundabout", 1, 3, 30, dict(force_lcf=0.5, delay_done=1)),
+    ("pg", 3, 15, 120, dict()),
 ])
 def test_host_phases_match_spec(map_name, S, A, T, kw):
     tables = build_map(map_name)
@@ -173,7 +174,7 @@ def test_det_math_accuracy():
 
 
 @pytest.mark.parametrize("name,odim", [("intersection", 91), ("roundabout", 91), ("parking_lot", 91),
-                                       ("bottleneck", 96), ("tollgate", 156)])
+                                       ("bottleneck", 96), ("tollgate", 156), ("pg", 91)])
 def test_map_tables(name, odim):
     """Observation widths are the ones the shipped policies pin (first-layer shapes of
     best_checkpoints/*.npz); routes are continuous chains."""
@@ -189,3 +190,35 @@ def test_map_tables(name, odim):
         assert 1 <= m.spawn_nroute[p] <= 4
         for k in range(m.spawn_nroute[p]):
             assert m.route_seg[m.spawn_route[p, k], 0] == m.spawn_seg[p]
+
+
+@pytest.mark.parametrize("seed,num_blocks", [(0, 0), (1, 1), (2, 3), (3, 4), (7, 4), (11, 2)])
+def test_procedural_maps(seed, num_blocks):
+    """`build_pg`: every seed gives a valid table set (continuous lane chains in both directions, spawn places on the
+    entry straights) and the host build of the kernel phases follows the spec on it."""
+    m = build_map("pg", seed=seed, num_blocks=num_blocks)
+    assert m.base_obs_dim == 91 and m.n_route == 4 and m.n_spawn == 16 and m.blob.size % 4 == 0
+    assert (m.route_nseg == num_blocks + 2).all()
+    for r in range(m.n_route):
+        ids = m.route_seg[r, :m.route_nseg[r]]
+        assert m.seg[ids[0], 4] == 0.0 and m.seg[ids[-1], 4] == 0.0
+        for a, b in zip(ids[:-1], ids[1:]):
+            ex, ey = osim.OracleSim._seg_end(m.seg[a])
+            assert abs(ex - m.seg[b, 0]) < 1e-3 and abs(ey - m.seg[b, 1]) < 1e-3, (seed, r)
+    # the two carriageways run in opposite directions next to each other: lane 0 of one ends beside lane 0 of the other
+    e0 = osim.OracleSim._seg_end(m.seg[m.route_seg[0, m.route_nseg[0] - 1]])
+    s2 = m.seg[m.route_seg[2, 0], 0:2]
+    assert abs(np.hypot(e0[0] - s2[0], e0[1] - s2[1]) - 3.5) < 1e-2
+    assert build_map("pg", seed=seed, num_blocks=num_blocks) is m              # cached per (seed, blocks)
+    if num_blocks in (3, 4):
+        S, A, cfg = 2, 15, osim.SimConfig(seed=seed)
+        cfg.num_agents = A
+        ref, hs = osim.OracleSim(m, S, A, cfg), sc.HostSim(m, S, A, cfg)
+        r = ref.reset()
+        sc.compare_outputs(r, hs.reset(), "reset")
+        rng = np.random.default_rng(seed)
+        for t in range(60):
+            act = _policy(r["obs"], rng, S, A)
+            r = ref.step(act)
+            sc.compare_outputs(r, hs.step(act), "pg seed %d step %d" % (seed, t))
+        sc.compare_state(ref, hs.state(), "pg seed %d" % seed)
