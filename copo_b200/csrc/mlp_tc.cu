@@ -139,6 +139,57 @@ __device__ __forceinline__ void st_global_256(void* p, uint32_t a0, uint32_t a1,
                  "r"(a4), "r"(a5), "r"(a6), "r"(a7)
                  : "memory");
 }
+// ---- packed fp32 pairs (sm_100: fma / mul / add .f32x2, SASS FFMA2 / FMUL2 / FADD2) -----------------------------------
+// EXPERIMENTAL (B2C_TC_PACKED=1; off by default, not measured yet): the epilogue's bias add, rational tanh and fused
+// output layer on two columns per instruction.  Same operations per element as the scalar path, so the results agree
+// up to the output layer's summation order and the division (rcp.approx * p instead of div.approx).
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t bc2(float x) { return pk2(x, x); }
+__device__ __forceinline__ uint64_t fast_tanh2(uint64_t x) {
+    float x0, x1;
+    upk2(x, x0, x1);
+    x0 = fminf(fmaxf(x0, -9.0f), 9.0f);
+    x1 = fminf(fmaxf(x1, -9.0f), 9.0f);
+    x = pk2(x0, x1);
+    const uint64_t x2 = mul2(x, x);
+    uint64_t p = bc2(-2.76076847742355e-16f);
+    p = fma2(p, x2, bc2(2.00018790482477e-13f));
+    p = fma2(p, x2, bc2(-8.60467152213735e-11f));
+    p = fma2(p, x2, bc2(5.12229709037114e-08f));
+    p = fma2(p, x2, bc2(1.48572235717979e-05f));
+    p = fma2(p, x2, bc2(6.37261928875436e-04f));
+    p = fma2(p, x2, bc2(4.89352455891786e-03f));
+    p = mul2(p, x);
+    uint64_t q = bc2(1.19825839466702e-06f);
+    q = fma2(q, x2, bc2(1.18534705686654e-04f));
+    q = fma2(q, x2, bc2(2.26843463243900e-03f));
+    q = fma2(q, x2, bc2(4.89352518554385e-03f));
+    float q0, q1, r0, r1;
+    upk2(q, q0, q1);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(q0));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(q1));
+    return mul2(p, pk2(r0, r1));
+}
 __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
     return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
@@ -167,7 +218,7 @@ struct LinearArgs {
 
 // EPI = epilogue warps (8, 12 or 16: two, three or four per scheduler).  The 8 column chunks of a tile are dealt to
 // EPI / 4 column groups; a warp reads the TMEM lanes of its quarter (warp % 4) and the chunks of its group.
-template <int EPI>
+template <int EPI, bool PACKED = false>
 __global__ void __launch_bounds__(128 + EPI * 32, 1)
 tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                  const __grid_constant__ LinearArgs args) {
@@ -292,12 +343,42 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const bool live = row < args.M;
             const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
             float hacc[HEAD_MAX] = {0.0f, 0.0f, 0.0f, 0.0f};
+            uint64_t hacc2[HEAD_MAX] = {0ull, 0ull, 0ull, 0ull};         // PACKED: (even, odd) column partial sums
 #pragma unroll 1
             for (int c = c_begin; c < c_end; ++c) {              // 32-column chunks of this warp's group
                 uint32_t r[32];
                 tmem_ld32(taddr0 + (uint32_t)(c * 32), r);
                 if (args.probe == 1) { hacc[0] += __uint_as_float(r[0]) + __uint_as_float(r[31]); continue; }
                 float v[32];
+                if constexpr (PACKED) {
+                    uint64_t vv[16];
+                    const ulonglong2* b2 = reinterpret_cast<const ulonglong2*>(s_bias + c * 32);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        ulonglong2 bb = b2[j];
+                        vv[2 * j] = add2(pk2(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])), bb.x);
+                        vv[2 * j + 1] = add2(pk2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), bb.y);
+                    }
+                    if (args.act == 1) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) vv[j] = fast_tanh2(vv[j]);
+                    }
+                    if (args.head_w) {
+                        for (int hj = 0; hj < args.head_n; ++hj) {
+                            const ulonglong2* w2 = reinterpret_cast<const ulonglong2*>(s_head_w + hj * BLOCK_N + c * 32);
+                            uint64_t a = hacc2[hj];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                ulonglong2 ww = w2[j];
+                                a = fma2(vv[2 * j], ww.x, a);
+                                a = fma2(vv[2 * j + 1], ww.y, a);
+                            }
+                            hacc2[hj] = a;
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) upk2(vv[j], v[2 * j], v[2 * j + 1]);
+                } else {
                 const float4* b4 = reinterpret_cast<const float4*>(s_bias + c * 32);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -321,6 +402,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         }
                         hacc[hj] = a;
                     }
+                }
                 }
                 if (live) {
                     if (args.dtanh_src) {
@@ -382,6 +464,14 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if constexpr (PACKED) {
+#pragma unroll
+                for (int hj = 0; hj < HEAD_MAX; ++hj) {
+                    float e, o;
+                    upk2(hacc2[hj], e, o);
+                    hacc[hj] += e + o;
+                }
+            }
             if (args.head_w) {
                 // the column groups of a row live in warps w, w + 4, ...: groups 1.. hand their partial sums to group 0
                 // through shared memory (named barrier 1 = the epilogue warps); summed in group order
@@ -717,6 +807,8 @@ static int tc_linear_launch(const uint16_t* a_split, const uint16_t* w_prep, con
         B2C_CUDA(cudaFuncSetAttribute(tc_linear_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX_OPTIN));
         B2C_CUDA(cudaFuncSetAttribute(tc_linear_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX_OPTIN));
         B2C_CUDA(cudaFuncSetAttribute(tc_linear_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX_OPTIN));
+        B2C_CUDA(cudaFuncSetAttribute(tc_linear_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX_OPTIN));
+        B2C_CUDA(cudaFuncSetAttribute(tc_linear_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX_OPTIN));
         int dev = 0;
         B2C_CUDA(cudaGetDevice(&dev));
         B2C_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -742,6 +834,7 @@ static int tc_linear_launch(const uint16_t* a_split, const uint16_t* w_prep, con
     // stores over more concurrent streams (profiles/r01_g_tc_probe_epi*.json)
     static const int epi_env = getenv("B2C_TC_EPI_WARPS") ? atoi(getenv("B2C_TC_EPI_WARPS")) : 0;
     const int epi = epi_env ? epi_env : (head ? 16 : 8);
+    static const bool packed = getenv("B2C_TC_PACKED") != nullptr;      // experimental f32x2 epilogue math
     a.probe = probe;
     a.products = products == 3 ? 3 : 4;
     a.resident = 0; a.stages = STAGES;
@@ -760,7 +853,9 @@ static int tc_linear_launch(const uint16_t* a_split, const uint16_t* w_prep, con
     }
     int tiles = (M + BLOCK_M - 1) / BLOCK_M;
     int grid = tiles < num_sms ? tiles : num_sms;
-    if (epi == 16) tc_linear_kernel<16><<<grid, 128 + 16 * 32, smem_bytes, (cudaStream_t)stream>>>(map_a, map_w, a);
+    if (packed && epi == 16) tc_linear_kernel<16, true><<<grid, 128 + 16 * 32, smem_bytes, (cudaStream_t)stream>>>(map_a, map_w, a);
+    else if (packed) tc_linear_kernel<8, true><<<grid, 128 + 8 * 32, smem_bytes, (cudaStream_t)stream>>>(map_a, map_w, a);
+    else if (epi == 16) tc_linear_kernel<16><<<grid, 128 + 16 * 32, smem_bytes, (cudaStream_t)stream>>>(map_a, map_w, a);
     else if (epi == 12) tc_linear_kernel<12><<<grid, 128 + 12 * 32, smem_bytes, (cudaStream_t)stream>>>(map_a, map_w, a);
     else tc_linear_kernel<8><<<grid, 128 + 8 * 32, smem_bytes, (cudaStream_t)stream>>>(map_a, map_w, a);
     B2C_CUDA(cudaGetLastError());
