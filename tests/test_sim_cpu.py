@@ -222,3 +222,34 @@ def test_procedural_maps(seed, num_blocks):
             r = ref.step(act)
             sc.compare_outputs(r, hs.step(act), "pg seed %d step %d" % (seed, t))
         sc.compare_state(ref, hs.state(), "pg seed %d" % seed)
+
+
+def test_laser_ownership_formula():
+    """Model of `lidar_spread` (env_step.cu): 32 pairs per warp, pair p owns lasers [excl_p, excl_p + cnt_p); live pairs
+    have cnt >= 1 and dead lanes only trail.  For the batch of lasers r0 .. r0+31 the owner of laser r0 + lane is
+    (pairs started before the batch) + popcount(starts at positions <= lane) - 1, where `starts` has a bit per pair that
+    begins inside the batch - the kernel gets it from one warp-wide OR.  Checked against a plain search."""
+    rng = np.random.default_rng(0)
+    for trial in range(300):
+        n_live = int(rng.integers(1, 33))
+        cnt = np.zeros(32, np.int64)
+        cnt[:n_live] = rng.integers(1, 73, n_live)
+        if trial % 3 == 0:
+            cnt[:n_live] = 1                                   # every pair a single laser
+        excl = np.concatenate([[0], np.cumsum(cnt)[:-1]])
+        total = int(cnt.sum())
+        before = 0
+        for r0 in range(0, total, 32):
+            pos = excl - r0
+            starts = 0
+            for p in range(32):
+                if cnt[p] > 0 and 0 <= pos[p] < 32:
+                    starts |= 1 << int(pos[p])
+            for lane in range(32):
+                r = r0 + lane
+                if r >= total:
+                    continue
+                lo = before + bin(starts & (0xffffffff >> (31 - lane))).count("1") - 1
+                want = int(np.searchsorted(excl[:n_live], r, side="right")) - 1
+                assert lo == want and excl[lo] <= r < excl[lo] + cnt[lo], (trial, r0, lane)
+            before += bin(starts).count("1")
