@@ -76,11 +76,16 @@ def test_env_step_bit_exact(map_name, S, A, T, kw, split, monkeypatch):
         assert seen["crash"] > 0 and seen["spawn"] > 0
 
 
-def test_env_full_size_properties():
-    """C2-sized batch (4096 x 40): invariants that do not need the oracle."""
+@pytest.mark.parametrize("map_name,S,A", [
+    ("intersection", 4096, 40),      # C2 (BASELINE.json configs[1])
+    ("roundabout", 4096, 40),        # C3
+    ("tollgate", 1024, 40),          # C4: 8192 scenes over 8 GPUs
+    ("parking_lot", 4096, 10),       # C5: 32768 scenes over 8 GPUs (small-observation path, fused kernel)
+])
+def test_env_full_size_properties(map_name, S, A):
+    """Per-GPU batches of BASELINE.json's configurations: invariants that do not need the oracle."""
     from copo_b200.batched_env import BatchedDrivingEnv, FLAG_VALID, FLAG_DONE, FLAG_SPAWNED, FLAG_ALIVE
-    S, A = 4096, 40
-    env = BatchedDrivingEnv("intersection", num_scenes=S, num_slots=A, num_agents=A, seed=0)
+    env = BatchedDrivingEnv(map_name, num_scenes=S, num_slots=A, num_agents=A, seed=0)
     o = env.reset()
     assert int(((o["flags"] & FLAG_SPAWNED) > 0).sum()) == S * A
     gen = torch.Generator(device="cuda").manual_seed(0)
@@ -103,7 +108,7 @@ def test_env_full_size_properties():
     g = rew.sum(1) / part.sum(1).clamp(min=1)
     assert torch.allclose(g, o["global_reward"], atol=1e-5)
     # identical scenes+seed reproduce bit-identically
-    env2 = BatchedDrivingEnv("intersection", num_scenes=S, num_slots=A, num_agents=A, seed=0)
+    env2 = BatchedDrivingEnv(map_name, num_scenes=S, num_slots=A, num_agents=A, seed=0)
     env2.reset()
     gen = torch.Generator(device="cuda").manual_seed(0)
     for t in range(60):
