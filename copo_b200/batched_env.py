@@ -153,6 +153,8 @@ class BatchedDrivingEnv:
             self._copy_stream = torch.cuda.Stream(device=self.device)
             self._ev_chunk = [torch.cuda.Event() for _ in self._chunks]
             self._ev_copy = torch.cuda.Event()
+            self._ev_act = torch.cuda.Event()
+            self._act_staged = False
             self._copy_pending = False
             self.h2d_bytes_per_step = self._dev_act.numel() * 4
             self.d2h_bytes_per_step = sum(v.numel() * v.element_size() for v in self._host.values())
@@ -166,12 +168,16 @@ class BatchedDrivingEnv:
         host = self._host_buffers()
         a = torch.as_tensor(actions_host, dtype=torch.float32)
         assert tuple(a.shape) == (self.S, self.A, 2), a.shape
-        if not (a.is_pinned() and a.is_contiguous()):
-            a = self._pin_act.copy_(a)
         cur = torch.cuda.current_stream(self.device)
+        if not (a.is_pinned() and a.is_contiguous()):
+            if self._act_staged:                             # the previous call's H2D copy may still be reading the
+                self._ev_act.synchronize()                   # staging buffer: wait before overwriting it
+            a = self._pin_act.copy_(a)
+            self._act_staged = True
         if self._copy_pending:                               # a forgotten wait_host() must not race the arena
             cur.wait_event(self._ev_copy)
         self._dev_act.copy_(a, non_blocking=True)
+        self._ev_act.record(cur)
         self.host_step_out["obs_split"] = obs_split
         dev_obs, host_obs = self.host_step_out["obs"], host["obs"]
         for c, (f, n) in enumerate(self._chunks):

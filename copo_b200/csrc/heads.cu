@@ -140,6 +140,7 @@ struct PpoHeadArgs {
     double* stats;              // [8]: sum(-surr), sum vloss0..2, sum entropy, sum kl, sum logp, rows
     int M, n_heads, mode;       // mode 0: PPO loss, 1: mean(logp) (old-policy term of the meta-gradient)
     float clip, vf_clip, vf_coeff, ent_coeff, kl_coeff, inv_rows;
+    int plain_vf;               // old_value_loss=False: clamp((v - t)^2, 0, vf_clip)
 };
 
 __global__ void ppo_head_kernel(const PpoHeadArgs a) {
@@ -185,6 +186,12 @@ __global__ void ppo_head_kernel(const PpoHeadArgs a) {
             for (int hd = 0; hd < a.n_heads; ++hd) {
                 float v = a.v_cur[hd][m], vo = a.v_old[hd][m], t = a.v_tgt[hd][m];
                 float l1 = (v - t) * (v - t);
+                if (a.plain_vf) {
+                    // torch.clamp passes the gradient where 0 <= x <= max (inclusive)
+                    a.dv[hd][m] = (l1 <= a.vf_clip) ? s * a.vf_coeff * 2.0f * (v - t) : 0.0f;
+                    st[1 + hd] = fminf(l1, a.vf_clip);
+                    continue;
+                }
                 float dvc = fminf(fmaxf(v - vo, -a.vf_clip), a.vf_clip);
                 float vc = vo + dvc;
                 float l2 = (vc - t) * (vc - t);
@@ -212,9 +219,14 @@ __global__ void ppo_head_kernel(const PpoHeadArgs a) {
 // with phi = (mean + std * eps) * pi/2
 __global__ void lcf_meta_terms_kernel(const float* __restrict__ adv, const float* __restrict__ nei,
                                       const float* __restrict__ eps, int M, float mean, float std,
-                                      double* __restrict__ out) {
+                                      const float* __restrict__ params, double* __restrict__ out) {
     int m = blockIdx.x * blockDim.x + threadIdx.x;
     double c = 0, d = 0, de = 0;
+    if (params) {
+        // CoPOModel.lcf_mean / lcf_std from the raw parameters (algo_copo.py:171-177)
+        mean = fminf(fmaxf(tanhf(params[0]), -1.0f + 1e-6f), 1.0f - 1e-6f);
+        std = expf(fminf(fmaxf(params[1], -20.0f), 2.0f));
+    }
     if (m < M) {
         float e = eps[m];
         float phi = (mean + std * e) * 1.57079632679489661923f;
@@ -301,7 +313,8 @@ int b2c_ppo_head(const b2c_ppo_head_args* p, void* stream) {
     }
     a.dlogits = p->dlogits; a.stats = p->stats; a.M = p->rows; a.n_heads = p->n_heads; a.mode = p->mode;
     a.clip = p->clip_param; a.vf_clip = p->vf_clip_param; a.vf_coeff = p->vf_loss_coeff; a.ent_coeff = p->entropy_coeff;
-    a.kl_coeff = p->kl_coeff; a.inv_rows = 1.0f / (float)p->rows;
+    a.kl_coeff = p->kl_coeff; a.inv_rows = 1.0f / (float)(p->norm_rows > 0 ? p->norm_rows : p->rows);
+    a.plain_vf = p->plain_value_loss ? 1 : 0;
     ppo_head_kernel<<<(p->rows + 255) / 256, 256, 0, (cudaStream_t)stream>>>(a);
     B2C_CUDA(cudaGetLastError());
     return B2C_OK;
@@ -312,7 +325,18 @@ int b2c_lcf_meta_terms(const float* adv, const float* nei_adv, const float* eps,
     if (rows == 0) return B2C_OK;
     if (!adv || !nei_adv || !eps || !out3) return b2c_set_error(B2C_ERR_ARG, "b2c_lcf_meta_terms: null argument");
     lcf_meta_terms_kernel<<<(rows + 255) / 256, 256, 0, (cudaStream_t)stream>>>(adv, nei_adv, eps, rows, lcf_mean, lcf_std,
-                                                                               out3);
+                                                                               nullptr, out3);
+    B2C_CUDA(cudaGetLastError());
+    return B2C_OK;
+}
+
+int b2c_lcf_meta_terms_params(const float* adv, const float* nei_adv, const float* eps, int rows,
+                              const float* lcf_parameters, double* out3, void* stream) {
+    if (rows == 0) return B2C_OK;
+    if (!adv || !nei_adv || !eps || !out3 || !lcf_parameters)
+        return b2c_set_error(B2C_ERR_ARG, "b2c_lcf_meta_terms_params: null argument");
+    lcf_meta_terms_kernel<<<(rows + 255) / 256, 256, 0, (cudaStream_t)stream>>>(adv, nei_adv, eps, rows, 0.0f, 1.0f,
+                                                                               lcf_parameters, out3);
     B2C_CUDA(cudaGetLastError());
     return B2C_OK;
 }

@@ -13,11 +13,16 @@ from .batched_env import (BatchedDrivingEnv, FLAG_ARRIVE, FLAG_CRASH, FLAG_DONE,
 
 
 def evaluate(model, env="MultiAgentIntersectionEnv", num_scenes=64, num_agents=None, horizon=1000, seed=0,
-             deterministic=False, lcf_mean=0.0, lcf_std=0.1, neighbours_distance=20.0, device=None):
+             deterministic=False, lcf_mean=0.0, lcf_std=0.1, neighbours_distance=20.0, device=None, append_lcf=None):
     """Runs one episode of `horizon` steps in every scene with `model` (CCModel / CoPOModel) acting for all agents.
-    `neighbours_distance` is RecorderEnv's evaluation radius (default 20, recoder.py:75)."""
+    `neighbours_distance` is RecorderEnv's evaluation radius (default 20, recoder.py:75).  `append_lcf`: whether the
+    policy takes the LCF as its last observation entry (CoPO policies); default: a CoPOModel does, any other model
+    does when its input is one wider than the map's base observation."""
+    from .maps import build_map
+    from .models import CoPOModel
     map_name = MAP_OF_ENV.get(env, env)
-    append_lcf = model.obs_dim in (92, 97, 157)              # CoPO policies take the LCF as the last obs entry
+    if append_lcf is None:
+        append_lcf = isinstance(model, CoPOModel) or model.obs_dim == build_map(map_name).base_obs_dim + 1
     sim = BatchedDrivingEnv(map_name, num_scenes=num_scenes, num_agents=num_agents, num_slots=num_agents,
                             horizon=horizon, auto_reset=False, append_lcf=append_lcf, seed=seed, lcf_mean=lcf_mean,
                             lcf_std=lcf_std, neighbours_distance=neighbours_distance, device=device or model.device)

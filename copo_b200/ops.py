@@ -29,7 +29,8 @@ class PpoHeadArgs(ctypes.Structure):
                  ("dlogits", ctypes.c_void_p), ("dv", ctypes.c_void_p * 3), ("stats", ctypes.c_void_p),
                  ("rows", ctypes.c_int32), ("n_heads", ctypes.c_int32), ("mode", ctypes.c_int32)] +
                 [(n, ctypes.c_float) for n in ("clip_param", "vf_clip_param", "vf_loss_coeff", "entropy_coeff",
-                                               "kl_coeff")])
+                                               "kl_coeff")] +
+                [("norm_rows", ctypes.c_int32), ("plain_value_loss", ctypes.c_int32)])
 
 
 class GaeArgs(ctypes.Structure):
@@ -115,8 +116,9 @@ def gaussian_sample(logits, eps=None, seed=0, step=0, deterministic=False, want_
     return (actions, logp, eps_out) if want_eps else (actions, logp)
 
 
-def ppo_head(logits, actions, old_logp, old_logits, adv, heads, cfg, mode=0, stats=None):
-    """heads: list of (v_cur, v_old, v_tgt) triples.  Returns (dlogits, [dv...], stats[8] float64)."""
+def ppo_head(logits, actions, old_logp, old_logits, adv, heads, cfg, mode=0, stats=None, norm_rows=0):
+    """heads: list of (v_cur, v_old, v_tgt) triples.  Returns (dlogits, [dv...], stats[8] float64).
+    norm_rows: rows the loss means are taken over (0: this call's rows; data parallel: the global minibatch size)."""
     lib = _lib_ready()
     M = logits.shape[0]
     dev = logits.device
@@ -135,15 +137,22 @@ def ppo_head(logits, actions, old_logp, old_logits, adv, heads, cfg, mode=0, sta
     a.rows, a.n_heads, a.mode = M, len(heads), mode
     a.clip_param, a.vf_clip_param = cfg["clip_param"], cfg["vf_clip_param"]
     a.vf_loss_coeff, a.entropy_coeff, a.kl_coeff = cfg["vf_loss_coeff"], cfg["entropy_coeff"], cfg["kl_coeff"]
+    a.norm_rows, a.plain_value_loss = int(norm_rows), 0 if cfg.get("old_value_loss", True) else 1
     _lib.check(lib.b2c_ppo_head(ctypes.byref(a), _lib.stream_ptr()))
     return dlogits, dvs, stats
 
 
-def lcf_meta_terms(adv, nei_adv, eps, lcf_mean, lcf_std):
+def lcf_meta_terms(adv, nei_adv, eps, lcf_mean=None, lcf_std=None, lcf_parameters=None):
+    """Sums of the LCF side of the meta-gradient; the current LCF comes either as host floats or (no host read) from
+    the model's raw `lcf_parameters` device tensor."""
     lib = _lib_ready()
     out = torch.zeros(3, dtype=torch.float64, device=adv.device)
-    _lib.check(lib.b2c_lcf_meta_terms(P(_f32(adv)), P(_f32(nei_adv)), P(_f32(eps)), c_int(adv.numel()),
-                                      c_float(lcf_mean), c_float(lcf_std), P(out), _lib.stream_ptr()))
+    if lcf_parameters is not None:
+        _lib.check(lib.b2c_lcf_meta_terms_params(P(_f32(adv)), P(_f32(nei_adv)), P(_f32(eps)), c_int(adv.numel()),
+                                                 P(_f32(lcf_parameters)), P(out), _lib.stream_ptr()))
+    else:
+        _lib.check(lib.b2c_lcf_meta_terms(P(_f32(adv)), P(_f32(nei_adv)), P(_f32(eps)), c_int(adv.numel()),
+                                          c_float(lcf_mean), c_float(lcf_std), P(out), _lib.stream_ptr()))
     return out
 
 

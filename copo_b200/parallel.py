@@ -20,8 +20,8 @@ def scene_offset(rank, scenes_per_rank):
 
 
 def num_minibatches(n_rows, minibatch_size, dist=None, device="cpu"):
-    """Every rank must run the same number of gradient all-reduces per epoch: the max over ranks of
-    ceil(rows / minibatch_size)."""
+    """Minibatches per epoch when every rank cuts its own `n_rows` into pieces of `minibatch_size`: the max over ranks of
+    ceil(rows / minibatch_size) (every rank must run the same number of gradient all-reduces)."""
     k = max(1, math.ceil(n_rows / max(1, minibatch_size)))
     if active(dist):
         t = torch.tensor([k], dtype=torch.int64, device=device)
@@ -31,15 +31,73 @@ def num_minibatches(n_rows, minibatch_size, dist=None, device="cpu"):
 
 
 def minibatch_bounds(n_rows, k):
-    """k contiguous [begin, end) slices covering n_rows (the last ones may be shorter, never empty if n_rows > 0)."""
-    size = max(1, math.ceil(n_rows / k))
-    return [(min(j * size, max(n_rows - 1, 0)), min((j + 1) * size, n_rows)) if j * size < n_rows else (0, min(1, n_rows))
-            for j in range(k)]
+    """k contiguous [begin, end) slices covering n_rows, sizes differing by at most one row (numpy.array_split);
+    slices are empty only when n_rows < k."""
+    base, extra = divmod(int(n_rows), int(k))
+    out, lo = [], 0
+    for j in range(k):
+        hi = lo + base + (1 if j < extra else 0)
+        out.append((lo, hi))
+        lo = hi
+    return out
 
 
-def allreduce_sum_(t, dist=None):
+def gather_row_counts(n_rows, dist=None, device="cpu"):
+    """[world] row counts of every rank (one small all-gather per training iteration)."""
+    if not active(dist):
+        return [int(n_rows)]
+    t = torch.tensor([int(n_rows)], dtype=torch.int64, device=device)
+    parts = [torch.zeros_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(parts, t)
+    return [int(p.item()) for p in parts]
+
+
+def minibatch_plan(row_counts, rank, minibatch_size):
+    """The reference cuts the WHOLE train batch (all workers' rows) into minibatches of `sgd_minibatch_size` rows
+    (rllib.utils.sgd.minibatches, called from train_one_step; algo_copo.py:555).  Data parallel: the global batch is
+    the union of the ranks' rows, k = ceil(total / minibatch_size), and rank r contributes the j-th of k near-equal
+    slices of its own (shuffled) rows to minibatch j.  Returns (this rank's k slices, the k GLOBAL minibatch sizes):
+    losses and gradients are normalised by the global size, so the all-reduced sum of the ranks' gradients is the
+    gradient of the whole-minibatch mean whatever the split."""
+    total = sum(row_counts)
+    k = max(1, math.ceil(total / max(1, int(minibatch_size))))
+    per_rank = [minibatch_bounds(n, k) for n in row_counts]
+    sizes = [sum(b[j][1] - b[j][0] for b in per_rank) for j in range(k)]
+    return per_rank[rank], sizes
+
+
+class AllReduceTimer:
+    """CUDA-event time spent inside the all-reduces of one training iteration (on the launching stream)."""
+
+    def __init__(self):
+        self.pairs, self.count = [], 0
+
+    def begin(self):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def end(self, e0):
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        self.pairs.append((e0, e1))
+        self.count += 1
+
+    def total_ms(self):
+        """Synchronises; returns (milliseconds, number of all-reduces) since the last call."""
+        torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b in self.pairs)
+        n = self.count
+        self.pairs, self.count = [], 0
+        return ms, n
+
+
+def allreduce_sum_(t, dist=None, timer=None):
     if active(dist):
+        e = timer.begin() if timer is not None and t.is_cuda else None
         dist.all_reduce(t)
+        if e is not None:
+            timer.end(e)
     return t
 
 

@@ -91,7 +91,12 @@ class IPPOPolicy:
         self.entropy_coeff = float(self.config["entropy_coeff"])
         self._optimizer = _Adam(self.model.flat, self.config["lr"])
         self.dist = dist                                 # torch.distributed module when data parallel, else None
+        self.ar_timer = None                             # parallel.AllReduceTimer when the trainer wants the share
         self.num_grad_updates = 0
+        if self.config.get("num_neighbours", 4) != 4 and self.config.get("fuse_mode") == "concat":
+            raise ValueError("fuse_mode='concat' is built for num_neighbours=4 (the reference default)")
+        if not self.config.get("use_gae", True) or not self.config.get("use_critic", True):
+            raise ValueError("use_gae=False / use_critic=False are not supported (the reference asserts use_critic)")
 
     @classmethod
     def default_config(cls):
@@ -120,11 +125,18 @@ class IPPOPolicy:
     def _adv_column(self):
         return ADVANTAGES
 
-    def loss(self, model, dist_class, train_batch):
+    def loss(self, model, dist_class, train_batch, global_rows=None):
+        """Forward + backward through the kernels; gradients land in `model.grad`.  `global_rows`: the row count the
+        means are taken over (data parallel: the GLOBAL minibatch size, so that summing the ranks' gradients and
+        losses gives the whole-minibatch mean; default: this batch's rows)."""
         cfg = dict(clip_param=self.config["clip_param"], vf_clip_param=self.config["vf_clip_param"],
                    vf_loss_coeff=self.config["vf_loss_coeff"], entropy_coeff=self.entropy_coeff,
-                   kl_coeff=self.kl_coeff)
+                   kl_coeff=self.kl_coeff, old_value_loss=self.config.get("old_value_loss", True))
         B = train_batch[OBS].shape[0]
+        rows = int(global_rows) if global_rows else B
+        if B == 0:                                   # a rank without rows in this minibatch contributes nothing
+            m = torch.zeros(8, dtype=torch.float64, device=self.device)
+            return self._fill_tower_stats(model, m, cfg, train_batch)
         pol = model.nets["policy"]
         tc = model._tc()
         # one [hi | lo] operand split per distinct input tensor (CoPO: obs is the critic input of all four networks)
@@ -145,17 +157,23 @@ class IPPOPolicy:
             head_acts.append((net_name, acts))
             heads.append((acts[3].reshape(-1), train_batch[old_col], train_batch[tgt_col]))
         dlogits, dvs, st = ops.ppo_head(acts_p[3], train_batch[ACTIONS], train_batch[ACTION_LOGP],
-                                        train_batch[ACTION_DIST_INPUTS], train_batch[self._adv_column()], heads, cfg)
+                                        train_batch[ACTION_DIST_INPUTS], train_batch[self._adv_column()], heads, cfg,
+                                        norm_rows=rows)
         pol.backward(acts_p, dlogits, tc)
         for (net_name, acts), dv in zip(head_acts, dvs):
             model.nets[net_name].backward(acts, dv.unsqueeze(1), tc)
-        m = st / B
+        return self._fill_tower_stats(model, st / rows, cfg, train_batch)
+
+    def _fill_tower_stats(self, model, m, cfg, train_batch):
         total = m[0] + cfg["vf_loss_coeff"] * (m[1] + m[2] + m[3]) - cfg["entropy_coeff"] * m[4] + cfg["kl_coeff"] * m[5]
         ts = model.tower_stats
         ts["total_loss"], ts["mean_policy_loss"], ts["mean_vf_loss"] = total, m[0], m[1]
         ts["mean_entropy"], ts["mean_kl_loss"] = m[4], m[5]
         ts["vf_explained_var"] = torch.zeros((), device=self.device)
         self._extra_tower_stats(model, m, train_batch)
+        # the same numbers as one device vector (the trainer accumulates these without a host sync per minibatch):
+        # total, policy, vf, nei vf, global vf, entropy, kl, mean logp
+        self.stats_vector = torch.stack([total, m[0], m[1], m[2], m[3], m[4], m[5], m[6]])
         return total
 
     compute_loss = loss                                  # BASELINE.json's name for the same hook
@@ -163,15 +181,25 @@ class IPPOPolicy:
     def _extra_tower_stats(self, model, m, train_batch):
         pass
 
-    def learn_on_batch(self, train_batch):
-        """zero grads -> loss fwd+bwd -> (all-reduce) -> Adam.  Returns the stats dict of this minibatch."""
-        self.model.zero_grad()
-        self.loss(self.model, None, train_batch)
-        scale = 1.0
+    def _global_rows(self, B, global_rows):
+        """Rows of the global minibatch: given by the trainer's plan, else summed over the ranks here."""
+        if global_rows:
+            return int(global_rows)
         if parallel.active(self.dist):
-            parallel.allreduce_sum_(self.model.grad, self.dist)      # one NCCL all-reduce of the flat gradient
-            scale = 1.0 / self.dist.get_world_size()                 # the mean is folded into the Adam kernel
-        self._optimizer.apply(self.model.grad, grad_scale=scale)
+            t = torch.tensor([B], dtype=torch.int64, device=self.device)
+            self.dist.all_reduce(t)
+            return int(t.item())
+        return B
+
+    def learn_on_batch(self, train_batch, global_rows=None):
+        """zero grads -> loss fwd+bwd -> (all-reduce) -> Adam.  Returns the stats dict of this minibatch.  Data
+        parallel: every rank's loss is normalised by the GLOBAL minibatch row count, so the all-reduced SUM of the
+        gradients is the gradient of the whole-minibatch mean (ranks may hold different numbers of rows)."""
+        rows = self._global_rows(train_batch[OBS].shape[0], global_rows)
+        self.model.zero_grad()
+        self.loss(self.model, None, train_batch, global_rows=rows)
+        parallel.allreduce_sum_(self.model.grad, self.dist, self.ar_timer)  # one NCCL all-reduce of the flat gradient
+        self._optimizer.apply(self.model.grad)
         self.model.mark_weights_changed()
         self.num_grad_updates += 1
         return dict(self.model.tower_stats)
@@ -224,7 +252,7 @@ class IPPOPolicy:
         return ro
 
     def _allreduce_stats(self, st):
-        return parallel.allreduce_sum_(st, self.dist)
+        return parallel.allreduce_sum_(st, self.dist, self.ar_timer)
 
 
 class CCPPOPolicy(IPPOPolicy):
@@ -329,32 +357,40 @@ class CoPOPolicy(CCPPOPolicy):
         return ro
 
     # ---- meta-gradient (a18) -------------------------------------------------------------------------------
-    def _policy_grad(self, model, batch, mode, adv):
+    def _policy_grad(self, model, batch, mode, adv, rows, out):
+        """Gradient of the policy network only, into `out` (this rank's share of the global-minibatch mean)."""
         cfg = dict(clip_param=self.config["clip_param"], vf_clip_param=0.0, vf_loss_coeff=0.0, entropy_coeff=0.0,
                    kl_coeff=0.0)
         pol = model.nets["policy"]
-        acts = pol.forward_train(batch[OBS], model._tc())
         model.grad[model.policy_slice()].zero_()
-        dlogits, _, st = ops.ppo_head(acts[3], batch[ACTIONS], batch[ACTION_LOGP], None, adv, [], cfg, mode=mode)
-        pol.backward(acts, dlogits, model._tc())
-        g = model.grad[model.policy_slice()].clone()
-        parallel.allreduce_mean_(g, self.dist)           # reduce the gradient vectors BEFORE the dot (bilinear)
-        return g, st
+        st = torch.zeros(8, dtype=torch.float64, device=self.device)
+        if batch[OBS].shape[0] > 0:
+            acts = pol.forward_train(batch[OBS], model._tc())
+            dlogits, _, st = ops.ppo_head(acts[3], batch[ACTIONS], batch[ACTION_LOGP], None, adv, [], cfg, mode=mode,
+                                          norm_rows=rows, stats=st)
+            pol.backward(acts, dlogits, model._tc())
+        out.copy_(model.grad[model.policy_slice()])
+        return st
 
-    def meta_update(self, train_batch, eps=None):
+    def meta_update(self, train_batch, eps=None, global_rows=None):
         B = train_batch[OBS].shape[0]
-        g_new, st_new = self._policy_grad(self.model, train_batch, 0, train_batch[GLOBAL_ADVANTAGES])
-        g_old, st_old = self._policy_grad(self.target_model, train_batch, 1, None)
+        rows = self._global_rows(B, global_rows)
+        n = self.model.policy_slice().stop - self.model.policy_slice().start
+        if getattr(self, "_meta_g", None) is None:
+            self._meta_g = torch.empty(2 * n, dtype=torch.float32, device=self.device)
+        g_new, g_old = self._meta_g[:n], self._meta_g[n:]
+        st_new = self._policy_grad(self.model, train_batch, 0, train_batch[GLOBAL_ADVANTAGES], rows, g_new)
+        st_old = self._policy_grad(self.target_model, train_batch, 1, None, rows, g_old)
+        # reduce BOTH gradient vectors (one all-reduce) BEFORE the dot product: it is bilinear
+        parallel.allreduce_sum_(self._meta_g, self.dist, self.ar_timer)
         grad_value = ops.dot(g_new, g_old)[0]
         if eps is None:
             eps = torch.randn(B, dtype=torch.float32, device=self.device)
-        mean_t, std_t = self.model.lcf_mean, self.model.lcf_std
-        mean, std = float(mean_t), float(std_t)
-        terms = ops.lcf_meta_terms(train_batch[ADVANTAGES], train_batch[NEI_ADVANTAGE], eps, mean, std)
+        std_t = self.model.lcf_std
+        terms = ops.lcf_meta_terms(train_batch[ADVANTAGES], train_batch[NEI_ADVANTAGE], eps,
+                                   lcf_parameters=self.model.lcf_parameters)
         # ranks can hold minibatches of different sizes: reduce the sums together with the row count
-        terms = self._allreduce_stats(torch.cat([terms, torch.tensor([float(B)], dtype=torch.float64,
-                                                                      device=self.device)]))
-        terms = terms[:3] / terms[3]
+        terms = self._allreduce_stats(torch.cat([terms, st_new[:1], st_old[6:7]])) / rows
         coordinated_mean = terms[0]
         lcf_adv_loss = (coordinated_mean - self._raw_lcf_adv_mean) / self._raw_lcf_adv_std
         p = self.model.lcf_parameters
@@ -365,12 +401,18 @@ class CoPOPolicy(CCPPOPolicy):
         self.model.lcf_grad.copy_((grad_value * dl).to(torch.float32))
         final = grad_value * lcf_adv_loss
         self._lcf_optimizer.apply(self.model.lcf_grad)
-        return dict(new_policy_ego_loss=float(st_new[0]) / B, old_policy_logp_loss=float(st_old[6]) / B,
-                    lcf_lcf_adv_loss=float(lcf_adv_loss), lcf_final_loss=float(final), grad_value=float(grad_value),
-                    lcf=float(self.model.lcf_mean), lcf_deg=float(self.model.lcf_mean) * 90,
-                    lcf_param=float(self.model.lcf_parameters[0]), coordinated_adv=float(coordinated_mean),
-                    global_adv=float(train_batch[GLOBAL_ADVANTAGES].mean()), lcf_std=float(self.model.lcf_std),
-                    lcf_std_deg=float(self.model.lcf_std) * 90, lcf_std_param=float(self.model.lcf_parameters[1]))
+        lm, ls, lp = self.model.lcf_mean, self.model.lcf_std, self.model.lcf_parameters
+        ga = train_batch[GLOBAL_ADVANTAGES].mean() if B > 0 else torch.zeros((), device=self.device)
+        keys = ("new_policy_ego_loss", "old_policy_logp_loss", "lcf_lcf_adv_loss", "lcf_final_loss", "grad_value", "lcf",
+                "lcf_deg", "lcf_param", "coordinated_adv", "global_adv", "lcf_std", "lcf_std_deg", "lcf_std_param")
+        vec = torch.stack([t.to(torch.float64) for t in (terms[3], terms[4], lcf_adv_loss, final, grad_value, lm, lm * 90,
+                                                         lp[0], coordinated_mean, ga, ls, ls * 90, lp[1])])
+        self.meta_stats_keys, self.meta_stats_vector = keys, vec          # device copy (no host sync) for the trainer
+        if not self.sync_stats:
+            return {}
+        return dict(zip(keys, vec.tolist()))                              # one device -> host read
+
+    sync_stats = True      # False: meta_update leaves its statistics on the device (meta_stats_vector) and returns {}
 
     def update_old_policy(self):
         self.target_model.flat.copy_(self.model.flat)

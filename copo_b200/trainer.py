@@ -69,6 +69,8 @@ class IPPOTrainer:
                                     delay_done=ec.get("delay_done", 25), device=self.device)
         self.env = env
         self.policy = self.policy_cls(env.D, 2, cfg, device=self.device, dist=dist)
+        if dist is not None and self.world > 1:
+            self.policy.ar_timer = parallel.AllReduceTimer()
         self._counters = {"num_env_steps_sampled": 0, "num_agent_steps_sampled": 0}
         self._timers = {}
         self._iteration = 0
@@ -153,14 +155,13 @@ class IPPOTrainer:
         valid = torch.nonzero(ro["flags"].reshape(R) & FLAG_VALID).reshape(-1)
         return cols, scal, wide, valid
 
-    def _num_minibatches(self, n_valid, mb):
-        return parallel.num_minibatches(n_valid, mb, _dist(), self.device)
-
     def _minibatches(self, cols, scal, wide, valid, mb):
-        """Shuffled minibatches over the valid rows (rllib.utils.sgd.minibatches)."""
-        k = self._num_minibatches(valid.numel(), mb)
+        """Shuffled minibatches over the valid rows (rllib.utils.sgd.minibatches).  Yields (batch, global_rows): with
+        more than one rank the GLOBAL train batch is cut into ceil(total / mb) minibatches and every rank contributes
+        a near-equal slice of its own shuffled rows to each (parallel.minibatch_plan)."""
+        bounds, sizes = parallel.minibatch_plan(self._row_counts, self.rank, mb)
         perm = valid[torch.randperm(valid.numel(), device=self.device)]
-        for lo, hi in parallel.minibatch_bounds(valid.numel(), k):
+        for (lo, hi), rows in zip(bounds, sizes):
             idx = perm[lo:hi].contiguous()
             batch = {c: ops.gather_rows(w, idx) for c, w in wide.items()}
             if P.CENTRALIZED_CRITIC_OBS not in batch:
@@ -168,19 +169,33 @@ class IPPOTrainer:
             s = ops.gather_rows(scal, idx)
             for n, c in enumerate(cols):
                 batch[c] = s[:, n].contiguous()
-            yield batch
+            yield batch, rows
 
     # ---- one training iteration ------------------------------------------------------------------------------
+    LEARNER_KEYS = ("total_loss", "policy_loss", "vf_loss", "mean_nei_vf_loss", "mean_global_vf_loss", "entropy", "kl",
+                    "mean_logp")
+
     def _learn(self, ro):
         cols, scal, wide, valid = self._flatten(ro)
-        stats, n = {}, 0
+        self._row_counts = parallel.gather_row_counts(valid.numel(), _dist(), self.device)
+        acc, n = torch.zeros(len(self.LEARNER_KEYS), dtype=torch.float64, device=self.device), 0
         for _ in range(int(self.config["num_sgd_iter"])):
-            for batch in self._minibatches(cols, scal, wide, valid, int(self.config["sgd_minibatch_size"])):
-                self.policy.learn_on_batch(batch)
-                for k, v in self.policy.extra_grad_info().items():
-                    stats[k] = stats.get(k, 0.0) + v
+            for batch, rows in self._minibatches(cols, scal, wide, valid, int(self.config["sgd_minibatch_size"])):
+                self.policy.learn_on_batch(batch, global_rows=rows)
+                acc += self.policy.stats_vector          # stays on the device: no host sync per minibatch
                 n += 1
-        return {k: v / max(n, 1) for k, v in stats.items()}, (cols, scal, wide, valid)
+        # every rank holds its share of each global-minibatch mean: the all-reduced sum is the learner statistic of
+        # the whole batch, identical on every rank (so is the KL coefficient derived from it)
+        acc = parallel.allreduce_sum_(acc / max(n, 1), _dist(), self.policy.ar_timer)
+        stats = dict(zip(self.LEARNER_KEYS, acc.tolist()))
+        pol = self.policy
+        stats.update(cur_kl_coeff=pol.kl_coeff, cur_lr=pol.config["lr"], entropy_coeff=pol.entropy_coeff,
+                     vf_explained_var=0.0)
+        if pol.algo == "copo":
+            stats.update(lcf=float(pol.model.lcf_mean), lcf_std=float(pol.model.lcf_std))
+        else:
+            stats.pop("mean_nei_vf_loss"), stats.pop("mean_global_vf_loss")
+        return stats, (cols, scal, wide, valid)
 
     def _episode_metrics(self, ro):
         f = ro["flags"]
@@ -205,12 +220,15 @@ class IPPOTrainer:
         t2 = time.perf_counter()
         results = {"default": {"learner_stats": learner_stats, "custom_metrics": {}}}
         self._after_sgd(ro, flat, results)
-        self.policy.update_kl(learner_stats["kl"])
+        self.policy.update_kl(learner_stats["kl"])       # the all-reduced mean KL: the same coefficient on every rank
         metrics = self._episode_metrics(ro)
         self._counters["num_env_steps_sampled"] += self.T * self.env.S
         self._counters["num_agent_steps_sampled"] += metrics["agent_steps"]
         self._timers = {"sample_time_ms": (t1 - t0) * 1e3, "learn_time_ms": (t2 - t1) * 1e3,
                         "sample_throughput": metrics["agent_steps"] / max(t1 - t0, 1e-9)}
+        if self.policy.ar_timer is not None:
+            ms, cnt = self.policy.ar_timer.total_ms()
+            self._timers.update(allreduce_ms=ms, allreduces=cnt)
         results["default"]["custom_metrics"].update(metrics)
         self._iteration += 1
         return results
@@ -245,14 +263,21 @@ class CoPOTrainer(CCPPOTrainer):
         cols, scal, wide, valid = flat
         pol = self.policy
         mb = int(self.config["lcf_sgd_minibatch_size"] or self.config["sgd_minibatch_size"])
-        rec, ret = {}, {}
-        for _ in range(int(self.config["lcf_num_iters"])):
-            for batch in self._minibatches(cols, scal, wide, valid, mb):
-                ret = pol.meta_update(batch)
-                for k, v in ret.items():
-                    rec.setdefault(k, []).append(v)
-        avg = {k: sum(v) / len(v) for k, v in rec.items() if k not in ("lcf", "lcf_std")}
-        last = {k: v for k, v in ret.items() if k in ("lcf", "lcf_std")}
+        acc, n = None, 0
+        pol.sync_stats = False                           # meta_update leaves its statistics on the device
+        try:
+            for _ in range(int(self.config["lcf_num_iters"])):
+                for batch, rows in self._minibatches(cols, scal, wide, valid, mb):
+                    pol.meta_update(batch, global_rows=rows)
+                    acc = pol.meta_stats_vector.clone() if acc is None else acc + pol.meta_stats_vector
+                    n += 1
+        finally:
+            pol.sync_stats = True
+        avg, last = {}, {}
+        if n:
+            mean_v, last_v = (acc / n).tolist(), pol.meta_stats_vector.tolist()
+            avg = {k: v for k, v in zip(pol.meta_stats_keys, mean_v) if k not in ("lcf", "lcf_std")}
+            last = {k: v for k, v in zip(pol.meta_stats_keys, last_v) if k in ("lcf", "lcf_std")}
         lcf_mean, lcf_std = float(pol.model.lcf_mean), float(pol.model.lcf_std)
         pol.assign_lcf(pol.model.lcf_parameters.clone(), lcf_mean, lcf_std)
         pol.update_old_policy()

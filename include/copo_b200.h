@@ -138,7 +138,8 @@ int b2c_gaussian_sample(const float* logits, const float* eps_in, float* actions
 /* Per-row forward + backward of the PPO objective (mode 0) or of mean(logp) (mode 1, the theta_old term of
  * CoPOPolicy.meta_update, algo_copo.py:265-272).  Gradients are those of
  *   mean(-surr + vf_loss_coeff * sum_h vf_loss_h - entropy_coeff * H) + kl_coeff * mean(KL(old || new))
- * with the clipped "old" value loss (algo_copo.py:360-367), including autograd's tie rule for min / max.
+ * with the clipped "old" value loss (algo_copo.py:360-367; or the plain clamped one, see plain_value_loss), including
+ * autograd's tie rule for min / max.
  * stats[8] (+=): sum(-surr), sum vf_loss[0..2], sum entropy, sum KL, sum logp, rows. */
 typedef struct {
     const float* logits;          /* [rows][4] current policy output */
@@ -154,6 +155,11 @@ typedef struct {
     double* stats;                /* [8] accumulated, may be NULL */
     int32_t rows, n_heads, mode;
     float clip_param, vf_clip_param, vf_loss_coeff, entropy_coeff, kl_coeff;
+    int32_t norm_rows;            /* rows the means are taken over; 0 = `rows`.  Data parallel: the GLOBAL minibatch row
+                                     count, so that the all-reduced SUM of the ranks' gradients is the gradient of the
+                                     whole-minibatch mean even when ranks hold different numbers of rows */
+    int32_t plain_value_loss;     /* 1: old_value_loss=False, vf_loss = clamp((v - target)^2, 0, vf_clip_param)
+                                     (algo_ippo.py:146-148, algo_copo.py:358-363) */
 } b2c_ppo_head_args;
 int b2c_ppo_head(const b2c_ppo_head_args* args, void* stream);
 
@@ -162,6 +168,10 @@ int b2c_ppo_head(const b2c_ppo_head_args* args, void* stream);
  * sum d, sum d * eps },  d = (-sin(phi) adv + cos(phi) nei) * pi/2. */
 int b2c_lcf_meta_terms(const float* adv, const float* nei_adv, const float* eps, int rows, float lcf_mean, float lcf_std,
                        double* out3, void* stream);
+/* same, reading the model's raw lcf_parameters[2] on the DEVICE (lcf_mean = clamp(tanh(p0)), lcf_std = exp(clamp(p1)),
+ * algo_copo.py:171-177): no host read of the current LCF between meta-update minibatches */
+int b2c_lcf_meta_terms_params(const float* adv, const float* nei_adv, const float* eps, int rows,
+                              const float* lcf_parameters, double* out3, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Rollout bookkeeping over time-major [T][N] columns (N = scenes x slots); flags are the B2C_FLAG_* bytes the

@@ -90,7 +90,9 @@ class SimConfig:
 class OracleSim:
     """S scenes x A slots, numpy float32, vectorised over scenes."""
 
-    def __init__(self, tables, num_scenes, num_slots, cfg: SimConfig, scene_offset=0):
+    def __init__(self, tables, num_scenes, num_slots, cfg: SimConfig, scene_offset=0, scene_ids=None):
+        """scene_ids: optional explicit global scene indices (replaying sampled scenes of a larger batch: scenes are
+        independent and only keyed by their global index through the RNG stream)."""
         self.m = tables
         self.S, self.A = int(num_scenes), int(num_slots)
         self.cfg = cfg
@@ -109,6 +111,8 @@ class OracleSim:
         self.rng_ctr = np.zeros(S, np.int32)
         self.agent_steps = np.zeros(S, np.int32)          # running count of agent-env-steps (metric counter)
         self.scene_id = (np.arange(S) + scene_offset).astype(np.int64)
+        if scene_ids is not None:
+            self.scene_id = np.asarray(scene_ids, dtype=np.int64).reshape(S)
         self.obs_dim = tables.base_obs_dim + (1 if cfg.append_lcf else 0)
 
     # ------------------------------------------------------------------------------------------

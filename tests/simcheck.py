@@ -99,6 +99,25 @@ def compare_state(sim, st, tag=""):
                                                                                b[tuple(idx)]))
 
 
+def compare_tiles(a, b, tag=""):
+    """Two unpacked state dicts (unpack_tiles) of the same batch: headers, status and - for present vehicles - every
+    field, bit for bit."""
+    present = (a["status"] == osim.ACTIVE) | (a["status"] == osim.LINGER)
+    for name in a:
+        x, y = a[name], b[name]
+        if x.dtype == np.float32:
+            ok = (x.view(np.uint32) == y.view(np.uint32)) | (x == y)
+        else:
+            ok = x == y
+        if name == "linger":
+            ok = ok | (a["status"] != osim.LINGER)
+        elif name not in HDR and name != "status":
+            ok = ok | ~present
+        if not np.all(ok):
+            idx = np.argwhere(~ok)[0]
+            raise AssertionError("%s state %s differs at %s: %r vs %r" % (tag, name, tuple(idx), x[tuple(idx)], y[tuple(idx)]))
+
+
 def make_cfg_c(cfg, S, A, D, do_reset=0, new_episode=0, scene_offset=0):
     c = EnvConfigC()
     c.S, c.A, c.AP, c.D = S, A, (A + 3) // 4 * 4, D

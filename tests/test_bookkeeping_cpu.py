@@ -231,6 +231,26 @@ def test_adam_and_kl_controller():
     assert om.update_kl(0.2, 0.01) == 0.2
 
 
+def test_product_kl_controller():
+    """IPPOPolicy.update_kl (the product's, not the oracle's) is rllib 2.2.0's KLCoeffMixin rule (called at
+    algo_copo.py:631-632): x1.5 above 2 x kl_target, x0.5 below 0.5 x kl_target; inclusive edges leave it alone.
+    The shipped training log shows the rule at work: cur_kl_coeff = 0.675 = 0.2 x 1.5^3."""
+    from types import SimpleNamespace
+    from copo_b200 import policy as P
+    pol = SimpleNamespace(config=P.ippo_config(), kl_coeff=0.2)
+    up = lambda kl: P.IPPOPolicy.update_kl(pol, kl)
+    assert up(0.03) == pytest.approx(0.3) and pol.kl_coeff == pytest.approx(0.3)
+    assert up(0.004) == pytest.approx(0.15)
+    assert up(0.01) == pytest.approx(0.15) and up(0.02) == pytest.approx(0.15) and up(0.005) == pytest.approx(0.15)
+    pol.kl_coeff = 0.2
+    for _ in range(3):
+        up(1.0)
+    assert pol.kl_coeff == pytest.approx(0.675)
+    for kl in (0.0, 0.0049, 0.0051, 0.0199, 0.0201, 5.0):
+        pol.kl_coeff = 0.2
+        assert up(kl) == pytest.approx(om.update_kl(0.2, kl))
+
+
 REF_CKPT = "/root/reference/copo_code/copo/best_checkpoints"
 
 

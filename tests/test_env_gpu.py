@@ -119,6 +119,59 @@ def test_env_full_size_properties(map_name, S, A):
         assert torch.equal(o[k], o2[k]), k
 
 
+def _sampled_scenes(S, A, n_random=6):
+    """first / last scenes, the scenes either side of CTA-group edges (the state kernel packs 128 // A scenes per CTA,
+    the last group can be ragged), and a few random ones"""
+    g = max(1, 128 // A)
+    last_group = (S - 1) // g * g
+    pick = {0, 1, g - 1, g, 2 * g - 1, S // 2, last_group - 1, last_group, S - 2, S - 1}
+    pick |= set(int(k) for k in np.random.default_rng(S + A).integers(0, S, n_random))
+    return sorted(k for k in pick if 0 <= k < S)
+
+
+@pytest.mark.parametrize("map_name,S,A,offset", [
+    ("intersection", 4096, 40, 0),        # C2 (BASELINE.json configs[1])
+    ("roundabout", 4096, 40, 0),          # C3
+    ("tollgate", 1024, 40, 3 * 1024),     # C4: 8192 scenes over 8 GPUs, the shard of rank 3
+    ("parking_lot", 4096, 10, 7 * 4096),  # C5: 32768 scenes over 8 GPUs, the shard of rank 7 (fused kernel)
+])
+def test_env_full_size_oracle_parity(map_name, S, A, offset):
+    """Per-GPU batches of BASELINE.json's configurations, bit for bit: sampled scenes of the full-size run are replayed
+    by the numpy oracle (scenes are independent and keyed by their global index), and EVERY scene is compared with the
+    host build of the phases (tests/hostsim), every output, every step."""
+    from copo_b200.batched_env import BatchedDrivingEnv
+    T = 70
+    tables = build_map(map_name)
+    cfg = osim.SimConfig(seed=5, horizon=60)              # scene restarts inside the run
+    cfg.num_agents = A
+    pick = _sampled_scenes(S, A)
+    ref = osim.OracleSim(tables, len(pick), A, cfg, scene_ids=[offset + k for k in pick])
+    host = sc.HostSim(tables, S, A, cfg, scene_offset=offset)
+    env = BatchedDrivingEnv(map_name, num_scenes=S, num_slots=A, num_agents=A, seed=5, horizon=60, scene_offset=offset)
+    r = ref.reset()
+    h = host.reset()
+    g = _to_np(env.reset())
+    sc.compare_outputs(h, g, "%s reset (host build, all scenes)" % map_name)
+    sc.compare_outputs(r, {k: v[pick] for k, v in g.items()}, "%s reset (oracle, sampled scenes)" % map_name)
+    rng = np.random.default_rng(3)
+    seen = dict(crash=0, spawn=0, done=0)
+    for t in range(T):
+        act = _policy(g["obs"], rng, S, A)
+        r = ref.step(act[pick])
+        h = host.step(act)
+        g = _to_np(env.step(torch.from_numpy(act).cuda()))
+        sc.compare_outputs(h, g, "%s step %d (host build, all scenes)" % (map_name, t))
+        sc.compare_outputs(r, {k: v[pick] for k, v in g.items()}, "%s step %d (oracle, sampled scenes)" % (map_name, t))
+        seen["crash"] += int(((r["flags"] & osim.F_CRASH) > 0).sum())
+        seen["spawn"] += int(((r["flags"] & osim.F_SPAWNED) > 0).sum())
+        seen["done"] += int(r["scene_done"].sum())
+    st = sc.unpack_tiles(env.get_state(), S, A)
+    sc.compare_state(ref, {k: v[pick] for k, v in st.items()}, "%s final state (oracle)" % map_name)
+    sc.compare_tiles(host.state(), st, "%s final state (host build, all scenes)" % map_name)
+    env.close()
+    assert seen["spawn"] > 0 and seen["done"] == len(pick), seen       # respawns and one restart per sampled scene
+
+
 @pytest.mark.parametrize("split", [0, 1])
 def test_env_emits_the_policy_operand(split, monkeypatch):
     """`obs_split` equals the [hi | lo] bf16 split of `obs` (bit for bit) - the env saves the policy a pass."""

@@ -306,6 +306,58 @@ def test_loss_and_gradients_match_oracle(algo, B, precision):
               ref.state_dict()["_hidden_layers.0._model.0.weight"], 1e-5, 2e-6)
 
 
+@pytest.mark.parametrize("algo", ["copo", "ippo"])
+def test_plain_value_loss_branch(algo):
+    """old_value_loss=False: vf_loss = clamp((v - target)^2, 0, vf_clip_param) (algo_ippo.py:146-148,
+    algo_copo.py:358-363) - loss and gradients against the torch-CPU oracle."""
+    from copo_b200 import policy as P
+    D, B = 92, 900
+    cls = {"copo": P.CoPOPolicy, "ippo": P.IPPOPolicy}[algo]
+    cfg = cls.default_config()
+    cfg.update(fuse_mode="none", precision="fp32", vf_clip_param=1.5, old_value_loss=False)
+    pol = cls(D, 2, cfg)
+    batch = _copo_batch(B, D, 4)
+    batch["centralized_critic_obs"] = batch["obs"]
+    ref = _oracle_model_from(pol.model, om.CoPOModel if algo == "copo" else om.CCModel)
+    ocfg = dict(om.DEFAULT_CFG, vf_clip_param=1.5, old_value_loss=False)
+    total, st = om.ppo_loss(ref, batch, ocfg, algo)
+    total.backward()
+    pol.model.zero_grad()
+    got = pol.loss(pol.model, None, {k: v.cuda() for k, v in batch.items()})
+    close(got, total, 2e-5, 1e-6)
+    close(pol.model.tower_stats["mean_vf_loss"], st["mean_vf_loss"], 1e-5, 1e-6)
+    assert float(st["mean_vf_loss"]) < 1.5 - 1e-3          # some rows are clamped, some are not
+    want_g = _flat_grad(pol.model, ref)
+    close(pol.model.grad, want_g, 2e-4, 2e-5 * float(want_g.abs().max()))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16_split"])
+def test_global_rows_normalisation_sums_to_the_whole_batch_gradient(precision):
+    """Data-parallel rule: each rank normalises by the GLOBAL minibatch row count; the sum of the ranks' gradients,
+    losses and KL is then the whole-minibatch mean even when the ranks hold different numbers of rows (here: one
+    process plays both ranks, 700 + 1348 rows, plus an empty share)."""
+    from copo_b200 import policy as P
+    D, B = 92, 2048
+    cfg = P.copo_config(precision=precision)
+    pol = P.CoPOPolicy(D, 2, cfg)
+    pol.kl_coeff = 0.3
+    batch = {k: v.cuda() for k, v in _copo_batch(B, D, 6).items()}
+    pol.model.zero_grad()
+    whole = pol.loss(pol.model, None, batch).clone()
+    g_whole, v_whole = pol.model.grad.clone(), pol.stats_vector.clone()
+    g_sum, l_sum, v_sum = torch.zeros_like(g_whole), 0.0, torch.zeros_like(v_whole)
+    for lo, hi in ((0, 700), (700, 2048), (2048, 2048)):
+        pol.model.zero_grad()
+        part = {k: v[lo:hi].contiguous() for k, v in batch.items()}
+        l_sum = l_sum + pol.loss(pol.model, None, part, global_rows=B)
+        g_sum += pol.model.grad
+        v_sum += pol.stats_vector
+    k = 1.0 if precision == "fp32" else 20.0
+    close(l_sum, whole, 1e-6 * k, 1e-7 * k)
+    close(v_sum, v_whole, 1e-6 * k, 1e-7 * k)
+    close(g_sum, g_whole, 1e-4 * k, 1e-6 * k * float(g_whole.abs().max()))
+
+
 @pytest.mark.parametrize("precision", ["fp32", "bf16_split"])
 def test_meta_update_matches_oracle(precision):
     from copo_b200 import policy as P

@@ -27,6 +27,53 @@ def _worker(rank, world, port, q):
     rows = [1000, 3000][rank]
     out["k"] = parallel.num_minibatches(rows, 512, dist)
     out["bounds_ok"] = all(hi > lo for lo, hi in parallel.minibatch_bounds(rows, out["k"]))
+    # 1b. the global minibatch plan: ranks with unequal row counts; the gradient of the whole-minibatch mean loss is the
+    # all-reduced SUM of per-rank gradients when every rank normalises by the GLOBAL minibatch size (and the learner
+    # statistic / KL that drives update_kl is the same on every rank)
+    counts = parallel.gather_row_counts([30, 70][rank], dist)
+    bounds, sizes = parallel.minibatch_plan(counts, rank, 32)
+    out["counts"], out["sizes"], out["bounds"] = counts, sizes, bounds
+    torch.manual_seed(0)
+    net = om.CoPOModel(10, hiddens=(8, 8)).double()
+    gen = torch.Generator().manual_seed(5)
+    R = 100
+    full = dict(obs=torch.rand(R, 10, generator=gen, dtype=torch.float64),
+                actions=torch.randn(R, 2, generator=gen, dtype=torch.float64),
+                action_logp=-2 + 0.1 * torch.randn(R, generator=gen, dtype=torch.float64),
+                action_dist_inputs=0.1 * torch.randn(R, 4, generator=gen, dtype=torch.float64))
+    for kcol in ("advantages", "normalized_advantages", "vf_preds", "value_targets", "nei_values", "nei_target",
+                 "global_values", "global_target", "nei_advantage", "global_advantages"):
+        full[kcol] = torch.randn(R, generator=gen, dtype=torch.float64)
+    full["centralized_critic_obs"] = full["obs"]
+    mine = {k: (v[:30] if rank == 0 else v[30:]) for k, v in full.items()}
+    grads, kls = [], []
+    for j, ((lo, hi), rows) in enumerate(zip(bounds, sizes)):
+        net.zero_grad()
+        kl = torch.zeros(1, dtype=torch.float64)
+        if hi > lo:
+            part = {k: v[lo:hi] for k, v in mine.items()}
+            loss, st = om.ppo_loss(net, part, dict(om.DEFAULT_CFG), "copo")
+            (loss * (hi - lo) / rows).backward()                  # this rank's share of the global-minibatch mean
+            kl = (st["mean_kl_loss"].detach() * (hi - lo) / rows).reshape(1)
+        g = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in net.parameters()])
+        parallel.allreduce_sum_(g, dist)
+        parallel.allreduce_sum_(kl, dist)
+        grads.append(g)
+        kls.append(float(kl))
+    # single-process reference over the same global minibatches (rank 0 rows then rank 1 rows of each slice)
+    all_bounds = [parallel.minibatch_bounds(n, len(sizes)) for n in counts]
+    err = 0.0
+    for j in range(len(sizes)):
+        idx = list(range(all_bounds[0][j][0], all_bounds[0][j][1])) + [30 + r for r in range(all_bounds[1][j][0],
+                                                                                               all_bounds[1][j][1])]
+        net.zero_grad()
+        part = {k: v[idx] for k, v in full.items()}
+        loss, st = om.ppo_loss(net, part, dict(om.DEFAULT_CFG), "copo")
+        loss.backward()
+        g = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in net.parameters()])
+        err = max(err, float((g - grads[j]).abs().max()) / (float(g.abs().max()) + 1e-30),
+                  abs(float(st["mean_kl_loss"].detach()) - kls[j]))
+    out["dp_grad_err"] = err
     # 2. whole-batch statistics from per-rank partial sums (algo_copo.py:547-551 needs the global mean / std)
     rng = np.random.default_rng(0)
     x = rng.normal(1.5, 2.0, 4000).astype(np.float32)
@@ -79,6 +126,9 @@ def test_world_size_two_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res[0]["k"] == res[1]["k"] == 6 and res[0]["bounds_ok"] and res[1]["bounds_ok"]
+    assert res[0]["counts"] == res[1]["counts"] == [30, 70] and res[0]["sizes"] == res[1]["sizes"] == [26, 26, 24, 24]
+    assert res[0]["bounds"] == [(0, 8), (8, 16), (16, 23), (23, 30)]
+    assert res[0]["dp_grad_err"] < 1e-12 and res[1]["dp_grad_err"] < 1e-12
     for r in (0, 1):
         assert np.allclose(res[r]["mean_std"], res[r]["want_mean_std"], rtol=1e-6)
         assert abs(res[r]["grad_value"] - res[r]["want_grad_value"]) < 1e-12 + 1e-9 * abs(res[r]["want_grad_value"])
@@ -90,8 +140,11 @@ def test_single_process_helpers():
     assert not parallel.active(None)
     assert parallel.num_minibatches(0, 512) == 1 and parallel.num_minibatches(1025, 512) == 3
     b = parallel.minibatch_bounds(10, 3)
-    assert b == [(0, 4), (4, 8), (8, 10)]
-    assert parallel.minibatch_bounds(2, 4)[0] == (0, 1) and all(hi > lo for lo, hi in parallel.minibatch_bounds(2, 4))
+    assert b == [(0, 4), (4, 7), (7, 10)]
+    assert parallel.minibatch_bounds(2, 4) == [(0, 1), (1, 2), (2, 2), (2, 2)]      # empty slices only when rows < k
+    assert parallel.minibatch_plan([10], 0, 4) == ([(0, 4), (4, 7), (7, 10)], [4, 3, 3])
+    assert parallel.minibatch_plan([0, 5], 0, 512) == ([(0, 0)], [5])
+    assert parallel.gather_row_counts(7) == [7]
     t = torch.ones(3)
     assert parallel.allreduce_mean_(t) is t
 

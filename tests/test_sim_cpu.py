@@ -253,3 +253,29 @@ def test_laser_ownership_formula():
                 want = int(np.searchsorted(excl[:n_live], r, side="right")) - 1
                 assert lo == want and excl[lo] <= r < excl[lo] + cnt[lo], (trial, r0, lane)
             before += bin(starts).count("1")
+
+
+def test_sampled_scenes_of_a_large_batch_replay_in_the_oracle():
+    """Scenes are independent and keyed by their global index: an oracle built over a few `scene_ids` reproduces
+    exactly those scenes of a larger (offset) batch - the mechanism the full-size GPU parity test relies on."""
+    name, S, A, offset = "intersection", 40, 40, 3 * 1024
+    tables = build_map(name)
+    cfg = osim.SimConfig(seed=5, horizon=30)
+    cfg.num_agents = A
+    pick = [0, 2, 3, 17, 38, 39]
+    ref = osim.OracleSim(tables, len(pick), A, cfg, scene_ids=[offset + k for k in pick])
+    host = sc.HostSim(tables, S, A, cfg, scene_offset=offset)
+    r, g = ref.reset(), host.reset()
+    sc.compare_outputs(r, {k: v[pick] for k, v in g.items()}, "reset")
+    rng = np.random.default_rng(3)
+    done = 0
+    for t in range(36):
+        act = rng.uniform(-1, 1, (S, A, 2)).astype(np.float32)
+        act[..., 0] *= 0.3
+        r, g = ref.step(act[pick]), host.step(act)
+        sc.compare_outputs(r, {k: v[pick] for k, v in g.items()}, "step %d" % t)
+        done += int(r["scene_done"].sum())
+    st = host.state()
+    sc.compare_state(ref, {k: v[pick] for k, v in st.items()}, "final")
+    sc.compare_tiles(st, st)
+    assert done == len(pick)
