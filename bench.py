@@ -323,6 +323,9 @@ def run_gpu(args):
     for r in range(RING):
         o = env.alloc_outputs()
         o["obs"] = obs[r + 1].view(S, A, D)
+        o["nei_list"] = None                 # optional outputs, computed only on request: the nearest-neighbour list
+        if copo:                             # feeds CCPPO's concat fusion, the mean-field mask its mean-field fusion
+            o["mf_mask"] = None
         outs.append(o)
     split = [env.alloc_obs_split() for _ in range(2)]      # the policy's [hi | lo] operand, written by the env
     first = dict(env.out)

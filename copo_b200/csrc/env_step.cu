@@ -22,6 +22,27 @@
 
 namespace b2c {
 
+// Shared-memory plan of one CTA working on `G` scenes at a time (offsets in bytes, every region 16-byte aligned).
+struct SmemPlan {
+    int map, st, obs, f, i, need, masks, queue, geom, total;
+};
+__host__ __device__ inline SmemPlan smem_plan(int G, int A, int D, int map_words, int tile_words, int n_warps,
+                                              bool split = false) {
+    SmemPlan p;
+    int o = 16;                                          // mbarrier
+    p.map = o;   o += map_words * 4;
+    p.st = o;    o += G * tile_words * 4;
+    p.obs = o;   o += split ? 0 : ((G * A * D + 3) & ~3) * 4;      // two-kernel mode: observations go straight to HBM
+    p.f = o;     o += ((G * 6 * A + 3) & ~3) * 4;
+    p.i = o;     o += ((G * (4 * A + MAX_SPAWN) + 3) & ~3) * 4;
+    p.need = o;  o += ((3 * G + 4 + 3) & ~3) * 4;        // need[G], scene_done[G], queue fill (1 or per scene)
+    p.masks = o; o += G * 4 * 8;                         // per scene: four slot masks (SceneView::masks)
+    p.queue = o; o += split ? 0 : ((G * A * A + 7) & ~7) * 2;    // two-kernel mode: the lidar kernel builds the pair list
+    p.geom = o;  (void)n_warps;
+    p.total = o;
+    return p;
+}
+
 struct EnvIO {
     const uint32_t* map;
     uint32_t* state;
@@ -48,6 +69,9 @@ struct EnvIO {
     int tile_words;
     int obs_bulk;   // 1 when the obs tiles can leave through a bulk store (16-byte aligned base)
     int group;      // scenes one CTA works on at a time
+    int rec_stride; // two-kernel mode: words between two non-laser columns of the record (odd, >= A)
+    SmemPlan pl;    // shared-memory offsets, computed once on the host (read from the constant bank instead of being
+                    // re-derived - the 48-register state kernel rematerialises them at every use)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -85,27 +109,6 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 
 static constexpr int ENV_MAX_THREADS = 256;
 static constexpr int ENV_MAX_GROUP = 16;      // scene tag in a queue entry is 4 bits
-
-// Shared-memory plan of one CTA working on `G` scenes at a time (offsets in bytes, every region 16-byte aligned).
-struct SmemPlan {
-    int map, st, obs, f, i, need, masks, queue, geom, total;
-};
-__host__ __device__ inline SmemPlan smem_plan(int G, int A, int D, int map_words, int tile_words, int n_warps,
-                                              bool split = false) {
-    SmemPlan p;
-    int o = 16;                                          // mbarrier
-    p.map = o;   o += map_words * 4;
-    p.st = o;    o += G * tile_words * 4;
-    p.obs = o;   o += split ? 0 : ((G * A * D + 3) & ~3) * 4;      // two-kernel mode: observations go straight to HBM
-    p.f = o;     o += ((G * 6 * A + 3) & ~3) * 4;
-    p.i = o;     o += ((G * (4 * A + MAX_SPAWN) + 3) & ~3) * 4;
-    p.need = o;  o += ((3 * G + 4 + 3) & ~3) * 4;        // need[G], scene_done[G], queue fill (1 or per scene)
-    p.masks = o; o += G * 4 * 8;                         // per scene: four slot masks (SceneView::masks)
-    p.queue = o; o += split ? 0 : ((G * A * A + 7) & ~7) * 2;    // two-kernel mode: the lidar kernel builds the pair list
-    p.geom = o;  (void)n_warps;
-    p.total = o;
-    return p;
-}
 
 // two fp32 values -> packed bf16 pairs: hi = bf16(x), lo = bf16(x - hi) (one packed conversion each; the same
 // bits as tc::split_rows_kernel produces, tests/test_env_gpu.py::test_env_emits_the_policy_operand)
@@ -163,13 +166,16 @@ __device__ __forceinline__ void lidar_spread(const PairGeom& g, int lid_off, boo
 // SPLIT = true: the state half of the two-kernel mode - per-slot phases only, small shared-memory footprint (no
 // observation tile) so several times more scenes are resident per SM; ego / navigation features, poses and the
 // slots' lidar broad-phase masks go to a scratch record for env_lidar_kernel.
-template <bool SPLIT>
+// TA / TD: slots per scene and observation width known at compile time (0 = read from the config at run time).  The
+// shapes of BASELINE.json's configurations get their own instantiation: slot loops unroll, the `tid / A` and
+// field * AP + slot address arithmetic folds into immediates.
+template <bool SPLIT, int TA, int TD>
 __global__ void __launch_bounds__(SPLIT ? 128 : ENV_MAX_THREADS, SPLIT ? 10 : 2)      // state kernel: 48 registers, 10 CTAs per SM
 env_step_kernel(const __grid_constant__ EnvConfig cfg, const __grid_constant__ EnvIO io) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    const int A = cfg.A, AP = cfg.AP, D = cfg.D, G = io.group;
+    const int A = TA ? TA : cfg.A, AP = TA ? ((TA + 3) & ~3) : cfg.AP, D = TD ? TD : cfg.D, G = io.group;
     const int tid = threadIdx.x, NT = blockDim.x;
-    const SmemPlan pl = smem_plan(G, A, D, io.map_words, io.tile_words, (int)(blockDim.x >> 5), SPLIT);
+    const SmemPlan& pl = io.pl;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     uint32_t* s_map = reinterpret_cast<uint32_t*>(smem_raw + pl.map);
     uint32_t* s_st = reinterpret_cast<uint32_t*>(smem_raw + pl.st);
@@ -188,6 +194,7 @@ env_step_kernel(const __grid_constant__ EnvConfig cfg, const __grid_constant__ E
         v.map = s_map; v.st = s_st + sl * io.tile_words;
         v.obs = SPLIT ? io.pose + (size_t)(scene_base + sl) * io.rec_words + 6 * A + 4 : s_obs + (size_t)sl * A * D;
         v.obs_compact = SPLIT ? 1 : 0;
+        v.obs_stride = io.rec_stride;
         float* f = s_f + sl * 6 * A;
         v.cs = f; v.sn = f + A; v.rew = f + 2 * A; v.long_last = f + 3 * A; v.loc_s = f + 4 * A; v.loc_l = f + 5 * A;
         int* q = s_i + sl * (4 * A + MAX_SPAWN);
@@ -228,7 +235,8 @@ env_step_kernel(const __grid_constant__ EnvConfig cfg, const __grid_constant__ E
             float2 a = reinterpret_cast<const float2*>(io.actions)[(size_t)scene0 * A + tid];
             act0 = a.x; act1 = a.y;
         }
-        mbar_wait(bar, parity);
+        if (tid == 0) mbar_wait(bar, parity);            // one thread polls; the others sleep at the barrier instead of
+        __syncthreads();                                 // spending issue slots on try_wait loops
         parity ^= 1u;
         first = false;
 
@@ -280,7 +288,7 @@ env_step_kernel(const __grid_constant__ EnvConfig cfg, const __grid_constant__ E
         // ---- P6b: neighbours (+ lidar pair queue), per-slot outputs, ego/navi features (thread = slot) ----
         const bool spare = (NT - ng * A) >= ng;          // idle threads take the per-scene reductions
         if (has_agent) {
-            NeiOut n = phase_neighbours(v, cfg, ia);
+            NeiOut n = phase_neighbours(v, cfg, ia, io.mf_mask != nullptr, io.nei_list != nullptr);
             if constexpr (SPLIT) {
                 uint32_t* pm = reinterpret_cast<uint32_t*>(io.pose + (size_t)(scene0 + sl_a) * io.rec_words + 4 * A + 4);
                 pm[ia] = (uint32_t)n.cull_mask; pm[A + ia] = (uint32_t)(n.cull_mask >> 32);
@@ -403,41 +411,45 @@ struct LidarIO {
     const float* pose;
     float* obs;
     uint32_t* obs_split;
-    int pair_stride, rec_words, kp, group, S, A, D, n_ray, ray_off;
+    int pair_stride, rec_words, rec_stride, kp, group, S, A, D, n_ray, ray_off;
 };
+static constexpr int LIDAR_RAYS = 72;      // laser count of every shipped map (the specialised kernels assume it)
 
 struct LidarPlan {
-    int ray, rec, pairs, nq, tile, total;
+    int ray, rec, pairs, nq, excl, tile, total;
 };
-__host__ __device__ inline LidarPlan lidar_plan(int G, int A, int D, int n_ray, int rec_words, int pair_stride) {
+__host__ __device__ inline LidarPlan lidar_plan(int G, int A, int D, int n_ray, int rec_words, int pair_stride,
+                                                int n_warps) {
     LidarPlan p;
     int o = 16;                                           // mbarrier
     p.ray = o;   o += (n_ray * 8 + 15) & ~15;
     p.rec = o;   o += G * rec_words * 4;                  // rec_words is a multiple of 4
     p.pairs = o; o += G * pair_stride * 2;                // pair_stride is a multiple of 8
     p.nq = o;    o += ((G + 3) & ~3) * 4;
+    p.excl = o;  o += n_warps * MAX_SLOTS * 4;                    // per warp: exclusive pair-list bases of the observers
     p.tile = o;  o += ((G * A * D + 3) & ~3) * 4;
     p.total = o;
     return p;
 }
 
+template <int TA, int TD>
 __global__ void __launch_bounds__(ENV_MAX_THREADS)
 env_lidar_kernel(const __grid_constant__ LidarIO io) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    const int A = io.A, D = io.D, G = io.group;
+    const int A = TA ? TA : io.A, D = TD ? TD : io.D, G = io.group;
     const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, n_warps = NT >> 5;
-    const int n_ray = io.n_ray;
+    const int n_ray = TA ? LIDAR_RAYS : io.n_ray;
     const int rec = io.rec_words;
-    const LidarPlan pl = lidar_plan(G, A, D, n_ray, rec, io.pair_stride);
+    const LidarPlan pl = lidar_plan(G, A, D, n_ray, rec, io.pair_stride, n_warps);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);          // record arrivals
     float2* s_ray = reinterpret_cast<float2*>(smem_raw + pl.ray);
     float* s_rec = reinterpret_cast<float*>(smem_raw + pl.rec);
     uint16_t* s_pairs = reinterpret_cast<uint16_t*>(smem_raw + pl.pairs);
     int* s_nq = reinterpret_cast<int*>(smem_raw + pl.nq);
+    int* s_excl = reinterpret_cast<int*>(smem_raw + pl.excl);
     float* s_tile = reinterpret_cast<float*>(smem_raw + pl.tile);     // [G][A][D]
     const int n_groups = (io.S + G - 1) / G;
     const int lid0 = EGO_DIM + NAVI_DIM;
-    const int n_ego = D - n_ray;                                  // non-laser columns
     auto fetch_record = [&](int grp) {                            // thread 0 only
         const int scene0 = grp * G;
         const int ng = (io.S - scene0 < G) ? io.S - scene0 : G;
@@ -454,27 +466,32 @@ env_lidar_kernel(const __grid_constant__ LidarIO io) {
         for (int k = tid; k < n_ray; k += NT) s_ray[k] = gr[k];
     }
     __syncthreads();
-    // warp 0 builds the pair lists, the other warps (all of them when there is only one) lay out the tile
-    const bool lays_out = (n_warps == 1) || (warp > 0);
-    const int lw = (n_warps == 1) ? 0 : warp - 1, n_lw = (n_warps == 1) ? 1 : n_warps - 1;
     const bool rows_vec = ((D & 3) == 0);                         // rows start 16-byte aligned
+    const int n_cell = D >> 2;                                    // float4 cells per row (rows_vec)
+    const int cell_lo = (lid0 + 3) >> 2, cell_hi = (lid0 + n_ray) >> 2;      // cells [cell_lo, cell_hi) hold lasers only
+    const int AS = io.rec_stride;                                 // words between two non-laser columns of the record
+    int parts = NT / A;                                           // threads that share one observer's mask expansion
+    parts = parts < 1 ? 1 : (parts > 4 ? 4 : parts);
+    const int span = (A + parts - 1) / parts;                     // slots per thread
     for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
         const int scene0 = grp * G;
         const int ng = (io.S - scene0 < G) ? io.S - scene0 : G;
-        mbar_wait(bar, parity);
+        if (tid == 0) mbar_wait(bar, parity);                     // one thread polls, the others sleep at the barrier
+        __syncthreads();
         parity ^= 1u;
         for (int sl = 0; sl < ng; ++sl) {
             const float* ps = s_rec + sl * rec;
             const uint32_t* hd = reinterpret_cast<const uint32_t*>(ps + 4 * A);
-            if (warp == 0) {
-                // pair list: observer `o` owns popc(mask[o]) consecutive entries; each lane expands observers
-                // `lane` and `lane + 32` (A <= 64)
+            // ---- pair list: observer `o` owns popc(mask[o]) consecutive entries, ascending box order.  Every warp
+            // takes the prefix sum of the populations (lane = observers `lane` and `lane + 32`, A <= 64) and keeps the
+            // bases in its own shared-memory row; then every thread expands one slice of one observer's mask (an
+            // observer's slots are dealt to `parts` threads), so the bit walks are short and run on all lanes --------
+            {
                 const uint32_t* cl = hd + 4;
                 const uint32_t* ch = cl + A;
                 const int o0 = lane, o1 = lane + 32;
-                unsigned long long m0 = (o0 < A) ? ((unsigned long long)cl[o0] | ((unsigned long long)ch[o0] << 32)) : 0ull;
-                unsigned long long m1 = (o1 < A) ? ((unsigned long long)cl[o1] | ((unsigned long long)ch[o1] << 32)) : 0ull;
-                const int c0 = __popcll(m0), c1 = __popcll(m1);
+                const int c0 = (o0 < A) ? __popc(cl[o0]) + __popc(ch[o0]) : 0;
+                const int c1 = (o1 < A) ? __popc(cl[o1]) + __popc(ch[o1]) : 0;
                 int i0 = c0, i1 = c1;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
@@ -482,35 +499,61 @@ env_lidar_kernel(const __grid_constant__ LidarIO io) {
                     if (lane >= d) { i0 += n0; i1 += n1; }
                 }
                 const int t0 = __shfl_sync(0xffffffffu, i0, 31), t1 = __shfl_sync(0xffffffffu, i1, 31);
+                int* my_excl = s_excl + warp * MAX_SLOTS;
+                my_excl[o0] = i0 - c0;                            // exclusive bases of observers lane / lane + 32
+                my_excl[o1] = t0 + i1 - c1;
+                __syncwarp();
                 uint16_t* q = s_pairs + (size_t)sl * io.pair_stride;
-                int w0 = i0 - c0, w1 = t0 + i1 - c1;
-#pragma unroll 1
-                while (m0 | m1) {
-                    if (m0) { const int j = __ffsll((long long)m0) - 1; m0 &= m0 - 1ull; q[w0++] = (uint16_t)((o0 << 6) | j); }
-                    if (m1) { const int j = __ffsll((long long)m1) - 1; m1 &= m1 - 1ull; q[w1++] = (uint16_t)((o1 << 6) | j); }
+                for (int item = tid; item < A * parts; item += NT) {
+                    const int o = item / parts, b0 = (item - o * parts) * span;
+                    const int b1 = (b0 + span < A) ? b0 + span : A;
+                    const unsigned long long m = (unsigned long long)cl[o] | ((unsigned long long)ch[o] << 32);
+                    const unsigned long long below = (1ull << b0) - 1ull;                     // b0 < A <= 64
+                    const unsigned long long upto = (b1 >= 64) ? ~0ull : (1ull << b1) - 1ull;
+                    int w = my_excl[o] + __popcll(m & below);
+                    BitWalk walk(m & upto & ~below);
+                    int j;
+                    while (walk.next(j)) q[w++] = (uint16_t)((o << 6) | j);
                 }
-                if (lane == 0) s_nq[sl] = t0 + t1;
+                if (tid == 0) s_nq[sl] = t0 + t1;
             }
-            if (lays_out) {
-                // observation rows: lasers start at "nothing within range" for participants (0 for empty rows), the
-                // other columns come out of the record (stored slot-fastest by the state kernel)
+            // ---- observation rows: lasers start at "nothing within range" for participants (0 for empty rows), the
+            // other columns come out of the record (stored slot-fastest by the state kernel, odd column stride) -----
+            {
                 const unsigned long long pm = (unsigned long long)hd[1] | ((unsigned long long)hd[2] << 32);
                 float* tile = s_tile + (size_t)sl * A * D;
                 const float* eg = ps + 6 * A + 4;
-                for (int i = lw; i < A; i += n_lw) {
-                    const float val = ((pm >> i) & 1ull) ? 1.0f : 0.0f;
-                    float* trow = tile + (size_t)i * D;
-                    if (rows_vec) {
-                        float4* t4 = reinterpret_cast<float4*>(trow);
-#pragma unroll 1
-                        for (int k = lane; k < (D >> 2); k += 32) t4[k] = make_float4(val, val, val, val);
-                    } else {
-#pragma unroll 1
-                        for (int k = lane; k < D; k += 32) trow[k] = val;
+                if (rows_vec) {
+                    // whole 16-byte cells: the cells that hold lasers only ...
+                    const int n_mid = cell_hi - cell_lo;
+                    for (int e = tid; e < A * n_mid; e += NT) {
+                        const int i = e / n_mid, q4 = cell_lo + (e - i * n_mid);
+                        const float val = ((pm >> i) & 1ull) ? 1.0f : 0.0f;
+                        reinterpret_cast<float4*>(tile + (size_t)i * D)[q4] = make_float4(val, val, val, val);
                     }
-                    __syncwarp();
-#pragma unroll 1
-                    for (int c = lane; c < n_ego; c += 32) trow[c < lid0 ? c : c + n_ray] = eg[c * A + i];
+                    // ... and the cells with columns of the record in them
+                    const int n_edge = n_cell - n_mid;
+                    for (int e = tid; e < A * n_edge; e += NT) {
+                        const int i = e / n_edge;
+                        int q4 = e - i * n_edge;
+                        q4 = (q4 < cell_lo) ? q4 : q4 - cell_lo + cell_hi;
+                        const float val = ((pm >> i) & 1ull) ? 1.0f : 0.0f;
+                        float x[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int col = 4 * q4 + u;
+                            const int src = (col < lid0) ? col : col - n_ray;
+                            x[u] = (col >= lid0 && col < lid0 + n_ray) ? val : eg[src * AS + i];
+                        }
+                        reinterpret_cast<float4*>(tile + (size_t)i * D)[q4] = make_float4(x[0], x[1], x[2], x[3]);
+                    }
+                } else {
+                    for (int e = tid; e < A * D; e += NT) {
+                        const int i = e / D, col = e - i * D;
+                        const float val = ((pm >> i) & 1ull) ? 1.0f : 0.0f;
+                        const int src = (col < lid0) ? col : col - n_ray;
+                        tile[e] = (col >= lid0 && col < lid0 + n_ray) ? val : eg[src * AS + i];
+                    }
                 }
             }
         }
@@ -600,15 +643,46 @@ env_lidar_kernel(const __grid_constant__ LidarIO io) {
 // ---- host side: handle + C ABI (include/copo_b200.h) ---------------------------------------------------
 using namespace b2c;
 
+typedef void (*b2c_step_fn)(const EnvConfig, const EnvIO);
+typedef void (*b2c_lidar_fn)(const LidarIO);
+
+// Shape-specialised instantiations (slots x observation width) for the launch mode each shape runs by default:
+// two-kernel mode from 16 slots up, the fused kernel below.  Everything else - other shapes, a mode forced through
+// B2C_ENV_SPLIT, maps with another laser count, B2C_ENV_GENERIC=1 - runs the generic kernels (all sizes at run time).
+#define B2C_SPLIT_SHAPES(X) X(40, 92) X(40, 91) X(40, 157) X(40, 156) X(30, 92) X(30, 91) X(20, 97) X(20, 96)
+#define B2C_FUSED_SHAPES(X) X(10, 92) X(10, 91)
+static b2c_step_fn pick_step_kernel(bool split, int A, int D, bool generic) {
+    if (!generic) {
+#define X(a, d) if (split && A == a && D == d) return env_step_kernel<true, a, d>;
+        B2C_SPLIT_SHAPES(X)
+#undef X
+#define X(a, d) if (!split && A == a && D == d) return env_step_kernel<false, a, d>;
+        B2C_FUSED_SHAPES(X)
+#undef X
+    }
+    return split ? env_step_kernel<true, 0, 0> : env_step_kernel<false, 0, 0>;
+}
+static b2c_lidar_fn pick_lidar_kernel(int A, int D, bool generic) {
+    if (!generic) {
+#define X(a, d) if (A == a && D == d) return env_lidar_kernel<a, d>;
+        B2C_SPLIT_SHAPES(X)
+#undef X
+    }
+    return env_lidar_kernel<0, 0>;
+}
+
 struct b2c_env {
     EnvConfig cfg;
+    b2c_step_fn step_fn;
+    b2c_lidar_fn lidar_fn;
     int group;
     int threads;
     int split;               // 1: two-kernel mode (state kernel + lidar kernel)
+    int specialised;         // 1: the shape has its own kernel instantiation
     int lidar_group, lidar_threads, lidar_ctas, ray_off;
     size_t lidar_smem;
     float* d_pose;
-    int pair_stride, n_ray, rec_words;
+    int pair_stride, n_ray, rec_words, rec_stride;
     uint32_t* d_map;
     uint32_t* d_state;
     int map_words;
@@ -671,29 +745,36 @@ int b2c_env_create(const b2c_env_config* c, const uint32_t* map_blob, int map_wo
     }
     e->smem = (size_t)smem_plan(e->group, k.A, k.D, map_words, e->tile_words, e->threads / 32, e->split).total;
     e->n_ray = (int)map_blob[M_NRAY];
-    e->d_pose = nullptr; e->rec_words = 0; e->pair_stride = 0;
+    e->d_pose = nullptr; e->rec_words = 0; e->pair_stride = 0; e->rec_stride = 0;
+    const bool generic = getenv("B2C_ENV_GENERIC") != nullptr || e->n_ray != LIDAR_RAYS;
+    e->step_fn = pick_step_kernel(e->split != 0, k.A, k.D, generic);
+    e->lidar_fn = pick_lidar_kernel(k.A, k.D, generic);
+    e->specialised = (e->step_fn != (e->split ? env_step_kernel<true, 0, 0> : env_step_kernel<false, 0, 0>)) ? 1 : 0;
     if (e->split) {
-        B2C_CUDA_OR(cudaFuncSetAttribute(env_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem),
+        B2C_CUDA_OR(cudaFuncSetAttribute(e->step_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem),
                     delete e);
         e->lidar_threads = 128;
         if (const char* t = getenv("B2C_LIDAR_THREADS")) e->lidar_threads = atoi(t);
         if (e->lidar_threads < 32 || e->lidar_threads > ENV_MAX_THREADS || (e->lidar_threads & 31)) e->lidar_threads = 128;
-        e->lidar_ctas = 64;
-        if (const char* t = getenv("B2C_LIDAR_CTAS")) e->lidar_ctas = atoi(t) > 0 ? atoi(t) : 64;
+        e->lidar_ctas = 9;                          // resident CTAs per SM (shared memory); each walks several scenes, so
+        if (const char* t = getenv("B2C_LIDAR_CTAS")) e->lidar_ctas = atoi(t) > 0 ? atoi(t) : 9;   // the prologue is paid once
         e->ray_off = (int)map_blob[M_OFF_RAY];
         e->lidar_group = 1;
         if (const char* g = getenv("B2C_LIDAR_GROUP")) e->lidar_group = atoi(g) > 0 ? atoi(g) : 1;
         e->pair_stride = (k.A * k.A + 7) & ~7;
-        e->rec_words = (6 * k.A + 4 + (k.D - e->n_ray) * k.A + 3) & ~3;
-        auto lsm = [&](int g) { return (size_t)lidar_plan(g, k.A, k.D, e->n_ray, e->rec_words, e->pair_stride).total; };
+        e->rec_stride = k.A | 1;
+        e->rec_words = (6 * k.A + 4 + (k.D - e->n_ray) * e->rec_stride + 3) & ~3;
+        auto lsm = [&](int g) {
+            return (size_t)lidar_plan(g, k.A, k.D, e->n_ray, e->rec_words, e->pair_stride, e->lidar_threads / 32).total;
+        };
         while (e->lidar_group > 1 && lsm(e->lidar_group) > 100 * 1024) e->lidar_group -= 1;
         if (e->lidar_group > k.S) e->lidar_group = k.S;
         e->lidar_smem = lsm(e->lidar_group);
-        B2C_CUDA_OR(cudaFuncSetAttribute(env_lidar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->lidar_smem),
+        B2C_CUDA_OR(cudaFuncSetAttribute(e->lidar_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->lidar_smem),
                     delete e);
         B2C_CUDA_OR(cudaMalloc(&e->d_pose, (size_t)k.S * e->rec_words * 4), delete e);
     } else {
-        B2C_CUDA_OR(cudaFuncSetAttribute(env_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem),
+        B2C_CUDA_OR(cudaFuncSetAttribute(e->step_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem),
                     delete e);
     }
     B2C_CUDA_OR(cudaMalloc(&e->d_map, (size_t)map_words * 4), delete e);
@@ -720,12 +801,13 @@ static void launch_lidar(b2c_env* e, float* obs, uint32_t* obs_split, int kp, cu
     LidarIO li;
     li.map = e->d_map; li.pose = e->d_pose ? e->d_pose + (size_t)first * e->rec_words : nullptr; li.obs = obs; li.obs_split = obs_split;
     li.pair_stride = e->pair_stride; li.rec_words = e->rec_words; li.n_ray = e->n_ray; li.ray_off = e->ray_off;
+    li.rec_stride = e->rec_stride;
     li.kp = kp; li.group = e->lidar_group; li.S = cfg.S; li.A = cfg.A; li.D = cfg.D;
     // one CTA per group of scenes (the hardware scheduler balances the uneven pair counts); very large batches loop
     int lg = (cfg.S + e->lidar_group - 1) / e->lidar_group;
     int lgrid = e->num_sms * e->lidar_ctas;
     if (lgrid > lg) lgrid = lg;
-    env_lidar_kernel<<<lgrid, e->lidar_threads, e->lidar_smem, st>>>(li);
+    e->lidar_fn<<<lgrid, e->lidar_threads, e->lidar_smem, st>>>(li);
 }
 
 static int launch_env(b2c_env* e, const float* actions, const b2c_env_io* o, int do_reset, int new_episode,
@@ -750,6 +832,8 @@ static int launch_env(b2c_env* e, const float* actions, const b2c_env_io* o, int
     io.obs_bulk = ((((size_t)cfg.A * cfg.D * 4) % 16 == 0) && (((uintptr_t)o->obs) % 16 == 0)) ? 1 : 0;
     io.group = e->group;
     io.pose = e->d_pose ? e->d_pose + (size_t)first * e->rec_words : nullptr; io.rec_words = e->rec_words;
+    io.rec_stride = e->rec_stride;
+    io.pl = smem_plan(e->group, cfg.A, cfg.D, e->map_words, e->tile_words, e->threads / 32, e->split != 0);
     int ctas_per_sm = (int)(227 * 1024 / (e->smem + 1024));
     int by_threads = 2048 / e->threads;
     if (ctas_per_sm > by_threads) ctas_per_sm = by_threads;
@@ -759,9 +843,9 @@ static int launch_env(b2c_env* e, const float* actions, const b2c_env_io* o, int
     if (grid > n_groups) grid = n_groups;
     cudaStream_t st = (cudaStream_t)stream;
     if (!e->split) {
-        env_step_kernel<false><<<grid, e->threads, e->smem, st>>>(cfg, io);
+        e->step_fn<<<grid, e->threads, e->smem, st>>>(cfg, io);
     } else {
-        env_step_kernel<true><<<grid, e->threads, e->smem, st>>>(cfg, io);
+        e->step_fn<<<grid, e->threads, e->smem, st>>>(cfg, io);
         B2C_CUDA(cudaGetLastError());
         launch_lidar(e, o->obs, io.obs_split, io.kp, st, first, count);
     }
@@ -806,6 +890,7 @@ int b2c_env_relaunch_lidar(b2c_env* e, const b2c_env_io* o, void* stream) {
 }
 int b2c_env_obs_dim(const b2c_env* e) { return e ? e->cfg.D : -1; }
 int b2c_env_kernels_per_step(const b2c_env* e) { return e ? (e->split ? 2 : 1) : -1; }
+int b2c_env_shape_specialised(const b2c_env* e) { return e ? e->specialised : -1; }
 int b2c_env_obs_split_width(const b2c_env* e) { return e ? 2 * ((e->cfg.D + 63) / 64 * 64) : -1; }
 int b2c_env_state_words(const b2c_env* e) { return e ? e->tile_words : -1; }
 int b2c_env_slots_padded(const b2c_env* e) { return e ? e->cfg.AP : -1; }

@@ -189,6 +189,46 @@ class MultiAgentDrivingEnv:
     def close(self):
         self._sim.close()
 
+    # ---- attributes the reference's callers read off a MetaDrive env ------------------------------
+    def _header(self, k):
+        AP = (self.A + 3) // 4 * 4
+        return int(self._sim.get_state()[0][16 * AP + k])
+
+    @property
+    def engine(self):
+        """`env.engine.global_seed`, `env.engine.current_map.road_network.get_bounding_box()` (env_wrappers.py:268-272;
+        legacy svo_env.py).  The seed of the running episode is the start seed plus the scene's episode counter."""
+        env = self
+
+        class _RoadNetwork:
+            def get_bounding_box(self):
+                return env._sim.tables.bounding_box()
+
+        class _Map:
+            road_network = _RoadNetwork()
+
+        class _Engine:
+            current_map = _Map()
+
+            @property
+            def global_seed(self):
+                return int(env.config["start_seed"]) + max(env._header(2) - 1, 0)       # header word 2: episode counter
+
+            episode_step = property(lambda self: env.episode_step)
+
+        return _Engine()
+
+    @property
+    def agent_manager(self):
+        """`env.agent_manager.next_agent_count` (legacy svo_env.py:256): how many agents the scene has named so far."""
+        env = self
+
+        class _AgentManager:
+            next_agent_count = property(lambda self: env._header(1))                     # header word 1: next agent id
+            active_agents = property(lambda self: env.vehicles)
+
+        return _AgentManager()
+
     def close_and_reset_num_agents(self, num_agents):
         """ChangeNEnv (env_wrappers.py:444-460): population change = slot masking, no re-allocation."""
         self.config["num_agents"] = num_agents

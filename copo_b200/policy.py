@@ -241,6 +241,51 @@ class IPPOPolicy:
         ro[ADVANTAGES], ro[VALUE_TARGETS] = adv[0], tgt[0]
         return ro
 
+    # ---- per-trajectory form: the hook RLlib calls (a8, a13) ------------------------------------------------
+    def postprocess_trajectory(self, sample_batch, other_agent_batches=None, episode=None):
+        """One agent's trajectory as RLlib hands it to the policy (algo_ccppo.py:322-374, algo_copo.py:473-502; IPPO:
+        stock PPO postprocessing): `sample_batch` is a mapping of numpy arrays under SampleBatch's column names
+        (`obs`, `new_obs`, `actions`, `rewards`, `dones`, `infos`, `t`), `other_agent_batches` maps agent id ->
+        (policy, batch) for the agents of the same episode, `episode=None` marks RLlib's initialisation call (no
+        fusion, no infos).  Adds the same columns as the reference; the value heads and the advantage scans run on the
+        device (the same kernels as `postprocess_rollout`, which processes all trajectories of a rollout at once and is
+        what the trainers use), the neighbour fusion is host logic over the few rows of one trajectory."""
+        sb = sample_batch
+        obs = np.asarray(sb[OBS], np.float32)
+        T = obs.shape[0]
+        dev = self.device
+        cobs = self._trajectory_critic_obs(sb, obs, other_agent_batches, episode)
+        if cobs is not None:
+            sb[CENTRALIZED_CRITIC_OBS] = cobs
+        cin = torch.as_tensor(cobs if cobs is not None else obs, device=dev).contiguous()
+        heads = self._trajectory_heads(sb, cin, episode)            # [(value column, reward column, adv, target)]
+        done_last = bool(np.asarray(sb[DONES])[-1])
+        flags = torch.full((T, 1), 1, dtype=torch.uint8, device=dev)
+        if done_last:
+            flags[-1, 0] = 3                                        # VALID | DONE: last_r = 0
+        rew, val = [], []
+        for vcol, rcol, _, _ in heads:
+            rew.append(torch.as_tensor(np.asarray(sb[rcol], np.float32), device=dev).reshape(T, 1).contiguous())
+            val.append(torch.as_tensor(sb[vcol], device=dev).reshape(T, 1).contiguous())
+        boot = None
+        if not done_last and self.algo == "ippo":                   # stock rllib: last_r = V(new_obs[-1])
+            nxt = torch.as_tensor(np.asarray(sb["new_obs"], np.float32)[-1:], device=dev)
+            boot = [self.model.central_value_function(nxt).reshape(1).contiguous()]
+        adv, tgt = ops.gae3(flags, rew, val, self.config["gamma"], self.config["lambda_"], bootstrap=boot)
+        for k, (_, _, acol, tcol) in enumerate(heads):
+            sb[acol] = adv[k].reshape(T).cpu().numpy()
+            sb[tcol] = tgt[k].reshape(T).cpu().numpy()
+        if "step_lcf" in sb:
+            assert sb["step_lcf"].max() == sb["step_lcf"].min()     # algo_copo.py:501
+        return sb
+
+    def _trajectory_critic_obs(self, sb, obs, other_agent_batches, episode):
+        return None                                                 # IPPO: the critic sees the agent's own observation
+
+    def _trajectory_heads(self, sb, cin, episode):
+        sb[VF_PREDS] = self.model.central_value_function(cin).cpu().numpy().astype(np.float32)
+        return [(VF_PREDS, REWARDS, ADVANTAGES, VALUE_TARGETS)]
+
     def standardize_advantages(self, ro):
         """Stock PPO training_step: standardize_fields(["advantages"]) over the whole train batch."""
         st = ops.lcf_mix_stats(ro["flags"].reshape(-1), ro[ADVANTAGES].reshape(-1), None, None, None)
@@ -282,6 +327,61 @@ class CCPPOPolicy(IPPOPolicy):
                                ro["mf_mask"].reshape(-1) if mode == "mf" else None,
                                ro["nei_list"].reshape(T * N, 4) if mode == "concat" else None, ro["slots"], mode,
                                self.config["counterfactual"])
+
+    def _trajectory_critic_obs(self, sb, obs, other_agent_batches, episode):
+        """The centralized critic observation of one trajectory (algo_ccppo.py:225-311, 328-355): own observation, then
+        the neighbours' observations (+ actions when `counterfactual`) taken from the rows of `other_agent_batches`
+        with the same environment time step `t` - the nearest `num_neighbours` in the order the env lists them
+        (concat), or the mean over those within `mf_nei_distance` (mean field; `>` skips, so `<=` is kept)."""
+        T, odim = obs.shape
+        if episode is None:                                # RLlib's initialisation call: the column is already there
+            return np.asarray(sb[CENTRALIZED_CRITIC_OBS], np.float32)
+        mode, cf = self.config["fuse_mode"], self.config["counterfactual"]
+        cobs = np.zeros((T, self.model.cobs_dim), np.float32)
+        cobs[:, :odim] = obs
+        if mode == "none":
+            assert odim == cobs.shape[1]
+            return cobs
+        assert other_agent_batches is not None
+        acts = np.asarray(sb[ACTIONS], np.float32)
+        adim = acts.shape[1]
+        other = odim + (adim if cf else 0)
+
+        def row_of(name, t):
+            if name not in other_agent_batches:
+                return None
+            _, nb = other_agent_batches[name]
+            hit = np.where(np.asarray(nb["t"]) == t)[0]
+            if len(hit) > 1:
+                raise ValueError("two rows of agent %r share the time step %r" % (name, t))
+            return (nb[OBS][hit[0]], nb[ACTIONS][hit[0]]) if len(hit) else None
+
+        for i in range(T):
+            info, t = sb["infos"][i], sb["t"][i]
+            if mode == "concat":
+                for cnt, name in enumerate(info["neighbours"]):
+                    if cnt >= self.config["num_neighbours"]:
+                        break
+                    r = row_of(name, t)
+                    if r is not None:
+                        start = odim + cnt * other
+                        cobs[i, start:start + odim] = r[0]
+                        if cf:
+                            cobs[i, start + odim:start + other] = r[1]
+            else:
+                obs_list, act_list = [], []
+                for name, dist in zip(info["neighbours"], info["neighbours_distance"]):
+                    if dist > self.config["mf_nei_distance"]:
+                        continue
+                    r = row_of(name, t)
+                    if r is not None:
+                        obs_list.append(r[0])
+                        act_list.append(r[1])
+                if obs_list:
+                    cobs[i, odim:2 * odim] = np.mean(np.asarray(obs_list, np.float32), axis=0)
+                    if cf:
+                        cobs[i, 2 * odim:2 * odim + adim] = np.mean(np.asarray(act_list, np.float32), axis=0)
+        return cobs
 
 
 class CoPOPolicy(CCPPOPolicy):
@@ -327,6 +427,22 @@ class CoPOPolicy(CCPPOPolicy):
         return ret
 
     # ---- postprocessing (a13, a12, a15) --------------------------------------------------------------------
+    def _trajectory_heads(self, sb, cin, episode):
+        """algo_copo.py:473-500: three value heads; neighbourhood / global rewards and the step LCF come out of the
+        infos the LCF environment filled (env_wrappers.py:313-357)."""
+        heads = super()._trajectory_heads(sb, cin, episode)
+        sb[NEI_VALUES] = self.model.get_nei_value(cin).cpu().numpy().astype(np.float32)
+        sb[GLOBAL_VALUES] = self.model.get_global_value(cin).cpu().numpy().astype(np.float32)
+        if episode is not None:
+            infos = sb["infos"]
+            assert isinstance(infos[0], dict)
+            sb[NEI_REWARDS] = np.array([info[NEI_REWARDS] for info in infos]).astype(np.float32)
+            sb[GLOBAL_REWARDS] = np.array([info[GLOBAL_REWARDS] for info in infos]).astype(np.float32)
+            if self.config["use_distributional_lcf"]:
+                sb["step_lcf"] = np.array([info["lcf"] for info in infos]).astype(np.float32)
+        return heads + [(NEI_VALUES, NEI_REWARDS, NEI_ADVANTAGE, NEI_TARGET),
+                        (GLOBAL_VALUES, GLOBAL_REWARDS, GLOBAL_ADVANTAGES, GLOBAL_TARGET)]
+
     def postprocess_rollout(self, ro):
         T, N = ro["flags"].shape
         cobs = self._critic_obs(ro)

@@ -32,41 +32,74 @@ def _dist():
     return dist if (dist.is_available() and dist.is_initialized()) else None
 
 
+def resolve_env(env):
+    """`config["env"]` as the reference's scripts pass it - a name registered through `get_rllib_compatible_env`
+    (torch_copo/utils/env_wrappers.py:559-597), an env class, a `MultiAgent*Env` class name or a map name - to
+    (map name, appends the LCF to the observation or None if the name does not say, default env config)."""
+    from . import envs as E
+    cls = env if isinstance(env, type) else E._REGISTRY.get(env)
+    if cls is None and isinstance(env, str) and hasattr(E, env) and isinstance(getattr(E, env), type):
+        cls = getattr(E, env)
+    if cls is not None:
+        in_registry = isinstance(env, type) or env in E._REGISTRY
+        return cls.MAP, (bool(cls.APPEND_LCF) if in_registry else None), cls.default_config()
+    return MAP_OF_ENV.get(env, env), None, {}
+
+
 class IPPOTrainer:
     policy_cls = P.IPPOPolicy
 
     @classmethod
     def get_default_config(cls):
         c = cls.policy_cls.default_config()
-        c.update_from_dict(dict(env="MultiAgentIntersectionEnv", num_scenes=64, sgd_minibatch_size=512,
+        c.update_from_dict(dict(env="MultiAgentIntersectionEnv", num_scenes=None, sgd_minibatch_size=512,
                                 rollout_fragment_length=200))
         return c
 
     def get_default_policy_class(self, config=None):
         return self.policy_cls
 
-    def __init__(self, config=None, env=None, device=None):
+    def __init__(self, config=None, env=None, device=None, logger_creator=None, **_unused):
+        """`config` may be an RLlib-style dict as the reference's scripts build it (train_copo.py:19-48): `env` is a
+        registered env name, `env_config` its overrides, `seed` may be None, `callbacks` a class with
+        `on_train_result`; RLlib resource keys (`num_gpus`, `num_cpus_per_worker`, ...) and the dead legacy keys the
+        scripts still pass (`initial_svo_std`, `svo_lr`, ...) are carried along and ignored.  Scenes per GPU:
+        `num_scenes`, else $B2C_NUM_SCENES, else train_batch_size / rollout_fragment_length (the number of concurrent
+        envs of the reference: 5 workers x 200-step fragments of a 2000-step batch -> 10)."""
+        import os
         cfg = self.get_default_config()
         if config:
-            cfg.update_from_dict(config)
+            cfg.update_from_dict(dict(config))
+        if cfg.get("seed") is None:
+            cfg["seed"] = 0
         self.config = cfg
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
         dist = _dist()
         self.rank = dist.get_rank() if dist else 0
         self.world = dist.get_world_size() if dist else 1
-        ec = dict(cfg.get("env_config", {}))
+        cb = cfg.get("callbacks")
+        self.callbacks = cb() if isinstance(cb, type) else (cb or None)
         if env is None:
-            name = cfg["env"]
-            map_name = MAP_OF_ENV.get(name, name)
+            map_name, env_lcf, ec = resolve_env(cfg["env"])
+            ec = dict(ec, **dict(cfg.get("env_config") or {}))
+            if not cfg.get("num_scenes"):
+                cfg["num_scenes"] = int(os.environ.get("B2C_NUM_SCENES", 0)) or max(
+                    1, int(cfg["train_batch_size"]) // int(cfg["rollout_fragment_length"]))
             S = int(cfg["num_scenes"])
-            append_lcf = self.policy_cls.algo == "copo"
+            append_lcf = env_lcf if env_lcf is not None else self.policy_cls.algo == "copo"
+            if self.policy_cls.algo == "copo" and not append_lcf:
+                raise ValueError("CoPO needs an LCF environment: wrap the env class with get_lcf_env "
+                                 "(torch_copo/train_copo.py:30)")
             env = BatchedDrivingEnv(map_name, num_scenes=S, num_agents=ec.get("num_agents"),
                                     num_slots=ec.get("num_agents"), seed=int(ec.get("start_seed", cfg.get("seed", 0))),
                                     scene_offset=parallel.scene_offset(self.rank, S), append_lcf=append_lcf,
-                                    neighbours_distance=ec.get("neighbours_distance", 40.0),
-                                    mf_nei_distance=cfg.get("mf_nei_distance", 10.0),
-                                    lcf_std=ec.get("lcf_normal_std", 0.1), horizon=ec.get("horizon", 1000),
-                                    delay_done=ec.get("delay_done", 25), device=self.device)
+                                    neighbours_distance=float(ec.get("neighbours_distance", 40.0)),
+                                    mf_nei_distance=float(cfg.get("mf_nei_distance", 10.0)),
+                                    lcf_std=float(ec.get("lcf_normal_std", 0.1)), horizon=int(ec.get("horizon", 1000)),
+                                    delay_done=int(ec.get("delay_done", 25)),
+                                    lcf_uniform=(ec.get("lcf_dist") == "uniform"),
+                                    force_lcf=float(ec.get("force_lcf", -100.0)), map_kwargs=ec.get("map_config"),
+                                    device=self.device)
         self.env = env
         self.policy = self.policy_cls(env.D, 2, cfg, device=self.device, dist=dist)
         if dist is not None and self.world > 1:
@@ -109,14 +142,18 @@ class IPPOTrainer:
                    "mf_mask": z((T, N), torch.int64), "nei_mask": z((T, N), torch.int64),
                    "nei_list": z((T, N, 4), torch.int8), "agent_id": z((T, N), torch.int32),
                    "scene_done": z((T, S), torch.uint8)}
+        # optional outputs the scene step only computes when asked: the mean-field mask and the nearest-neighbour list
+        # feed the critic-obs fusion of CCPPO (algo_ccppo.py:225-311) and nothing else
+        fuse = self.config.get("fuse_mode", "none") if self.policy_cls.algo != "ippo" else "none"
         self._step_out = []
         for t in range(T):
             r = self.ro
             self._step_out.append(dict(
                 obs=r[P.OBS][t + 1].view(S, A, D), reward=r[P.REWARDS][t].view(S, A), flags=r["flags"][t].view(S, A),
-                nei_mask=r["nei_mask"][t].view(S, A), mf_mask=r["mf_mask"][t].view(S, A),
+                nei_mask=r["nei_mask"][t].view(S, A), mf_mask=r["mf_mask"][t].view(S, A) if fuse == "mf" else None,
                 nei_reward=r[P.NEI_REWARDS][t].view(S, A), global_reward=r[P.GLOBAL_REWARDS][t],
-                nei_list=r["nei_list"][t].view(S, A, 4), agent_id=r["agent_id"][t].view(S, A),
+                nei_list=r["nei_list"][t].view(S, A, 4) if fuse == "concat" else None,
+                agent_id=r["agent_id"][t].view(S, A),
                 lcf=r["step_lcf"][t].view(S, A), scene_done=r["scene_done"][t]))
 
     def sample(self):
@@ -203,10 +240,20 @@ class IPPOTrainer:
         n = max(int(done.sum()), 1)
         rate = lambda bit: float(((f & bit) > 0)[done].sum()) / n
         valid = (f & FLAG_VALID) > 0
-        return dict(success_rate=rate(FLAG_ARRIVE), crash_rate=rate(FLAG_CRASH), out_of_road_rate=rate(FLAG_OUT),
-                    max_step_rate=rate(FLAG_MAXSTEP), episodes=int(done.sum()),
-                    step_reward_mean=float(ro[P.REWARDS][valid].mean()) if bool(valid.any()) else 0.0,
-                    agent_steps=int(valid.sum()))
+        steps, eps = int(valid.sum()), int(done.sum())
+        rsum = float((ro[P.REWARDS] * valid).sum())
+        m = dict(success_rate=rate(FLAG_ARRIVE), crash_rate=rate(FLAG_CRASH), out_of_road_rate=rate(FLAG_OUT),
+                 max_step_rate=rate(FLAG_MAXSTEP), episodes=eps, step_reward_mean=rsum / max(steps, 1),
+                 agent_steps=steps,
+                 # per-agent episode length / reward / cost of this fragment in steady state: totals over the
+                 # fragment divided by the episodes that ended in it
+                 episode_length=steps / n, episode_reward=rsum / n,
+                 episode_cost=float((((f & FLAG_CRASH) > 0) & valid).sum()) / n)
+        # the names RLlib gives the means of MultiAgentDrivingCallbacks' custom metrics (callbacks.py:48-147)
+        for k in ("success_rate", "crash_rate", "out_of_road_rate", "max_step_rate", "episode_length", "episode_reward",
+                  "episode_cost", "step_reward"):
+            m[k + "_mean"] = m.get(k, m.get(k + "_mean"))
+        return m
 
     def training_step(self):
         t0 = time.perf_counter()
@@ -240,15 +287,30 @@ class IPPOTrainer:
         t0 = time.perf_counter()
         res = self.training_step()
         info = res["default"]
+        cm = info["custom_metrics"]
         return {"training_iteration": self._iteration, "time_this_iter_s": time.perf_counter() - t0,
                 "timesteps_total": self._counters["num_env_steps_sampled"] * self.world,
                 "agent_timesteps_total": self._counters["num_agent_steps_sampled"] * self.world,
+                "episodes_this_iter": cm.get("episodes", 0), "episode_reward_mean": cm.get("episode_reward", 0.0),
+                "episode_len_mean": cm.get("episode_length", 0.0), "policy_reward_mean": {},
                 "info": {"learner": {"default": info}}, "timers": dict(self._timers),
-                "custom_metrics": info["custom_metrics"],
-                "success": info["custom_metrics"].get("success_rate", 0.0)}
+                "custom_metrics": cm, "success": cm.get("success_rate", 0.0)}
+
+    def save(self, checkpoint_dir="."):
+        """Writes `checkpoint-<iteration>` in the trial-checkpoint layout the reference's evaluator reads
+        (copo/eval/get_policy_function_from_checkpoint.py:12-50); returns its path."""
+        import os
+        from . import checkpoint as C
+        d = os.path.join(checkpoint_dir, "checkpoint_%06d" % self._iteration)
+        os.makedirs(d, exist_ok=True)
+        path = os.path.join(d, "checkpoint-%d" % self._iteration)
+        C.save_rllib_checkpoint(path, self.policy.model.state_dict())
+        return path
 
     def stop(self):
         self.env.close()
+
+    cleanup = stop
 
 
 class CCPPOTrainer(IPPOTrainer):

@@ -99,6 +99,7 @@ int b2c_env_relaunch_lidar(b2c_env* env, const b2c_env_io* out, void* stream);
 int b2c_env_obs_dim(const b2c_env* env);
 int b2c_env_obs_split_width(const b2c_env* env);
 int b2c_env_kernels_per_step(const b2c_env* env);            /* 1: fused kernel, 2: state kernel + lidar kernel */
+int b2c_env_shape_specialised(const b2c_env* env);           /* 1: (slots, obs width) has a compile-time specialised kernel */
 int b2c_env_state_words(const b2c_env* env);                /* u32 words per scene tile */
 int b2c_env_slots_padded(const b2c_env* env);
 int b2c_env_get_state(b2c_env* env, uint32_t* dst_host, void* stream);       /* synchronises the stream */

@@ -384,11 +384,15 @@ class OracleSim:
         S, A, cfg = self.S, self.A, self.cfg
         dx = self.x[:, :, None] - self.x[:, None, :]
         dy = self.y[:, :, None] - self.y[:, None, :]
-        dist = np.sqrt(dx * dx + dy * dy).astype(f32)
+        # Distances are compared SQUARED (float32 dx*dx + dy*dy against the float32 square of the radius): the
+        # reference compares float64 Euclidean norms (env_wrappers.py:133, 156; algo_ccppo.py:283), which is the same
+        # test in exact arithmetic, and the squared form has one rounding less than a float32 square root (fewer
+        # artificial ties in the nearest-neighbour order).
+        dist = (dx * dx + dy * dy).astype(f32)                     # squared
         eye = np.eye(A, dtype=bool)[None]
         pair = part[:, :, None] & part[:, None, :] & ~eye
-        inr = pair & (dist < cfg.neighbours_distance)
-        mf = inr & ~(dist > cfg.mf_nei_distance)
+        inr = pair & (dist < f32(cfg.neighbours_distance * cfg.neighbours_distance))
+        mf = inr & ~(dist > f32(cfg.mf_nei_distance * cfg.mf_nei_distance))
         bits = (np.uint64(1) << np.arange(A, dtype=np.uint64))[None, None, :]
         nei_mask = np.where(inr, bits, np.uint64(0)).sum(axis=2, dtype=np.uint64)
         mf_mask = np.where(mf, bits, np.uint64(0)).sum(axis=2, dtype=np.uint64)

@@ -178,3 +178,23 @@ def test_procedural_map_env():
     for t in range(30):
         oa, r, d, i = a.step({k: np.array([0.0, 0.8], np.float32) for k in a.vehicles})
     assert all("neighbours" in inf and 0.0 <= inf["route_completion"] <= 1.05 for inf in i.values())
+
+
+def test_attributes_the_reference_reads_off_a_metadrive_env():
+    """SURVEY.md 8b "Env attributes read by callers": `engine.global_seed`, `engine.current_map.road_network
+    .get_bounding_box()`, `agent_manager.next_agent_count`, besides `vehicles` / `.position`."""
+    env = envs.get_lcf_env(envs.MultiAgentIntersectionEnv)({"num_agents": 6, "start_seed": 5000, "delay_done": 0})
+    env.reset()
+    assert env.engine.global_seed == 5000 and env.agent_manager.next_agent_count == 6
+    box = env.engine.current_map.road_network.get_bounding_box()
+    assert len(box) == 4 and box[0] < box[1] and box[2] < box[3]
+    for k, v in env.vehicles.items():
+        assert box[0] - 5 <= v.position[0] <= box[1] + 5 and box[2] - 5 <= v.position[1] <= box[3] + 5
+    named = 6
+    for t in range(60):                                   # everybody steers off the road: respawns under fresh names
+        o, r, d, i = env.step({k: np.array([1.0, 1.0], np.float32) for k in env.vehicles})
+        named = max(named, max(int(k[5:]) for k in o) + 1)
+    assert env.agent_manager.next_agent_count == named > 6
+    env.reset()
+    assert env.engine.global_seed == 5001                 # the next episode of the same start seed
+    assert set(env.agent_manager.active_agents) == set(env.vehicles)
