@@ -106,6 +106,13 @@ __device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t by
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// Programmatic dependent launch (two-kernel mode): a kernel launched with the programmatic-serialisation attribute may
+// start while its predecessor in the stream is still running; everything it reads that the predecessor writes comes
+// after pdl_wait() (which returns when the predecessor has completed and its writes are visible).  Without the
+// attribute both are no-ops.  Rule kept by every kernel here: pdl_trigger() is only called when nothing the NEXT kernel
+// reads before its own pdl_wait() can still be written by this kernel or by anything before it.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 static constexpr int ENV_MAX_THREADS = 256;
 static constexpr int ENV_MAX_GROUP = 16;      // scene tag in a queue entry is 4 bits
@@ -210,6 +217,9 @@ env_step_kernel(const __grid_constant__ EnvConfig cfg, const __grid_constant__ E
     uint32_t parity = 0;
     if (tid == 0) mbar_init(bar, 1);
     for (int k = tid; k < 4 * G; k += NT) s_masks[k] = 0ull;
+    // two-kernel mode: the lidar kernel may start its prologue (laser table, barriers) now - it reads the record only
+    // after its own pdl_wait(), i.e. when this whole grid is done
+    if constexpr (SPLIT) pdl_trigger();
     __syncthreads();
     bool first = true;
     const int sl_a = tid / A, ia = tid - sl_a * A;       // this thread's (scene in group, slot)
@@ -230,6 +240,9 @@ env_step_kernel(const __grid_constant__ EnvConfig cfg, const __grid_constant__ E
             bulk_g2s(s_st, g_tiles, (uint32_t)ng * tile_bytes, bar);
             *s_nq = 0;
         }
+        // the map and the state tiles are already on their way; the actions (and every output buffer) belong to the
+        // kernel before this one in the stream until pdl_wait() returns
+        if constexpr (SPLIT) { if (first) pdl_wait(); }
         float act0 = 0.0f, act1 = 0.0f;
         if (has_agent && !cfg.do_reset) {
             float2 a = reinterpret_cast<const float2*>(io.actions)[(size_t)scene0 * A + tid];
@@ -457,14 +470,14 @@ env_lidar_kernel(const __grid_constant__ LidarIO io) {
         bulk_g2s(s_rec, io.pose + (size_t)scene0 * rec, (uint32_t)(ng * rec * 4), bar);
     };
     uint32_t parity = 0;
-    if (tid == 0) {
-        mbar_init(bar, 1);
-        if ((int)blockIdx.x < n_groups) fetch_record(blockIdx.x);  // in flight while the laser table loads
-    }
+    if (tid == 0) mbar_init(bar, 1);
     {
-        const float2* gr = reinterpret_cast<const float2*>(io.map + io.ray_off);
+        const float2* gr = reinterpret_cast<const float2*>(io.map + io.ray_off);     // the map is never rewritten
         for (int k = tid; k < n_ray; k += NT) s_ray[k] = gr[k];
     }
+    pdl_wait();                                                   // the state kernel's records are complete and visible
+    pdl_trigger();                                                // (so is everything before it: the next kernel may start)
+    if (tid == 0 && (int)blockIdx.x < n_groups) fetch_record(blockIdx.x);
     __syncthreads();
     const bool rows_vec = ((D & 3) == 0);                         // rows start 16-byte aligned
     const int n_cell = D >> 2;                                    // float4 cells per row (rows_vec)
@@ -679,6 +692,8 @@ struct b2c_env {
     int threads;
     int split;               // 1: two-kernel mode (state kernel + lidar kernel)
     int specialised;         // 1: the shape has its own kernel instantiation
+    int pdl;                 // two-kernel mode, programmatic dependent launch (B2C_ENV_PDL): bit 0 = the lidar kernel starts
+                             // while the state kernel drains, bit 1 = the state kernel starts while its predecessor drains
     int lidar_group, lidar_threads, lidar_ctas, ray_off;
     size_t lidar_smem;
     float* d_pose;
@@ -691,6 +706,19 @@ struct b2c_env {
     int num_sms;
     size_t smem;
 };
+
+// Launch with (or without) the programmatic-serialisation attribute: the kernel may begin while the one before it in
+// the stream drains (see pdl_wait / pdl_trigger).
+template <typename... KArgs, typename... Args>
+static void launch_pdl(void (*fn)(KArgs...), int grid, int threads, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3((unsigned)threads); lc.dynamicSmemBytes = smem; lc.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at; lc.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&lc, fn, args...);
+}
 
 extern "C" {
 
@@ -750,6 +778,10 @@ int b2c_env_create(const b2c_env_config* c, const uint32_t* map_blob, int map_wo
     e->step_fn = pick_step_kernel(e->split != 0, k.A, k.D, generic);
     e->lidar_fn = pick_lidar_kernel(k.A, k.D, generic);
     e->specialised = (e->step_fn != (e->split ? env_step_kernel<true, 0, 0> : env_step_kernel<false, 0, 0>)) ? 1 : 0;
+    // measured on B200 (profiles/r02_b_env_pdl.md): the lidar kernel gains ~3 % from starting early; the state kernel
+    // loses more than that when its CTAs take their places before the previous kernel is done, so only bit 0 is on
+    e->pdl = 1;
+    if (const char* t = getenv("B2C_ENV_PDL")) e->pdl = atoi(t) & 3;
     if (e->split) {
         B2C_CUDA_OR(cudaFuncSetAttribute(e->step_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem),
                     delete e);
@@ -807,7 +839,7 @@ static void launch_lidar(b2c_env* e, float* obs, uint32_t* obs_split, int kp, cu
     int lg = (cfg.S + e->lidar_group - 1) / e->lidar_group;
     int lgrid = e->num_sms * e->lidar_ctas;
     if (lgrid > lg) lgrid = lg;
-    e->lidar_fn<<<lgrid, e->lidar_threads, e->lidar_smem, st>>>(li);
+    launch_pdl(e->lidar_fn, lgrid, e->lidar_threads, e->lidar_smem, st, (e->pdl & 1) != 0, li);
 }
 
 static int launch_env(b2c_env* e, const float* actions, const b2c_env_io* o, int do_reset, int new_episode,
@@ -845,7 +877,7 @@ static int launch_env(b2c_env* e, const float* actions, const b2c_env_io* o, int
     if (!e->split) {
         e->step_fn<<<grid, e->threads, e->smem, st>>>(cfg, io);
     } else {
-        e->step_fn<<<grid, e->threads, e->smem, st>>>(cfg, io);
+        launch_pdl(e->step_fn, grid, e->threads, e->smem, st, (e->pdl & 2) != 0, cfg, io);
         B2C_CUDA(cudaGetLastError());
         launch_lidar(e, o->obs, io.obs_split, io.kp, st, first, count);
     }

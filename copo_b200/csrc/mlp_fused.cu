@@ -1,0 +1,373 @@
+// mlp_fused.cu - one kernel for the whole inference pass of a policy / value network (K5 of SURVEY.md 2.2):
+//
+//   out[M x n] = head( tanh( tanh( A[M x K] W1^T + b1 ) W2^T + b2 ) )          n = 4 (policy logits) or 1 (a value)
+//
+// and, for the rollout step, the Gaussian action sample and its log-probability on the 4 logits.  The two 256-wide
+// hidden layers never leave the SM: the first layer's accumulator is read from TMEM, biased, squashed, split into
+// bf16 [hi | lo] and written straight into the shared-memory ring as the A operand of the second layer's reduction
+// blocks (the SWIZZLE_128B K-major image a TMA load would have produced), while the second layer's weight blocks
+// arrive by TMA next to it.  Compared with tc_linear + tc_linear_head this removes the [M][512] bf16 hidden operand
+// from HBM (write + read, 1 KB per row each way) and one launch.  Same arithmetic, same order of the MMAs and the
+// same epilogue functions as the two-kernel path, so the results are bit-identical to it.
+//
+// Persistent, one CTA per SM, 128-row tiles, 640 threads:
+//   warp 0       TMA producer: per tile, kp1/64 stages {A_hi, A_lo, W1_hi, W1_lo} then 4 stages {W2_hi, W2_lo}
+//   warp 1       MMA issuer (one thread): layer 1 -> TMEM columns 0..255, layer 2 -> columns 256..511
+//   warp 2       TMEM allocation
+//   warps 4-11   epilogue 1: D1 -> +b1 -> tanh -> [hi | lo] -> ring (two column groups: reduction blocks 0,2 / 1,3)
+//   warps 12-19  epilogue 2: D2 -> +b2 -> tanh -> output layer -> (sample) -> global
+// so the first layer of tile i+1 runs on the tensor cores while epilogue 2 of tile i is still reading D2.
+//
+// Replaces: CCModel / CoPOModel forward without gradients (torch_copo/algo_ccppo.py:108-170, 201-219;
+// algo_copo.py:138-153) - compute_actions in the rollout, value predictions in postprocess_trajectory.
+#include "tc_common.cuh"
+
+namespace b2c {
+namespace tc {
+
+constexpr int F_EPI1 = 8, F_EPI2 = 8;
+constexpr int F_THREADS = 128 + (F_EPI1 + F_EPI2) * 32;
+constexpr int F_SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 2 * BLOCK_N * 4 /*biases*/ +
+                             HEAD_MAX * BLOCK_N * 4 /*head weights*/ + BLOCK_M * HEAD_MAX * 4 /*head partials*/;
+
+struct FusedArgs {
+    const float* b1;          // [256]
+    const float* b2;          // [256]
+    const float* head_w;      // [head_n][256]
+    const float* head_b;      // [head_n]
+    float* head_out;          // [M][head_n]
+    float* actions;           // [M][2] or null (head_n = 4)
+    float* logp;              // [M] or null
+    int M, kp1_blocks, head_n, products;
+    uint32_t seed, step;
+};
+
+__device__ __forceinline__ void fence_async_shared() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+__global__ void __launch_bounds__(F_THREADS, 1)
+tc_mlp2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w1,
+               const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ FusedArgs args) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* ring = smem;
+    uint8_t* misc = ring + STAGES * STAGE_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(misc);          // [STAGES] TMA bytes landed
+    uint64_t* empty = full + STAGES;                             // [STAGES] the stage's MMAs have retired
+    uint64_t* hfull = empty + STAGES;                            // [STAGES] the hidden block is in the stage's A half
+    uint64_t* d1_full = hfull + STAGES;
+    uint64_t* d1_empty = d1_full + 1;
+    uint64_t* d2_full = d1_empty + 1;
+    uint64_t* d2_empty = d2_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d2_empty + 1);
+    float* s_b1 = reinterpret_cast<float*>(misc + 256);
+    float* s_b2 = s_b1 + BLOCK_N;
+    float* s_head_w = s_b2 + BLOCK_N;                            // [HEAD_MAX][256]
+    float* s_part = s_head_w + HEAD_MAX * BLOCK_N;               // [128][HEAD_MAX]: the upper column group's partial sums
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_tiles = (args.M + BLOCK_M - 1) / BLOCK_M;
+    const int nb1 = args.kp1_blocks;
+    const int nb = nb1 + 4;                                      // reduction blocks (= ring stages used) per tile
+    const int kp1 = nb1 * BLOCK_K;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w1) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w2) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&hfull[s], 4); }
+        mbar_init(d1_full, 1); mbar_init(d1_empty, F_EPI1);
+        mbar_init(d2_full, 1); mbar_init(d2_empty, F_EPI2);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // everything above touches no global data; what follows may read what the previous kernel in the stream wrote
+    // (observations, freshly updated weights).  Launched with programmatic serialisation this kernel's prologue
+    // overlaps the previous kernel's tail; the next kernel may start its own prologue from here on.
+    griddep_wait();
+    griddep_trigger();
+    for (int i = threadIdx.x; i < BLOCK_N; i += F_THREADS) { s_b1[i] = args.b1[i]; s_b2[i] = args.b2[i]; }
+    for (int i = threadIdx.x; i < args.head_n * BLOCK_N; i += F_THREADS) s_head_w[i] = args.head_w[i];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_d1 = tmem_base, tmem_d2 = tmem_base + (uint32_t)BLOCK_N;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            uint32_t g = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                for (int b = 0; b < nb; ++b, ++g) {
+                    const int s = (int)(g & 1u);
+                    mbar_wait(&empty[s], ((g >> 1) & 1u) ^ 1u);
+                    uint8_t* st = ring + s * STAGE_BYTES;
+                    uint8_t* sw = st + 2 * A_STAGE_BYTES;
+                    if (b < nb1) {
+                        mbar_expect_tx(&full[s], (uint32_t)STAGE_BYTES);
+                        tma_load_2d(st, &map_a, b * BLOCK_K, tile * BLOCK_M, &full[s]);                          // A_hi
+                        tma_load_2d(st + A_STAGE_BYTES, &map_a, kp1 + b * BLOCK_K, tile * BLOCK_M, &full[s]);    // A_lo
+                        tma_load_2d(sw, &map_w1, b * BLOCK_K, 0, &full[s]);                                      // W1_hi
+                        tma_load_2d(sw + B_STAGE_BYTES, &map_w1, kp1 + b * BLOCK_K, 0, &full[s]);                // W1_lo
+                    } else {
+                        const int c = b - nb1;
+                        mbar_expect_tx(&full[s], (uint32_t)W_PAIR_BYTES);
+                        tma_load_2d(sw, &map_w2, c * BLOCK_K, 0, &full[s]);                                      // W2_hi
+                        tma_load_2d(sw + B_STAGE_BYTES, &map_w2, BLOCK_N + c * BLOCK_K, 0, &full[s]);            // W2_lo
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            uint32_t g = 0, t_local = 0;
+            uint32_t hcnt[STAGES] = {0u, 0u};                    // layer-2 uses of each stage so far (hfull phase)
+            auto issue_block = [&](int s, uint32_t tmem_d, bool first_block) {
+                const uint32_t sa = smem_u32(ring + s * STAGE_BYTES);
+                const uint32_t sw = sa + 2 * A_STAGE_BYTES;
+                const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + A_STAGE_BYTES);
+                const uint64_t w_hi = make_desc(sw), w_lo = make_desc(sw + B_STAGE_BYTES);
+#pragma unroll
+                for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                    const uint64_t o = (uint64_t)(k * 2);        // 32 B inside the 128 B swizzle row
+                    umma_bf16(tmem_d, a_hi + o, w_hi + o, IDESC, (first_block && k == 0) ? 0u : 1u);
+                    umma_bf16(tmem_d, a_lo + o, w_hi + o, IDESC, 1u);
+                    umma_bf16(tmem_d, a_hi + o, w_lo + o, IDESC, 1u);
+                    if (args.products == 4) umma_bf16(tmem_d, a_lo + o, w_lo + o, IDESC, 1u);
+                }
+                umma_commit(&empty[s]);                          // frees the stage when these MMAs retire
+            };
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t_local) {
+                // ---- layer 1 -> D1 (epilogue 1 is done with the previous tile's D1) ----
+                mbar_wait(d1_empty, (t_local & 1u) ^ 1u);
+                tc_fence_after();
+                for (int b = 0; b < nb1; ++b, ++g) {
+                    const int s = (int)(g & 1u);
+                    mbar_wait(&full[s], (g >> 1) & 1u);
+                    tc_fence_after();
+                    issue_block(s, tmem_d1, b == 0);
+                }
+                umma_commit(d1_full);
+                // ---- layer 2 -> D2 (epilogue 2 is done with the previous tile's D2) ----
+                mbar_wait(d2_empty, (t_local & 1u) ^ 1u);
+                tc_fence_after();
+                for (int c = 0; c < 4; ++c, ++g) {
+                    const int s = (int)(g & 1u);
+                    mbar_wait(&full[s], (g >> 1) & 1u);          // W2 block landed
+                    mbar_wait(&hfull[s], hcnt[s] & 1u);          // hidden block written by epilogue 1
+                    hcnt[s] += 1u;
+                    tc_fence_after();
+                    issue_block(s, tmem_d2, c == 0);
+                }
+                umma_commit(d2_full);
+            }
+        }
+    } else if (warp >= 4 && warp < 4 + F_EPI1) {
+        // ===== epilogue 1: D1 -> tanh -> [hi | lo] A operand of layer 2 =====
+        const int q = warp & 3;                                  // TMEM lane quarter = rows 32 q .. 32 q + 31 of the tile
+        const int grp = (warp - 4) >> 2;                         // column group: reduction blocks grp, grp + 2
+        const int r = q * 32 + lane;                             // row in the tile
+        const uint32_t row_off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
+        const uint32_t swz = (uint32_t)(r & 7);
+        uint32_t t_local = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t_local) {
+            mbar_wait(d1_full, t_local & 1u);
+            tc_fence_after();
+            const uint32_t taddr0 = tmem_d1 + ((uint32_t)(q * 32) << 16);
+            const uint32_t g_base = t_local * (uint32_t)nb + (uint32_t)nb1;
+#pragma unroll 1
+            for (int cc = 0; cc < 2; ++cc) {
+                const int c = grp + 2 * cc;                      // reduction block of layer 2 = hidden columns 64 c ..
+                const uint32_t g = g_base + (uint32_t)c;
+                const int s = (int)(g & 1u);
+                uint8_t* a_hi = ring + s * STAGE_BYTES + row_off;
+                uint8_t* a_lo = a_hi + A_STAGE_BYTES;
+#pragma unroll 1
+                for (int h = 0; h < 2; ++h) {                    // 32 columns at a time
+                    uint32_t rr[32];
+                    tmem_ld32(taddr0 + (uint32_t)(c * 64 + h * 32), rr);
+                    if (cc == 1 && h == 1) {                     // this warp's last read of D1: hand it back early
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(d1_empty);
+                    }
+                    float v[32];
+                    const float4* b4 = reinterpret_cast<const float4*>(s_b1 + c * 64 + h * 32);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float4 bb = b4[j];
+                        v[4 * j] = __uint_as_float(rr[4 * j]) + bb.x; v[4 * j + 1] = __uint_as_float(rr[4 * j + 1]) + bb.y;
+                        v[4 * j + 2] = __uint_as_float(rr[4 * j + 2]) + bb.z; v[4 * j + 3] = __uint_as_float(rr[4 * j + 3]) + bb.w;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = fast_tanh(v[j]);
+                    uint32_t hi[16], lo[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                        uint32_t hb = *reinterpret_cast<uint32_t*>(&h2);
+                        float r0 = v[2 * j] - __uint_as_float(hb << 16);
+                        float r1 = v[2 * j + 1] - __uint_as_float(hb & 0xffff0000u);
+                        __nv_bfloat162 l2 = __floats2bfloat162_rn(r0, r1);
+                        hi[j] = hb; lo[j] = *reinterpret_cast<uint32_t*>(&l2);
+                    }
+                    if (h == 0) mbar_wait(&empty[s], ((g >> 1) & 1u) ^ 1u);       // the stage's previous MMAs have retired
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {                // 16-byte chunks 4 h + j of the row, XOR-swizzled
+                        const uint32_t off = ((uint32_t)(4 * h + j) ^ swz) << 4;
+                        *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                        *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                    }
+                }
+                fence_async_shared();                            // generic-proxy stores -> visible to the tensor core
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&hfull[s]);
+            }
+        }
+    } else if (warp >= 4 + F_EPI1) {
+        // ===== epilogue 2: D2 -> tanh -> output layer (+ sample) =====
+        const int q = warp & 3;
+        const int grp = (warp - 4 - F_EPI1) >> 2;                // column group: chunks 4 grp .. 4 grp + 3
+        const int rloc = q * 32 + lane;
+        uint32_t t_local = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t_local) {
+            mbar_wait(d2_full, t_local & 1u);
+            tc_fence_after();
+            const int row = tile * BLOCK_M + rloc;
+            const bool live = row < args.M;
+            const uint32_t taddr0 = tmem_d2 + ((uint32_t)(q * 32) << 16);
+            float hacc[HEAD_MAX] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll 1
+            for (int c = 4 * grp; c < 4 * grp + 4; ++c) {
+                uint32_t rr[32];
+                tmem_ld32(taddr0 + (uint32_t)(c * 32), rr);
+                if (c == 4 * grp + 3) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(d2_empty);
+                }
+                float v[32];
+                const float4* b4 = reinterpret_cast<const float4*>(s_b2 + c * 32);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4 bb = b4[j];
+                    v[4 * j] = __uint_as_float(rr[4 * j]) + bb.x; v[4 * j + 1] = __uint_as_float(rr[4 * j + 1]) + bb.y;
+                    v[4 * j + 2] = __uint_as_float(rr[4 * j + 2]) + bb.z; v[4 * j + 3] = __uint_as_float(rr[4 * j + 3]) + bb.w;
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fast_tanh(v[j]);
+                for (int hj = 0; hj < args.head_n; ++hj) {
+                    const float4* w4 = reinterpret_cast<const float4*>(s_head_w + hj * BLOCK_N + c * 32);
+                    float a = hacc[hj];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float4 ww = w4[j];
+                        a = fmaf(v[4 * j], ww.x, a); a = fmaf(v[4 * j + 1], ww.y, a);
+                        a = fmaf(v[4 * j + 2], ww.z, a); a = fmaf(v[4 * j + 3], ww.w, a);
+                    }
+                    hacc[hj] = a;
+                }
+            }
+            // the upper column group hands its partial sums to the lower one (named barrier 2 = epilogue 2)
+            if (grp == 1) {
+#pragma unroll
+                for (int hj = 0; hj < HEAD_MAX; ++hj) s_part[rloc * HEAD_MAX + hj] = hacc[hj];
+            }
+            asm volatile("bar.sync 2, %0;" ::"n"(F_EPI2 * 32) : "memory");
+            if (grp == 0 && live) {
+                float o[HEAD_MAX];
+#pragma unroll
+                for (int hj = 0; hj < HEAD_MAX; ++hj) {
+                    float t = hacc[hj] + s_part[rloc * HEAD_MAX + hj];
+                    o[hj] = (hj < args.head_n) ? t + args.head_b[hj] : 0.0f;
+                }
+                if (args.head_n == 4) {
+                    reinterpret_cast<float4*>(args.head_out)[row] = make_float4(o[0], o[1], o[2], o[3]);
+                    if (args.actions) {
+                        float e0, e1;
+                        normal2(args.seed, args.step, (uint32_t)row, e0, e1);
+                        float s0 = expf(o[2]), s1 = expf(o[3]);
+                        float a0 = o[0] + s0 * e0, a1 = o[1] + s1 * e1;
+                        float z0 = (a0 - o[0]) / s0, z1 = (a1 - o[1]) / s1;
+                        reinterpret_cast<float2*>(args.actions)[row] = make_float2(a0, a1);
+                        if (args.logp) args.logp[row] = -0.5f * (z0 * z0 + z1 * z1) - 1.8378770664093453f - (o[2] + o[3]);
+                    }
+                } else {
+                    for (int hj = 0; hj < args.head_n; ++hj) args.head_out[(size_t)row * args.head_n + hj] = o[hj];
+                }
+            }
+            asm volatile("bar.sync 2, %0;" ::"n"(F_EPI2 * 32) : "memory");
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+}  // namespace tc
+}  // namespace b2c
+
+using namespace b2c::tc;
+
+extern "C" {
+
+int b2c_tc_mlp2_head(const uint16_t* a_split, int Kp1, const uint16_t* w1_prep, const float* b1, const uint16_t* w2_prep,
+                     const float* b2, const b2c_tc_head* head, int M, void* stream) {
+    if (M == 0) return B2C_OK;
+    if (!a_split || !w1_prep || !w2_prep || !b1 || !b2 || M < 0 || Kp1 < BLOCK_K || Kp1 % BLOCK_K)
+        return b2c_set_error(B2C_ERR_ARG, "b2c_tc_mlp2_head: bad argument");
+    if (!head || !head->weight || !head->bias || !head->out || (head->n != 1 && head->n != 4))
+        return b2c_set_error(B2C_ERR_ARG, "b2c_tc_mlp2_head: the output layer needs weight, bias, out and n in {1, 4}");
+    if (head->actions && head->n != 4) return b2c_set_error(B2C_ERR_ARG, "b2c_tc_mlp2_head: sampling needs the 4 policy logits");
+    if (((uintptr_t)a_split | (uintptr_t)w1_prep | (uintptr_t)w2_prep | (uintptr_t)head->out | (uintptr_t)head->actions) & 15)
+        return b2c_set_error(B2C_ERR_ARG, "b2c_tc_mlp2_head: pointers must be 16-byte aligned");
+    static int attr_set = 0;
+    static int num_sms = 0;
+    if (!attr_set) {
+        B2C_CUDA(cudaFuncSetAttribute(tc_mlp2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_BYTES));
+        int dev = 0;
+        B2C_CUDA(cudaGetDevice(&dev));
+        B2C_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+        attr_set = 1;
+    }
+    CUtensorMap map_a, map_w1, map_w2;
+    int rc = make_map(&map_a, a_split, (uint64_t)M, (uint64_t)2 * Kp1, BLOCK_M);
+    if (rc) return rc;
+    rc = make_map(&map_w1, w1_prep, (uint64_t)BLOCK_N, (uint64_t)2 * Kp1, BLOCK_N);
+    if (rc) return rc;
+    rc = make_map(&map_w2, w2_prep, (uint64_t)BLOCK_N, (uint64_t)2 * BLOCK_N, BLOCK_N);
+    if (rc) return rc;
+    static const int products = getenv("B2C_TC_PRODUCTS") ? atoi(getenv("B2C_TC_PRODUCTS")) : 4;
+    static const bool pdl = !(getenv("B2C_TC_PDL") && atoi(getenv("B2C_TC_PDL")) == 0);
+    FusedArgs a;
+    a.b1 = b1; a.b2 = b2; a.head_w = head->weight; a.head_b = head->bias; a.head_out = head->out;
+    a.actions = head->actions; a.logp = head->logp; a.M = M; a.kp1_blocks = Kp1 / BLOCK_K; a.head_n = head->n;
+    a.products = products == 3 ? 3 : 4;
+    a.seed = head->seed; a.step = head->step;
+    const int tiles = (M + BLOCK_M - 1) / BLOCK_M;
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3((unsigned)(tiles < num_sms ? tiles : num_sms));
+    lc.blockDim = dim3((unsigned)F_THREADS);
+    lc.dynamicSmemBytes = F_SMEM_BYTES;
+    lc.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at; lc.numAttrs = pdl ? 1 : 0;
+    B2C_CUDA(cudaLaunchKernelEx(&lc, tc_mlp2_kernel, map_a, map_w1, map_w2, a));
+    return B2C_OK;
+}
+
+}  // extern "C"

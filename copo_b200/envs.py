@@ -150,9 +150,14 @@ class MultiAgentDrivingEnv:
             acted = bool(f & FLAG_VALID)
             r[k] = float(rew[i]) if acted else 0.0
             d[k] = bool(f & FLAG_DONE)
-            pos = np.array([ff[F_X, i], ff[F_Y, i]], np.float64)
             others = [j for j in part if j != i and (int(nei_mask[i]) >> j) & 1]
-            dist = {j: float(np.linalg.norm(pos - np.array([ff[F_X, j], ff[F_Y, j]], np.float64))) for j in others}
+            # distances as the kernel takes them (float32 squared distance, sim_core.cuh phase_neighbours), square root
+            # in float64: `dist > r` here decides exactly like `d2 > r * r` there, so the masks the kernel emits
+            # (nei_mask, mf_mask, nei_list) and the lists a host-side consumer derives from these infos agree, ties on
+            # the spawn grid included
+            dx, dy = ff[F_X, i] - ff[F_X, others], ff[F_Y, i] - ff[F_Y, others]
+            d2 = (dx * dx + dy * dy).astype(np.float32)
+            dist = {j: float(np.sqrt(np.float64(d2[n]))) for n, j in enumerate(others)}
             order = sorted(others, key=lambda j: dist[j])
             total = float(route_len[int(fld[F_ROUTE, i])])
             cur = float(ff[F_DONE_LEN, i] + ff[F_S, i])

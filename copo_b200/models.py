@@ -15,7 +15,13 @@ import math
 import numpy as np
 import torch
 
+import os
+
 from . import ops
+
+# inference passes (rollout actions, value predictions) run the one-kernel network (mlp_fused.cu); B2C_TC_FUSED=0 falls
+# back to the layer-by-layer kernels (same bits) for A/B measurements
+FUSED_INFERENCE = os.environ.get("B2C_TC_FUSED", "1") != "0"
 
 
 def centralized_critic_obs_dim(obs_dim, act_dim, counterfactual=True, num_neighbours=4, fuse_mode="mf"):
@@ -78,6 +84,10 @@ class _Net:
         if tc_version is not None and self.tc_ok():
             w1, w2, _ = self.tc_weights(tc_version)
             s0 = x_split if x_split is not None else ops.tc_split_rows(x)
+            if self.out_dim in (1, 4) and FUSED_INFERENCE:       # one kernel, the hidden layers never leave the SM
+                out, actions, logp = ops.tc_mlp2_head(s0, w1, self.b[0], w2, self.b[1], self.W[2], self.b[2], sample=sample,
+                                                      out=out, actions=actions, logp=logp)
+                return out if sample is None else (out, actions, logp)
             _, s1 = ops.tc_linear(s0, w1, self.b[0], act=1, want_f32=False, want_split=True)
             if self.out_dim in (1, 4):       # the narrow output layer rides in the layer-2 epilogue
                 out, actions, logp, _ = ops.tc_linear_head(s1, w2, self.b[1], self.W[2], self.b[2], act=1, sample=sample,

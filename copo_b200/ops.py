@@ -357,3 +357,31 @@ def tc_linear_head(a_split, w_prep, bias, head_w, head_b, act=1, sample=None, wa
     _lib.check(lib.b2c_tc_linear_head(P(a_split), P(w_prep), P(bias), P(h), c_int(256 if want_f32 else 0), c_int(M),
                                       c_int(Kp), c_int(act), ctypes.byref(hd), _lib.stream_ptr()))
     return out, actions, logp, h
+
+
+def tc_mlp2_head(a_split, w1_prep, b1, w2_prep, b2, head_w, head_b, sample=None, out=None, actions=None, logp=None):
+    """The whole inference pass of a 256-256 tanh network in ONE kernel (mlp_fused.cu): both hidden layers stay on the
+    SM, the narrow output layer (n = 1 or 4) and - with sample = (seed, step) - the Gaussian action draw ride in the last
+    epilogue.  Bit-identical to tc_linear + tc_linear_head.  Returns (head_out [M, n], actions or None, logp or None)."""
+    lib = _lib_ready()
+    M, two_kp = a_split.shape
+    Kp = two_kp // 2
+    n = head_w.shape[0]
+    dev = a_split.device
+    assert a_split.dtype == torch.bfloat16 and a_split.is_contiguous()
+    assert w1_prep.shape == (256, 2 * Kp) and w2_prep.shape == (256, 512) and head_w.shape == (n, 256)
+    assert w1_prep.is_contiguous() and w2_prep.is_contiguous() and head_w.is_contiguous()
+    if out is None:
+        out = torch.empty((M, n), dtype=torch.float32, device=dev)
+    hd = TcHead()
+    hd.weight, hd.bias, hd.out, hd.n = head_w.data_ptr(), head_b.data_ptr(), out.data_ptr(), n
+    if sample is not None:
+        if actions is None:
+            actions = torch.empty((M, 2), dtype=torch.float32, device=dev)
+        if logp is None:
+            logp = torch.empty((M,), dtype=torch.float32, device=dev)
+        hd.actions, hd.logp = actions.data_ptr(), logp.data_ptr()
+        hd.seed, hd.step = sample[0] & 0xFFFFFFFF, sample[1] & 0xFFFFFFFF
+    _lib.check(lib.b2c_tc_mlp2_head(P(a_split), c_int(Kp), P(w1_prep), P(b1), P(w2_prep), P(b2), ctypes.byref(hd), c_int(M),
+                                    _lib.stream_ptr()))
+    return out, actions, logp

@@ -245,6 +245,12 @@ typedef struct {
 } b2c_tc_head;
 int b2c_tc_linear_head(const uint16_t* a_split, const uint16_t* w_prep, const float* bias, float* out_f32, int ld_out,
                        int M, int Kp, int act, const b2c_tc_head* head, void* stream);
+/* The whole inference pass of a [K]-256-256-n tanh network in one kernel (n in {1, 4}; replaces CCModel / CoPOModel
+ * forward without gradients, algo_ccppo.py:201-219, algo_copo.py:138-153): head.out = head(tanh(tanh(a W1^T + b1) W2^T + b2)),
+ * plus the action sample when head.actions is set.  The hidden layers stay in tensor memory / shared memory; results are
+ * bit-identical to b2c_tc_linear followed by b2c_tc_linear_head.  w1_prep [256][2*Kp1], w2_prep [256][512]. */
+int b2c_tc_mlp2_head(const uint16_t* a_split, int Kp1, const uint16_t* w1_prep, const float* b1, const uint16_t* w2_prep,
+                     const float* b2, const b2c_tc_head* head, int M, void* stream);
 /* Weight gradient of a 256-wide layer on the tensor cores: dW[256][K] += dz^T x from the [hi | lo] operands
  * (dz_split [M][512], x_split [M][2*Kp], Kp <= 256).  workspace: b2c_tc_wgrad_parts() * 256 * Kp floats; the
  * per-CTA partial sums are added in a fixed order (deterministic). */

@@ -126,3 +126,34 @@ def test_tc_fused_head_and_sample(M):
     assert torch.equal(a2, actions) and torch.equal(l2, logits)
     v, _, _, _ = ops.tc_linear_head(a, w, b2, W3[:1].contiguous(), b3[:1].contiguous(), act=1)
     assert float((v[:, 0] - want[:, 0]).abs().max()) < 2e-5
+
+
+@pytest.mark.parametrize("M,K", [(1, 92), (129, 92), (5000, 157), (148 * 128 * 2 + 77, 92), (4096, 40), (3000, 184)])
+def test_tc_one_kernel_network_matches_the_layer_kernels(M, K):
+    """mlp_fused.cu: obs -> 256 tanh -> 256 tanh -> logits (+ sample) in one kernel, the hidden operand handed over in
+    shared memory, against tc_linear + tc_linear_head (same MMAs in the same order, same epilogue functions; only the
+    output layer's 256-term sum is split over two column groups instead of four, so the last bits can differ); and
+    against float64 within the split-bf16 budget.  Covers ragged tile tails, 1..3 first-layer reduction blocks (odd and
+    even stage parity of the ring across tiles) and both output widths."""
+    from copo_b200 import ops
+    g = torch.Generator().manual_seed(M + K)
+    x = (torch.rand(M, K, generator=g) * 2 - 1).cuda()
+    W1, b1 = (torch.randn(256, K, generator=g) / K ** 0.5).cuda(), (0.1 * torch.randn(256, generator=g)).cuda()
+    W2, b2 = (torch.randn(256, 256, generator=g) / 16).cuda(), (0.1 * torch.randn(256, generator=g)).cuda()
+    W3, b3 = (torch.randn(4, 256, generator=g) / 16).cuda(), (0.1 * torch.randn(4, generator=g)).cuda()
+    a, w1, w2 = ops.tc_split_rows(x), ops.tc_prep_weight(W1), ops.tc_prep_weight(W2)
+    _, s1 = ops.tc_linear(a, w1, b1, act=1, want_f32=False, want_split=True)
+    want, wact, wlogp, _ = ops.tc_linear_head(s1, w2, b2, W3, b3, act=1, sample=(7, 3))
+    first = None
+    for rep in range(3):                                    # same bits on every launch
+        got, act, logp = ops.tc_mlp2_head(a, w1, b1, w2, b2, W3, b3, sample=(7, 3))
+        assert float((got - want).abs().max()) < 2e-6 and float((act - wact).abs().max()) < 1e-5
+        assert float((logp - wlogp).abs().max()) < 1e-4
+        if first is None:
+            first = (got.clone(), act.clone(), logp.clone())
+        assert torch.equal(got, first[0]) and torch.equal(act, first[1]) and torch.equal(logp, first[2])
+    ref = _ref(_ref(_ref(x.cpu(), W1.cpu(), b1.cpu(), 1), W2.cpu(), b2.cpu(), 1), W3.cpu(), b3.cpu(), 0)
+    assert float((got.cpu().double() - ref).abs().max()) < 2e-5
+    v, _, _ = ops.tc_mlp2_head(a, w1, b1, w2, b2, W3[:1].contiguous(), b3[:1].contiguous())
+    wv, _, _, _ = ops.tc_linear_head(s1, w2, b2, W3[:1].contiguous(), b3[:1].contiguous(), act=1)
+    assert float((v - wv).abs().max()) < 2e-6

@@ -20,7 +20,8 @@ def _rollout(env, pol, T, seed=0):
                             "nei_list", "action_logp", "action_dist_inputs")}
     slot_rows = []                                          # per step: {agent name: slot}
     for t in range(T):
-        names = sorted(obs.keys(), key=lambda k: env._slot_of[k])
+        # agents that act this step (a terminated agent's last observation is returned once more, without a slot)
+        names = sorted((k for k in obs if k in env._slot_of), key=lambda k: env._slot_of[k])
         slots = [env._slot_of[k] for k in names]
         x = torch.as_tensor(np.stack([obs[k] for k in names]), device=dev)
         act, logp, logits = pol.compute_actions(x, step=t)
@@ -84,6 +85,9 @@ def test_per_trajectory_postprocess_equals_the_batched_rollout_form(algo, env_na
     for name in pol.model.nets:                             # non-trivial critics: O(1) values
         if name != "policy":
             pol.model.nets[name].W[2].mul_(200.0)
+    # a policy that floors the throttle and steers to one side (std 0.3): agents leave the road or crash within a few
+    # dozen steps, so slots are respawned under fresh names inside the recorded window
+    pol.model.nets["policy"].b[2].copy_(torch.tensor([0.5, 1.0, -1.2, -1.2], device=pol.device))
     batches, ro, slot_rows = _rollout(env, pol, T=70)
     assert len(batches) > 16                                # respawned agents: more names than slots
     ro = pol.postprocess_rollout(ro)
