@@ -8,7 +8,8 @@
 // blocks (the SWIZZLE_128B K-major image a TMA load would have produced), while the second layer's weight blocks
 // arrive by TMA next to it.  Compared with tc_linear + tc_linear_head this removes the [M][512] bf16 hidden operand
 // from HBM (write + read, 1 KB per row each way) and one launch.  Same arithmetic, same order of the MMAs and the
-// same epilogue functions as the two-kernel path, so the results are bit-identical to it.
+// same epilogue functions as the two-kernel path: the hidden layers are bit-identical to it, the 256-term sum of the
+// output layer is grouped differently (last-bit differences).
 //
 // Persistent, one CTA per SM, 128-row tiles, 640 threads:
 //   warp 0       TMA producer: per tile, kp1/64 stages {A_hi, A_lo, W1_hi, W1_lo} then 4 stages {W2_hi, W2_lo}
@@ -42,6 +43,14 @@ struct FusedArgs {
     uint32_t seed, step;
 };
 
+// epilogue warps wait with a back-off: a failed probe sleeps instead of spinning on issue slots the other epilogue's
+// warps could use
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\tnanosleep.u32 64;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
 __device__ __forceinline__ void fence_async_shared() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -130,7 +139,7 @@ tc_mlp2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // ===== MMA issuer =====
         if (lane == 0) {
             uint32_t g = 0, t_local = 0;
-            uint32_t hcnt[STAGES] = {0u, 0u};                    // layer-2 uses of each stage so far (hfull phase)
+            uint32_t hcnt0 = 0u, hcnt1 = 0u;                     // layer-2 uses of each stage so far (hfull phase)
             auto issue_block = [&](int s, uint32_t tmem_d, bool first_block) {
                 const uint32_t sa = smem_u32(ring + s * STAGE_BYTES);
                 const uint32_t sw = sa + 2 * A_STAGE_BYTES;
@@ -163,8 +172,8 @@ tc_mlp2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 for (int c = 0; c < 4; ++c, ++g) {
                     const int s = (int)(g & 1u);
                     mbar_wait(&full[s], (g >> 1) & 1u);          // W2 block landed
-                    mbar_wait(&hfull[s], hcnt[s] & 1u);          // hidden block written by epilogue 1
-                    hcnt[s] += 1u;
+                    mbar_wait(&hfull[s], (s ? hcnt1 : hcnt0) & 1u);      // hidden block written by epilogue 1
+                    if (s) hcnt1 += 1u; else hcnt0 += 1u;
                     tc_fence_after();
                     issue_block(s, tmem_d2, c == 0);
                 }
@@ -180,7 +189,7 @@ tc_mlp2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const uint32_t swz = (uint32_t)(r & 7);
         uint32_t t_local = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t_local) {
-            mbar_wait(d1_full, t_local & 1u);
+            mbar_wait_backoff(d1_full, t_local & 1u);
             tc_fence_after();
             const uint32_t taddr0 = tmem_d1 + ((uint32_t)(q * 32) << 16);
             const uint32_t g_base = t_local * (uint32_t)nb + (uint32_t)nb1;
@@ -200,27 +209,18 @@ tc_mlp2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         __syncwarp();
                         if (lane == 0) mbar_arrive(d1_empty);
                     }
-                    float v[32];
-                    const float4* b4 = reinterpret_cast<const float4*>(s_b1 + c * 64 + h * 32);
+                    // bias, tanh and the [hi | lo] split on column pairs (fma.rn.f32x2: two columns per instruction)
+                    uint32_t hi[16], lo[16];
+                    const ulonglong2* bp = reinterpret_cast<const ulonglong2*>(s_b1 + c * 64 + h * 32);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        float4 bb = b4[j];
-                        v[4 * j] = __uint_as_float(rr[4 * j]) + bb.x; v[4 * j + 1] = __uint_as_float(rr[4 * j + 1]) + bb.y;
-                        v[4 * j + 2] = __uint_as_float(rr[4 * j + 2]) + bb.z; v[4 * j + 3] = __uint_as_float(rr[4 * j + 3]) + bb.w;
+                        const ulonglong2 bb = bp[j];
+                        const uint64_t t0 = fast_tanh2(add2(pk2(__uint_as_float(rr[4 * j]), __uint_as_float(rr[4 * j + 1])), bb.x));
+                        const uint64_t t1 = fast_tanh2(add2(pk2(__uint_as_float(rr[4 * j + 2]), __uint_as_float(rr[4 * j + 3])), bb.y));
+                        split2(t0, hi[2 * j], lo[2 * j]);
+                        split2(t1, hi[2 * j + 1], lo[2 * j + 1]);
                     }
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = fast_tanh(v[j]);
-                    uint32_t hi[16], lo[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-                        uint32_t hb = *reinterpret_cast<uint32_t*>(&h2);
-                        float r0 = v[2 * j] - __uint_as_float(hb << 16);
-                        float r1 = v[2 * j + 1] - __uint_as_float(hb & 0xffff0000u);
-                        __nv_bfloat162 l2 = __floats2bfloat162_rn(r0, r1);
-                        hi[j] = hb; lo[j] = *reinterpret_cast<uint32_t*>(&l2);
-                    }
-                    if (h == 0) mbar_wait(&empty[s], ((g >> 1) & 1u) ^ 1u);       // the stage's previous MMAs have retired
+                    if (h == 0) mbar_wait_backoff(&empty[s], ((g >> 1) & 1u) ^ 1u);   // the stage's previous MMAs have retired
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {                // 16-byte chunks 4 h + j of the row, XOR-swizzled
                         const uint32_t off = ((uint32_t)(4 * h + j) ^ swz) << 4;
@@ -240,12 +240,12 @@ tc_mlp2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int rloc = q * 32 + lane;
         uint32_t t_local = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t_local) {
-            mbar_wait(d2_full, t_local & 1u);
+            mbar_wait_backoff(d2_full, t_local & 1u);
             tc_fence_after();
             const int row = tile * BLOCK_M + rloc;
             const bool live = row < args.M;
             const uint32_t taddr0 = tmem_d2 + ((uint32_t)(q * 32) << 16);
-            float hacc[HEAD_MAX] = {0.0f, 0.0f, 0.0f, 0.0f};
+            uint64_t hacc2[HEAD_MAX] = {0ull, 0ull, 0ull, 0ull};
 #pragma unroll 1
             for (int c = 4 * grp; c < 4 * grp + 4; ++c) {
                 uint32_t rr[32];
@@ -255,27 +255,42 @@ tc_mlp2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     __syncwarp();
                     if (lane == 0) mbar_arrive(d2_empty);
                 }
-                float v[32];
-                const float4* b4 = reinterpret_cast<const float4*>(s_b2 + c * 32);
+                uint64_t vv[16];
+                const ulonglong2* bp = reinterpret_cast<const ulonglong2*>(s_b2 + c * 32);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    float4 bb = b4[j];
-                    v[4 * j] = __uint_as_float(rr[4 * j]) + bb.x; v[4 * j + 1] = __uint_as_float(rr[4 * j + 1]) + bb.y;
-                    v[4 * j + 2] = __uint_as_float(rr[4 * j + 2]) + bb.z; v[4 * j + 3] = __uint_as_float(rr[4 * j + 3]) + bb.w;
+                    const ulonglong2 bb = bp[j];
+                    vv[2 * j] = fast_tanh2(add2(pk2(__uint_as_float(rr[4 * j]), __uint_as_float(rr[4 * j + 1])), bb.x));
+                    vv[2 * j + 1] = fast_tanh2(add2(pk2(__uint_as_float(rr[4 * j + 2]), __uint_as_float(rr[4 * j + 3])), bb.y));
                 }
+                // output layer: (even column, odd column) partial sums per output
+                if (args.head_n == 4) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = fast_tanh(v[j]);
-                for (int hj = 0; hj < args.head_n; ++hj) {
-                    const float4* w4 = reinterpret_cast<const float4*>(s_head_w + hj * BLOCK_N + c * 32);
-                    float a = hacc[hj];
+                    for (int hj = 0; hj < 4; ++hj) {
+                        const ulonglong2* wp = reinterpret_cast<const ulonglong2*>(s_head_w + hj * BLOCK_N + c * 32);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const ulonglong2 ww = wp[j];
+                            hacc2[hj] = fma2(vv[2 * j], ww.x, hacc2[hj]);
+                            hacc2[hj] = fma2(vv[2 * j + 1], ww.y, hacc2[hj]);
+                        }
+                    }
+                } else {
+                    const ulonglong2* wp = reinterpret_cast<const ulonglong2*>(s_head_w + c * 32);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        float4 ww = w4[j];
-                        a = fmaf(v[4 * j], ww.x, a); a = fmaf(v[4 * j + 1], ww.y, a);
-                        a = fmaf(v[4 * j + 2], ww.z, a); a = fmaf(v[4 * j + 3], ww.w, a);
+                        const ulonglong2 ww = wp[j];
+                        hacc2[0] = fma2(vv[2 * j], ww.x, hacc2[0]);
+                        hacc2[0] = fma2(vv[2 * j + 1], ww.y, hacc2[0]);
                     }
-                    hacc[hj] = a;
                 }
+            }
+            float hacc[HEAD_MAX];
+#pragma unroll
+            for (int hj = 0; hj < HEAD_MAX; ++hj) {
+                float e, o;
+                upk2(hacc2[hj], e, o);
+                hacc[hj] = e + o;
             }
             // the upper column group hands its partial sums to the lower one (named barrier 2 = epilogue 2)
             if (grp == 1) {
@@ -302,7 +317,7 @@ tc_mlp2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         if (args.logp) args.logp[row] = -0.5f * (z0 * z0 + z1 * z1) - 1.8378770664093453f - (o[2] + o[3]);
                     }
                 } else {
-                    for (int hj = 0; hj < args.head_n; ++hj) args.head_out[(size_t)row * args.head_n + hj] = o[hj];
+                    args.head_out[row] = o[0];                   // head_n = 1
                 }
             }
             asm volatile("bar.sync 2, %0;" ::"n"(F_EPI2 * 32) : "memory");

@@ -95,10 +95,23 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// clamp to [-9, 9] in one instruction: min(|x|, 9) with the sign of x
+__device__ __forceinline__ float clamp9(float x) {
+    float y;
+    asm("min.xorsign.abs.f32 %0, %1, %2;" : "=f"(y) : "f"(x), "f"(9.0f));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ float fast_tanh(float x) {
     // odd rational minimax (13/6) on [-9, 9]: relative error < 4e-7 down to the smallest arguments (an exp-based
-    // form loses relative accuracy near 0, which the value heads then amplify); checked in tests/test_tc_gpu.py
-    x = fminf(fmaxf(x, -9.0f), 9.0f);
+    // form loses relative accuracy near 0, which the value heads then amplify); checked in tests/test_tc_gpu.py.
+    // The denominator lies in [4.8e-3, 1.7], so the plain reciprocal approximation (no range scaling) is exact enough;
+    // fast_tanh2 below performs the same operations on two values at once and returns the same bits.
+    x = clamp9(x);
     const float x2 = x * x;
     float p = -2.76076847742355e-16f;
     p = fmaf(p, x2, 2.00018790482477e-13f);
@@ -112,7 +125,7 @@ __device__ __forceinline__ float fast_tanh(float x) {
     q = fmaf(q, x2, 1.18534705686654e-04f);
     q = fmaf(q, x2, 2.26843463243900e-03f);
     q = fmaf(q, x2, 4.89352518554385e-03f);
-    return __fdividef(p, q);
+    return p * rcp_approx(q);
 }
 // 32-byte global store (sm_100: STG.256): one thread fills a whole 32-byte sector, so the row-per-thread epilogue
 // writes full sectors instead of two half-filled ones per 16-byte store pair
@@ -123,9 +136,9 @@ __device__ __forceinline__ void st_global_256(void* p, uint32_t a0, uint32_t a1,
                  : "memory");
 }
 // ---- packed fp32 pairs (sm_100: fma / mul / add .f32x2, SASS FFMA2 / FMUL2 / FADD2) -----------------------------------
-// EXPERIMENTAL (B2C_TC_PACKED=1; off by default, not measured yet): the epilogue's bias add, rational tanh and fused
-// output layer on two columns per instruction.  Same operations per element as the scalar path, so the results agree
-// up to the output layer's summation order and the division (rcp.approx * p instead of div.approx).
+// The epilogues' bias add, rational tanh, [hi | lo] split and fused output layer on two columns per instruction.  Same
+// operations per element as the scalar forms, so the hidden layers come out bit-identical; the fused output layer sums
+// even and odd columns separately (last-bit differences).
 __device__ __forceinline__ uint64_t pk2(float lo, float hi) {
     uint64_t r;
     asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
@@ -151,9 +164,7 @@ __device__ __forceinline__ uint64_t bc2(float x) { return pk2(x, x); }
 __device__ __forceinline__ uint64_t fast_tanh2(uint64_t x) {
     float x0, x1;
     upk2(x, x0, x1);
-    x0 = fminf(fmaxf(x0, -9.0f), 9.0f);
-    x1 = fminf(fmaxf(x1, -9.0f), 9.0f);
-    x = pk2(x0, x1);
+    x = pk2(clamp9(x0), clamp9(x1));
     const uint64_t x2 = mul2(x, x);
     uint64_t p = bc2(-2.76076847742355e-16f);
     p = fma2(p, x2, bc2(2.00018790482477e-13f));
@@ -167,11 +178,20 @@ __device__ __forceinline__ uint64_t fast_tanh2(uint64_t x) {
     q = fma2(q, x2, bc2(1.18534705686654e-04f));
     q = fma2(q, x2, bc2(2.26843463243900e-03f));
     q = fma2(q, x2, bc2(4.89352518554385e-03f));
-    float q0, q1, r0, r1;
+    float q0, q1;
     upk2(q, q0, q1);
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(q0));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(q1));
-    return mul2(p, pk2(r0, r1));
+    return mul2(p, pk2(rcp_approx(q0), rcp_approx(q1)));
+}
+// two fp32 values -> bf16 pairs hi = bf16(v), lo = bf16(v - hi) (the [hi | lo] operand split; v - hi is exact)
+__device__ __forceinline__ void split2(uint64_t v, uint32_t& hi, uint32_t& lo) {
+    float v0, v1, r0, r1;
+    upk2(v, v0, v1);
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
+    hi = *reinterpret_cast<uint32_t*>(&h2);
+    const uint64_t r = fma2(pk2(__uint_as_float(hi << 16), __uint_as_float(hi & 0xffff0000u)), bc2(-1.0f), v);
+    upk2(r, r0, r1);
+    __nv_bfloat162 l2 = __floats2bfloat162_rn(r0, r1);
+    lo = *reinterpret_cast<uint32_t*>(&l2);
 }
 __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
     return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
