@@ -15,9 +15,11 @@
 //   warp 0       TMA producer: per tile, kp1/64 stages {A_hi, A_lo, W1_hi, W1_lo} then 4 stages {W2_hi, W2_lo}
 //   warp 1       MMA issuer (one thread): layer 1 -> TMEM columns 0..255, layer 2 -> columns 256..511
 //   warp 2       TMEM allocation
-//   warps 4-11   epilogue 1: D1 -> +b1 -> tanh -> [hi | lo] -> ring (two column groups: reduction blocks 0,2 / 1,3)
-//   warps 12-19  epilogue 2: D2 -> +b2 -> tanh -> output layer -> (sample) -> global
-// so the first layer of tile i+1 runs on the tensor cores while epilogue 2 of tile i is still reading D2.
+//   warp 3       finaliser: sums the output layer's partial sums, adds the bias, samples, writes the rows
+//   warps 4-19   epilogue (4 TMEM lane quarters x 4 column groups), per tile: first D1 -> +b1 -> tanh -> [hi | lo] ->
+//                ring, all 16 warps on one reduction block at a time (the tensor core idles until the first block is
+//                there: measured timeline in profiles/r02_c_fused_trace.md); then D2 -> +b2 -> tanh -> partial sums
+// so the first layer of tile i+1 runs on the tensor cores while the epilogue warps are still on D2 of tile i.
 //
 // Replaces: CCModel / CoPOModel forward without gradients (torch_copo/algo_ccppo.py:108-170, 201-219;
 // algo_copo.py:138-153) - compute_actions in the rollout, value predictions in postprocess_trajectory.
@@ -26,10 +28,12 @@
 namespace b2c {
 namespace tc {
 
-constexpr int F_EPI1 = 8, F_EPI2 = 8;
-constexpr int F_THREADS = 128 + (F_EPI1 + F_EPI2) * 32;
+constexpr int F_EPI = 16;                                 // epilogue warps: 4 TMEM lane quarters x 4 column groups
+constexpr int F_GROUPS = F_EPI / 4;
+constexpr int F_THREADS = 128 + F_EPI * 32;
 constexpr int F_SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 2 * BLOCK_N * 4 /*biases*/ +
-                             HEAD_MAX * BLOCK_N * 4 /*head weights*/ + BLOCK_M * HEAD_MAX * 4 /*head partials*/;
+                             HEAD_MAX * BLOCK_N * 4 /*head weights*/ +
+                             2 * F_GROUPS * BLOCK_M * HEAD_MAX * 4 /*output-layer partial sums, two tiles*/;
 
 struct FusedArgs {
     const float* b1;          // [256]
@@ -41,7 +45,9 @@ struct FusedArgs {
     float* logp;              // [M] or null
     int M, kp1_blocks, head_n, products;
     uint32_t seed, step;
+    long long* trace;         // diagnostics (b2c_tc_mlp2_set_trace): CTA 0 stamps clock64() at 16 pipeline events per tile
 };
+#define F_TRACE(k) do { if (args.trace && blockIdx.x == 0) args.trace[t_local * 16 + (k)] = clock64(); } while (0)
 
 // epilogue warps wait with a back-off: a failed probe sleeps instead of spinning on issue slots the other epilogue's
 // warps could use
@@ -59,7 +65,9 @@ __global__ void __launch_bounds__(F_THREADS, 1)
 tc_mlp2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w1,
                const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ FusedArgs args) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment by pointer arithmetic (not an integer round trip): the compiler keeps the shared address space
+    // and emits LDS / STS instead of generic loads and stores for everything derived from `smem`
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* ring = smem;
     uint8_t* misc = ring + STAGES * STAGE_BYTES;
     uint64_t* full = reinterpret_cast<uint64_t*>(misc);          // [STAGES] TMA bytes landed
@@ -69,11 +77,13 @@ tc_mlp2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint64_t* d1_empty = d1_full + 1;
     uint64_t* d2_full = d1_empty + 1;
     uint64_t* d2_empty = d2_full + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d2_empty + 1);
+    uint64_t* part_full = d2_empty + 1;                          // [2] the 16 epilogue warps posted their partial sums
+    uint64_t* part_empty = part_full + 2;                        // [2] the finaliser has consumed them
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(part_empty + 2);
     float* s_b1 = reinterpret_cast<float*>(misc + 256);
     float* s_b2 = s_b1 + BLOCK_N;
     float* s_head_w = s_b2 + BLOCK_N;                            // [HEAD_MAX][256]
-    float* s_part = s_head_w + HEAD_MAX * BLOCK_N;               // [128][HEAD_MAX]: the upper column group's partial sums
+    float* s_part = s_head_w + HEAD_MAX * BLOCK_N;               // [2 tiles][4 column groups][128][HEAD_MAX] partial sums
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_tiles = (args.M + BLOCK_M - 1) / BLOCK_M;
@@ -87,9 +97,10 @@ tc_mlp2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w2) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&hfull[s], 4); }
-        mbar_init(d1_full, 1); mbar_init(d1_empty, F_EPI1);
-        mbar_init(d2_full, 1); mbar_init(d2_empty, F_EPI2);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&hfull[s], F_EPI); }
+        mbar_init(d1_full, 1); mbar_init(d1_empty, F_EPI);
+        mbar_init(d2_full, 1); mbar_init(d2_empty, F_EPI);
+        for (int k = 0; k < 2; ++k) { mbar_init(&part_full[k], F_EPI); mbar_init(&part_empty[k], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -113,11 +124,13 @@ tc_mlp2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            uint32_t g = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            uint32_t g = 0, t_local = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t_local) {
                 for (int b = 0; b < nb; ++b, ++g) {
                     const int s = (int)(g & 1u);
                     mbar_wait(&empty[s], ((g >> 1) & 1u) ^ 1u);
+                    if (b == 0) F_TRACE(14);
+                    if (b == nb1) F_TRACE(15);
                     uint8_t* st = ring + s * STAGE_BYTES;
                     uint8_t* sw = st + 2 * A_STAGE_BYTES;
                     if (b < nb1) {
@@ -158,169 +171,201 @@ tc_mlp2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t_local) {
                 // ---- layer 1 -> D1 (epilogue 1 is done with the previous tile's D1) ----
                 mbar_wait(d1_empty, (t_local & 1u) ^ 1u);
+                F_TRACE(13);
                 tc_fence_after();
                 for (int b = 0; b < nb1; ++b, ++g) {
                     const int s = (int)(g & 1u);
                     mbar_wait(&full[s], (g >> 1) & 1u);
+                    if (b < 2) F_TRACE(b);
                     tc_fence_after();
                     issue_block(s, tmem_d1, b == 0);
                 }
                 umma_commit(d1_full);
                 // ---- layer 2 -> D2 (epilogue 2 is done with the previous tile's D2) ----
                 mbar_wait(d2_empty, (t_local & 1u) ^ 1u);
+                F_TRACE(2);
                 tc_fence_after();
                 for (int c = 0; c < 4; ++c, ++g) {
                     const int s = (int)(g & 1u);
                     mbar_wait(&full[s], (g >> 1) & 1u);          // W2 block landed
                     mbar_wait(&hfull[s], (s ? hcnt1 : hcnt0) & 1u);      // hidden block written by epilogue 1
                     if (s) hcnt1 += 1u; else hcnt0 += 1u;
+                    F_TRACE(3 + c);
                     tc_fence_after();
                     issue_block(s, tmem_d2, c == 0);
                 }
                 umma_commit(d2_full);
             }
         }
-    } else if (warp >= 4 && warp < 4 + F_EPI1) {
-        // ===== epilogue 1: D1 -> tanh -> [hi | lo] A operand of layer 2 =====
+    } else if (warp == 3) {
+        // ===== finaliser: output-layer sums of the four column groups -> bias -> (sample) -> global.  Off the epilogue
+        // warps' critical path: they post their partial sums and go straight to the next tile =====
+        uint32_t t_local = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t_local) {
+            const int buf = (int)(t_local & 1u);
+            mbar_wait_backoff(&part_full[buf], (t_local >> 1) & 1u);
+            const float4* part = reinterpret_cast<const float4*>(s_part + buf * F_GROUPS * BLOCK_M * HEAD_MAX);
+#pragma unroll 1
+            for (int pass = 0; pass < BLOCK_M / 32; ++pass) {
+                const int rloc = pass * 32 + lane;
+                const int row = tile * BLOCK_M + rloc;
+                float4 t = part[rloc];
+#pragma unroll
+                for (int gq = 1; gq < F_GROUPS; ++gq) {          // fixed order: group 0 + 1 + 2 + 3
+                    const float4 u = part[gq * BLOCK_M + rloc];
+                    t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+                }
+                if (row < args.M) {
+                    if (args.head_n == 4) {
+                        const float o0 = t.x + args.head_b[0], o1 = t.y + args.head_b[1];
+                        const float o2 = t.z + args.head_b[2], o3 = t.w + args.head_b[3];
+                        reinterpret_cast<float4*>(args.head_out)[row] = make_float4(o0, o1, o2, o3);
+                        if (args.actions) {
+                            float e0, e1;
+                            normal2(args.seed, args.step, (uint32_t)row, e0, e1);
+                            float s0 = expf(o2), s1 = expf(o3);
+                            float a0 = o0 + s0 * e0, a1 = o1 + s1 * e1;
+                            float z0 = (a0 - o0) / s0, z1 = (a1 - o1) / s1;
+                            reinterpret_cast<float2*>(args.actions)[row] = make_float2(a0, a1);
+                            if (args.logp) args.logp[row] = -0.5f * (z0 * z0 + z1 * z1) - 1.8378770664093453f - (o2 + o3);
+                        }
+                    } else {
+                        args.head_out[row] = t.x + args.head_b[0];               // head_n = 1
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&part_empty[buf]);
+            if (lane == 0) F_TRACE(12);
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue warps (16 = 4 TMEM lane quarters x 4 column groups) =====
+        // Two jobs per tile: E1(t) = D1 -> +b1 -> tanh -> [hi | lo] A operand of layer 2 (all warps on one reduction
+        // block at a time - the tensor core idles until the first block is there), and E2(t) = D2 -> +b2 -> tanh ->
+        // partial sums of the output layer.  They are interleaved so that neither the tensor core nor these warps wait
+        // for the other longer than necessary (measured timelines: profiles/r02_c_fused_trace.md):
+        //   iteration i:  E2(i-1) first half | read E2(i-1) second half into registers, hand D2 back |
+        //                 E1(i), all four blocks | E2(i-1) second half from the registers, post the partial sums
+        // D2 is free again ~half an E2 after it filled, and E1(i)'s first block is not queued behind a whole E2.
         const int q = warp & 3;                                  // TMEM lane quarter = rows 32 q .. 32 q + 31 of the tile
-        const int grp = (warp - 4) >> 2;                         // column group: reduction blocks grp, grp + 2
+        const int sub = (warp - 4) >> 2;                         // column group 0..3
         const int r = q * 32 + lane;                             // row in the tile
         const uint32_t row_off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
         const uint32_t swz = (uint32_t)(r & 7);
-        uint32_t t_local = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t_local) {
-            mbar_wait_backoff(d1_full, t_local & 1u);
-            tc_fence_after();
-            const uint32_t taddr0 = tmem_d1 + ((uint32_t)(q * 32) << 16);
-            const uint32_t g_base = t_local * (uint32_t)nb + (uint32_t)nb1;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+        // bias + tanh on 32 raw accumulator columns, then the output layer's (even, odd) partial sums
+        auto e2_half = [&](const uint32_t* rr, int c, uint64_t* hacc2) {
+            uint64_t vv[16];
+            const ulonglong2* bp = reinterpret_cast<const ulonglong2*>(s_b2 + c * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const ulonglong2 bb = bp[j];
+                vv[2 * j] = fast_tanh2(add2(pk2(__uint_as_float(rr[4 * j]), __uint_as_float(rr[4 * j + 1])), bb.x));
+                vv[2 * j + 1] = fast_tanh2(add2(pk2(__uint_as_float(rr[4 * j + 2]), __uint_as_float(rr[4 * j + 3])), bb.y));
+            }
+            if (args.head_n == 4) {
+#pragma unroll
+                for (int hj = 0; hj < 4; ++hj) {
+                    const ulonglong2* wp = reinterpret_cast<const ulonglong2*>(s_head_w + hj * BLOCK_N + c * 32);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const ulonglong2 ww = wp[j];
+                        hacc2[hj] = fma2(vv[2 * j], ww.x, hacc2[hj]);
+                        hacc2[hj] = fma2(vv[2 * j + 1], ww.y, hacc2[hj]);
+                    }
+                }
+            } else {
+                const ulonglong2* wp = reinterpret_cast<const ulonglong2*>(s_head_w + c * 32);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const ulonglong2 ww = wp[j];
+                    hacc2[0] = fma2(vv[2 * j], ww.x, hacc2[0]);
+                    hacc2[0] = fma2(vv[2 * j + 1], ww.y, hacc2[0]);
+                }
+            }
+        };
+
 #pragma unroll 1
-            for (int cc = 0; cc < 2; ++cc) {
-                const int c = grp + 2 * cc;                      // reduction block of layer 2 = hidden columns 64 c ..
-                const uint32_t g = g_base + (uint32_t)c;
-                const int s = (int)(g & 1u);
-                uint8_t* a_hi = ring + s * STAGE_BYTES + row_off;
-                uint8_t* a_lo = a_hi + A_STAGE_BYTES;
+        for (int i = 0; i <= my_tiles; ++i) {
+            const uint32_t t_local = (uint32_t)i;                // tile of E1 in this iteration (F_TRACE index)
+            const uint32_t tp = (uint32_t)(i - 1);               // tile of E2 in this iteration
+            uint64_t hacc2[HEAD_MAX] = {0ull, 0ull, 0ull, 0ull};
+            uint32_t rb[32];                                     // second half of E2's columns, raw, held across E1
+            if (i > 0) {
+                mbar_wait_backoff(d2_full, tp & 1u);
+                if (warp == 4 && lane == 0) { if (args.trace && blockIdx.x == 0) args.trace[tp * 16 + 10] = clock64(); }
+                tc_fence_after();
+                uint32_t ra[32];
+                tmem_ld32(tmem_d2 + lane_base + (uint32_t)(sub * 64), ra);
+                e2_half(ra, 2 * sub, hacc2);
+                tmem_ld32(tmem_d2 + lane_base + (uint32_t)(sub * 64 + 32), rb);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(d2_empty);            // layer 2 of the next tile may start
+                if (warp == 4 && lane == 0) { if (args.trace && blockIdx.x == 0) args.trace[tp * 16 + 11] = clock64(); }
+            }
+            if (i < my_tiles) {
+                // ---- E1(i): 16 columns of every reduction block ----
+                mbar_wait_backoff(d1_full, t_local & 1u);
+                if (warp == 4 && lane == 0) F_TRACE(7);
+                tc_fence_after();
+                const uint32_t g_base = t_local * (uint32_t)nb + (uint32_t)nb1;
 #pragma unroll 1
-                for (int h = 0; h < 2; ++h) {                    // 32 columns at a time
-                    uint32_t rr[32];
-                    tmem_ld32(taddr0 + (uint32_t)(c * 64 + h * 32), rr);
-                    if (cc == 1 && h == 1) {                     // this warp's last read of D1: hand it back early
+                for (int c = 0; c < 4; ++c) {                    // reduction block of layer 2 = hidden columns 64 c ..
+                    const uint32_t g = g_base + (uint32_t)c;
+                    const int s = (int)(g & 1u);
+                    uint8_t* a_hi = ring + s * STAGE_BYTES + row_off;
+                    uint8_t* a_lo = a_hi + A_STAGE_BYTES;
+                    uint32_t rr[16];
+                    tmem_ld16(tmem_d1 + lane_base + (uint32_t)(c * 64 + sub * 16), rr);
+                    if (c == 3) {                                // this warp's last read of D1: hand it back early
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(d1_empty);
                     }
-                    // bias, tanh and the [hi | lo] split on column pairs (fma.rn.f32x2: two columns per instruction)
-                    uint32_t hi[16], lo[16];
-                    const ulonglong2* bp = reinterpret_cast<const ulonglong2*>(s_b1 + c * 64 + h * 32);
+                    // bias, tanh and the [hi | lo] split on column pairs (f32x2: two columns per instruction)
+                    uint32_t hi[8], lo[8];
+                    const ulonglong2* bp = reinterpret_cast<const ulonglong2*>(s_b1 + c * 64 + sub * 16);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
+                    for (int j = 0; j < 4; ++j) {
                         const ulonglong2 bb = bp[j];
                         const uint64_t t0 = fast_tanh2(add2(pk2(__uint_as_float(rr[4 * j]), __uint_as_float(rr[4 * j + 1])), bb.x));
                         const uint64_t t1 = fast_tanh2(add2(pk2(__uint_as_float(rr[4 * j + 2]), __uint_as_float(rr[4 * j + 3])), bb.y));
                         split2(t0, hi[2 * j], lo[2 * j]);
                         split2(t1, hi[2 * j + 1], lo[2 * j + 1]);
                     }
-                    if (h == 0) mbar_wait_backoff(&empty[s], ((g >> 1) & 1u) ^ 1u);   // the stage's previous MMAs have retired
+                    mbar_wait_backoff(&empty[s], ((g >> 1) & 1u) ^ 1u);          // the stage's previous MMAs have retired
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {                // 16-byte chunks 4 h + j of the row, XOR-swizzled
-                        const uint32_t off = ((uint32_t)(4 * h + j) ^ swz) << 4;
+                    for (int j = 0; j < 2; ++j) {                // 16-byte chunks 2 sub + j of the row, XOR-swizzled
+                        const uint32_t off = ((uint32_t)(2 * sub + j) ^ swz) << 4;
                         *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
                         *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
                     }
-                }
-                fence_async_shared();                            // generic-proxy stores -> visible to the tensor core
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&hfull[s]);
-            }
-        }
-    } else if (warp >= 4 + F_EPI1) {
-        // ===== epilogue 2: D2 -> tanh -> output layer (+ sample) =====
-        const int q = warp & 3;
-        const int grp = (warp - 4 - F_EPI1) >> 2;                // column group: chunks 4 grp .. 4 grp + 3
-        const int rloc = q * 32 + lane;
-        uint32_t t_local = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t_local) {
-            mbar_wait_backoff(d2_full, t_local & 1u);
-            tc_fence_after();
-            const int row = tile * BLOCK_M + rloc;
-            const bool live = row < args.M;
-            const uint32_t taddr0 = tmem_d2 + ((uint32_t)(q * 32) << 16);
-            uint64_t hacc2[HEAD_MAX] = {0ull, 0ull, 0ull, 0ull};
-#pragma unroll 1
-            for (int c = 4 * grp; c < 4 * grp + 4; ++c) {
-                uint32_t rr[32];
-                tmem_ld32(taddr0 + (uint32_t)(c * 32), rr);
-                if (c == 4 * grp + 3) {
-                    tc_fence_before();
+                    fence_async_shared();                        // generic-proxy stores -> visible to the tensor core
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(d2_empty);
-                }
-                uint64_t vv[16];
-                const ulonglong2* bp = reinterpret_cast<const ulonglong2*>(s_b2 + c * 32);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const ulonglong2 bb = bp[j];
-                    vv[2 * j] = fast_tanh2(add2(pk2(__uint_as_float(rr[4 * j]), __uint_as_float(rr[4 * j + 1])), bb.x));
-                    vv[2 * j + 1] = fast_tanh2(add2(pk2(__uint_as_float(rr[4 * j + 2]), __uint_as_float(rr[4 * j + 3])), bb.y));
-                }
-                // output layer: (even column, odd column) partial sums per output
-                if (args.head_n == 4) {
-#pragma unroll
-                    for (int hj = 0; hj < 4; ++hj) {
-                        const ulonglong2* wp = reinterpret_cast<const ulonglong2*>(s_head_w + hj * BLOCK_N + c * 32);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const ulonglong2 ww = wp[j];
-                            hacc2[hj] = fma2(vv[2 * j], ww.x, hacc2[hj]);
-                            hacc2[hj] = fma2(vv[2 * j + 1], ww.y, hacc2[hj]);
-                        }
-                    }
-                } else {
-                    const ulonglong2* wp = reinterpret_cast<const ulonglong2*>(s_head_w + c * 32);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const ulonglong2 ww = wp[j];
-                        hacc2[0] = fma2(vv[2 * j], ww.x, hacc2[0]);
-                        hacc2[0] = fma2(vv[2 * j + 1], ww.y, hacc2[0]);
-                    }
+                    if (lane == 0) mbar_arrive(&hfull[s]);
+                    if (warp == 4 && lane == 0 && c < 2) F_TRACE(8 + c);
                 }
             }
-            float hacc[HEAD_MAX];
-#pragma unroll
-            for (int hj = 0; hj < HEAD_MAX; ++hj) {
-                float e, o;
-                upk2(hacc2[hj], e, o);
-                hacc[hj] = e + o;
-            }
-            // the upper column group hands its partial sums to the lower one (named barrier 2 = epilogue 2)
-            if (grp == 1) {
-#pragma unroll
-                for (int hj = 0; hj < HEAD_MAX; ++hj) s_part[rloc * HEAD_MAX + hj] = hacc[hj];
-            }
-            asm volatile("bar.sync 2, %0;" ::"n"(F_EPI2 * 32) : "memory");
-            if (grp == 0 && live) {
-                float o[HEAD_MAX];
+            if (i > 0) {
+                // ---- E2(i-1), second half, and the partial sums for the finaliser (double-buffered by tile parity) ----
+                e2_half(rb, 2 * sub + 1, hacc2);
+                const int buf = (int)(tp & 1u);
+                float hs[HEAD_MAX];
 #pragma unroll
                 for (int hj = 0; hj < HEAD_MAX; ++hj) {
-                    float t = hacc[hj] + s_part[rloc * HEAD_MAX + hj];
-                    o[hj] = (hj < args.head_n) ? t + args.head_b[hj] : 0.0f;
+                    float e, o;
+                    upk2(hacc2[hj], e, o);
+                    hs[hj] = e + o;
                 }
-                if (args.head_n == 4) {
-                    reinterpret_cast<float4*>(args.head_out)[row] = make_float4(o[0], o[1], o[2], o[3]);
-                    if (args.actions) {
-                        float e0, e1;
-                        normal2(args.seed, args.step, (uint32_t)row, e0, e1);
-                        float s0 = expf(o[2]), s1 = expf(o[3]);
-                        float a0 = o[0] + s0 * e0, a1 = o[1] + s1 * e1;
-                        float z0 = (a0 - o[0]) / s0, z1 = (a1 - o[1]) / s1;
-                        reinterpret_cast<float2*>(args.actions)[row] = make_float2(a0, a1);
-                        if (args.logp) args.logp[row] = -0.5f * (z0 * z0 + z1 * z1) - 1.8378770664093453f - (o[2] + o[3]);
-                    }
-                } else {
-                    args.head_out[row] = o[0];                   // head_n = 1
-                }
+                mbar_wait_backoff(&part_empty[buf], ((tp >> 1) & 1u) ^ 1u);      // the finaliser is done with tile tp - 2
+                reinterpret_cast<float4*>(s_part + (buf * F_GROUPS + sub) * BLOCK_M * HEAD_MAX)[r] =
+                    make_float4(hs[0], hs[1], hs[2], hs[3]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&part_full[buf]);
             }
-            asm volatile("bar.sync 2, %0;" ::"n"(F_EPI2 * 32) : "memory");
         }
     }
     tc_fence_before();
@@ -336,7 +381,13 @@ tc_mlp2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
 using namespace b2c::tc;
 
+static long long* g_trace = nullptr;
+
 extern "C" {
+
+/* diagnostics: CTA 0 of the following b2c_tc_mlp2_head launches writes clock64() stamps of 16 pipeline events per tile
+ * into dev_buffer ([tiles of CTA 0][16]); null turns it off */
+int b2c_tc_mlp2_set_trace(long long* dev_buffer) { g_trace = dev_buffer; return B2C_OK; }
 
 int b2c_tc_mlp2_head(const uint16_t* a_split, int Kp1, const uint16_t* w1_prep, const float* b1, const uint16_t* w2_prep,
                      const float* b2, const b2c_tc_head* head, int M, void* stream) {
@@ -371,6 +422,7 @@ int b2c_tc_mlp2_head(const uint16_t* a_split, int Kp1, const uint16_t* w1_prep, 
     a.actions = head->actions; a.logp = head->logp; a.M = M; a.kp1_blocks = Kp1 / BLOCK_K; a.head_n = head->n;
     a.products = products == 3 ? 3 : 4;
     a.seed = head->seed; a.step = head->step;
+    a.trace = g_trace;
     const int tiles = (M + BLOCK_M - 1) / BLOCK_M;
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3((unsigned)(tiles < num_sms ? tiles : num_sms));

@@ -55,7 +55,9 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     constexpr int NT = 128 + EPI * 32;
     constexpr int GROUPS = EPI / 4;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment by pointer arithmetic (not an integer round trip): the compiler keeps the shared address space
+    // and emits LDS / STS instead of generic loads and stores for everything derived from `smem`
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const bool resident = args.resident != 0;
     const int n_stages = args.stages;
     const int stage_bytes = resident ? A_PAIR_BYTES : STAGE_BYTES;
@@ -416,7 +418,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_constant__ CUtensorMap map_x,
                 const __grid_constant__ WgradArgs args) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment by pointer arithmetic (not an integer round trip): the compiler keeps the shared address space
+    // and emits LDS / STS instead of generic loads and stores for everything derived from `smem`
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES);
     uint64_t* empty = full + WG_STAGES;
     uint64_t* done = empty + WG_STAGES;

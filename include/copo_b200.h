@@ -251,6 +251,9 @@ int b2c_tc_linear_head(const uint16_t* a_split, const uint16_t* w_prep, const fl
  * bit-identical to b2c_tc_linear followed by b2c_tc_linear_head.  w1_prep [256][2*Kp1], w2_prep [256][512]. */
 int b2c_tc_mlp2_head(const uint16_t* a_split, int Kp1, const uint16_t* w1_prep, const float* b1, const uint16_t* w2_prep,
                      const float* b2, const b2c_tc_head* head, int M, void* stream);
+/* Diagnostics: CTA 0 of the following b2c_tc_mlp2_head launches stamps clock64() at 16 pipeline events per tile into
+ * dev_buffer ([tiles of CTA 0][16] int64); NULL turns it off (tools/fused_trace.py prints the timeline). */
+int b2c_tc_mlp2_set_trace(long long* dev_buffer);
 /* Weight gradient of a 256-wide layer on the tensor cores: dW[256][K] += dz^T x from the [hi | lo] operands
  * (dz_split [M][512], x_split [M][2*Kp], Kp <= 256).  workspace: b2c_tc_wgrad_parts() * 256 * Kp floats; the
  * per-CTA partial sums are added in a fixed order (deterministic). */
