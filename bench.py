@@ -300,9 +300,7 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL_DEBUG stays as the caller set it; its log goes to stderr so that stdout remains the one JSON line
-        if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
-            os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
+        # NCCL_DEBUG stays as the caller set it; NCCL logs to file descriptor 1, which main() has pointed at stderr
         dist.init_process_group("nccl", device_id=dev)
     c = CONFIGS[args.config]
     S, A = (args.scenes or c["scenes"]), c["slots"]
@@ -342,7 +340,7 @@ def run_gpu(args):
         return pol.model.central_value_function(cobs)
 
     def rollout_step():
-        """policy forward (two tcgen05 kernels; logits + Gaussian sample in the second one's epilogue) -> fused scene
+        """policy forward (one tcgen05 kernel; logits + Gaussian sample in its epilogue) -> fused scene
         step (which also emits the next observation as the policy's bf16 operand); everything stays in HBM"""
         t = state["t"]
         r = t % RING
@@ -416,6 +414,8 @@ def run_gpu(args):
     _, s1 = ops.tc_linear(a1, w1, net.b[0], act=1, want_f32=False, want_split=True)
     l2_ms = time_kernel(lambda: ops.tc_linear_head(s1, w2, net.b[1], net.W[2], net.b[2], act=1, sample=(1, 1)))
     l1_ms = time_kernel(lambda: ops.tc_linear(a1, w1, net.b[0], act=1, want_f32=False, out_split=s1, want_split=True))
+    # the rollout's policy forward: ONE kernel (mlp_fused.cu), hidden layers on chip
+    mlp_ms = time_kernel(lambda: ops.tc_mlp2_head(a1, w1, net.b[0], w2, net.b[1], net.W[2], net.b[2], sample=(1, 1)))
     fuse_ms = None
     if not copo:
         fuse_ms = time_kernel(lambda: ops.cc_obs_fuse(obs[0], acts[0], outs[0]["flags"].view(-1),
@@ -492,6 +492,9 @@ def run_gpu(args):
     env_gbs = algo_bytes / (env_ms * 1e-3) / 1e9
     l2_flops = 2.0 * N * 256 * 256                   # algorithmic fp32-equivalent flops of the 256x256 layer
     l2_tf = l2_flops / (l2_ms * 1e-3) / 1e12
+    mlp_flops = 2.0 * N * (D * 256 + 256 * 256 + 4 * 256)           # the whole policy network, fp32-equivalent
+    mlp_issued = 4 * 2.0 * N * 256 * (env.split_width // 2 + 256)    # bf16 flops the tensor cores execute (4 products)
+    mlp_tf = mlp_flops / (mlp_ms * 1e-3) / 1e12
     traffic, traffic_src = _ncu_traffic(args.config)
     env_roof = {"bound": "hbm", "achieved": env_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": env_gbs / hbm_peak,
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
@@ -505,12 +508,18 @@ def run_gpu(args):
                                                 "for the policy's first layer (not in SURVEY 8d's figure)"},
                 "note": "issue-bound, not HBM-bound (72-laser lidar + neighbour search are ALU work): see profiles/ for the "
                         "instruction mix and issue-slot utilisation"}
-    mlp_roof = {"bound": "tensor", "achieved": l2_tf, "peak": tc_peak, "unit": "TFLOP/s", "frac": l2_tf / tc_peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "tc_linear_kernel (256x256 layer, bf16_split)",
-                "algorithmic_flops_per_launch": l2_flops, "kernel_ms": l2_ms, "tensor_flops_issued": 4 * l2_flops,
-                "note": "achieved counts fp32-equivalent flops; the kernel issues 4x as many bf16 flops (hi/lo split "
-                        "operands, four products)"}
-    others = [mlp_roof]
+    mlp_roof = {"bound": "tensor", "achieved": mlp_tf, "peak": tc_peak, "unit": "TFLOP/s", "frac": mlp_tf / tc_peak,
+                "traffic": None, "peak_source": peak_src,
+                "kernel": "tc_mlp2_kernel (policy network %d-256-256-4 + sample in one launch, bf16_split)" % D,
+                "algorithmic_flops_per_launch": mlp_flops, "kernel_ms": mlp_ms, "tensor_flops_issued": mlp_issued,
+                "frac_of_issued_bf16_flops": mlp_issued / (mlp_ms * 1e-3) / 1e12 / tc_peak,
+                "note": "achieved counts fp32-equivalent flops; the kernel executes 4x as many bf16 flops on zero-padded "
+                        "reduction lengths (hi/lo split operands, four products): frac_of_issued_bf16_flops"}
+    layer_roof = {"bound": "tensor", "achieved": l2_tf, "peak": tc_peak, "unit": "TFLOP/s", "frac": l2_tf / tc_peak,
+                  "traffic": None, "peak_source": peak_src,
+                  "kernel": "tc_linear_kernel (one 256x256 layer + logits + sample; the learner's forward kernel)",
+                  "algorithmic_flops_per_launch": l2_flops, "kernel_ms": l2_ms, "tensor_flops_issued": 4 * l2_flops}
+    others = [mlp_roof, layer_roof]
     if fuse_ms is not None:
         fb = N * (4 * D + 4 * (2 * D + 2))           # read own obs + write the fused critic obs (1100 B at D = 91)
         others.append({"bound": "hbm", "kernel": "cc_obs_fuse_kernel (mean-field)", "kernel_ms": fuse_ms,
@@ -529,8 +538,8 @@ def run_gpu(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "ms_per_step_back_to_back_no_flush": noflush_ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": (c["label"] % S) + ", one rollout step: policy MLP forward (%d-256-256-4, tcgen05 "
-                               "split-bf16, logits + Gaussian sample in the layer-2 epilogue) + scene step (dynamics, "
+        "config": {"workload": (c["label"] % S) + ", one rollout step: policy MLP forward (%d-256-256-4, one "
+                               "tcgen05 split-bf16 kernel, logits + Gaussian sample in its epilogue) + scene step (dynamics, "
                                "crash/out/arrive, respawn, neighbours + nei/global reward, 72-laser lidar obs%s)%s"
                                % (D, " + LCF" if copo else "",
                                   "" if copo else " + mean-field critic-obs fusion + central value head (184-256-256-1)"),
@@ -544,6 +553,7 @@ def run_gpu(args):
         "roofline_other": others,
         "kernel_ms": {"env_step": env_ms, "env_lidar_kernel": lidar_ms,
                       "env_state_kernel": (env_ms - lidar_ms) if lidar_ms is not None else None,
+                      "tc_mlp2_policy_forward_and_sample": mlp_ms,
                       "tc_linear_layer1": l1_ms, "tc_linear_layer2_with_logits_and_sample": l2_ms,
                       "cc_obs_fuse_mf": fuse_ms},
         "cpu_baseline": cpu,
@@ -614,10 +624,18 @@ def main():
     ap.add_argument("--train-scenes", type=int, default=0)
     ap.add_argument("--train-fragment", type=int, default=16)
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: whatever libraries write to file descriptor 1 while the bench runs (NCCL's
+    # version banner / debug log when NCCL_DEBUG is set, torch warnings) is sent to stderr instead; the JSON line goes
+    # to the original stdout
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     if args.impl == "reference":
         run_reference(args)
     else:
         run_gpu(args)
+    real_stdout.flush()
 
 
 if __name__ == "__main__":

@@ -778,9 +778,10 @@ int b2c_env_create(const b2c_env_config* c, const uint32_t* map_blob, int map_wo
     e->step_fn = pick_step_kernel(e->split != 0, k.A, k.D, generic);
     e->lidar_fn = pick_lidar_kernel(k.A, k.D, generic);
     e->specialised = (e->step_fn != (e->split ? env_step_kernel<true, 0, 0> : env_step_kernel<false, 0, 0>)) ? 1 : 0;
-    // measured on B200 (profiles/r02_b_env_pdl.md): the lidar kernel gains ~3 % from starting early; the state kernel
-    // loses more than that when its CTAs take their places before the previous kernel is done, so only bit 0 is on
-    e->pdl = 1;
+    // measured on B200 (profiles/r02_b_env_pdl.md, C2 shape, back-to-back steps): none 0.1022 ms, lidar early 0.1136,
+    // state early 0.0989, both 0.1089 - the state kernel gains from loading its tiles while its predecessor drains, the
+    // lidar kernel's early CTAs only take shared memory away from the state kernel's last wave; so only bit 1 is on
+    e->pdl = 2;
     if (const char* t = getenv("B2C_ENV_PDL")) e->pdl = atoi(t) & 3;
     if (e->split) {
         B2C_CUDA_OR(cudaFuncSetAttribute(e->step_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem),

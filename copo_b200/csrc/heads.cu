@@ -57,16 +57,16 @@ __global__ void head_forward_kernel(const float* __restrict__ h, int ldh, const 
 }
 
 // thread k of a CTA owns column k: dz[m][k] = (sum_j dy[m][j] W[j][k]) * (1 - h[m][k]^2), dW[j][k] += sum_m dy h,
-// db[j] += sum_m dy[m][j].  A CTA walks a contiguous chunk of rows, four rows in flight per thread; dz can also
+// db[j] += sum_m dy[m][j], optionally dz_colsum[k] += sum_m dz[m][k] (bias gradient of the hidden layer below).  A CTA walks a contiguous chunk of rows, four rows in flight per thread; dz can also
 // leave as the [hi | lo] bf16 operand of the tensor-core kernels (dz_split [M][2 * K], K = 256).
 template <int NOUT>
 __global__ void head_backward_kernel(const float* __restrict__ dy, int ldy, const float* __restrict__ h, int ldh,
                                      const float* __restrict__ W, float* __restrict__ dz, int ldz,
                                      uint16_t* __restrict__ dz_split, float* __restrict__ dW, float* __restrict__ db,
-                                     int M, int K, int rows, int dtanh) {
+                                     float* __restrict__ dz_colsum, int M, int K, int rows, int dtanh) {
     const int k = blockIdx.y * blockDim.x + threadIdx.x;
     const int m_begin = blockIdx.x * rows, m_end = min(M, m_begin + rows);
-    float w[NOUT], accw[NOUT], accb = 0.0f;
+    float w[NOUT], accw[NOUT], accb = 0.0f, accz = 0.0f;
 #pragma unroll
     for (int j = 0; j < NOUT; ++j) { w[j] = (k < K) ? W[j * K + k] : 0.0f; accw[j] = 0.0f; }
     constexpr int U = 4;
@@ -88,6 +88,7 @@ __global__ void head_backward_kernel(const float* __restrict__ dy, int ldy, cons
 #pragma unroll
                 for (int j = 0; j < NOUT; ++j) { s = fmaf(g[u][j], w[j], s); accw[j] = fmaf(g[u][j], hv[u], accw[j]); }
                 const float z = dtanh ? s * (1.0f - hv[u] * hv[u]) : s;
+                accz += z;
                 if (dz) dz[(size_t)m * ldz + k] = z;
                 if (dz_split) {
                     __nv_bfloat16 hi = __float2bfloat16_rn(z);
@@ -104,6 +105,8 @@ __global__ void head_backward_kernel(const float* __restrict__ dy, int ldy, cons
         for (int j = 0; j < NOUT; ++j) atomicAdd(&dW[j * K + k], accw[j]);
     }
     if (db && blockIdx.y == 0 && threadIdx.x < NOUT) atomicAdd(&db[threadIdx.x], accb);
+    // column sums of dz = the bias gradient of the layer that produced h (the thread owns the column: no reduction)
+    if (dz_colsum && k < K) atomicAdd(&dz_colsum[k], accz);
 }
 
 // logits[m] = (mu0, mu1, ls0, ls1); action = mu + exp(ls) * eps; logp as TorchDiagGaussian.logp
@@ -141,6 +144,8 @@ struct PpoHeadArgs {
     int M, n_heads, mode;       // mode 0: PPO loss, 1: mean(logp) (old-policy term of the meta-gradient)
     float clip, vf_clip, vf_coeff, ent_coeff, kl_coeff, inv_rows;
     int plain_vf;               // old_value_loss=False: clamp((v - t)^2, 0, vf_clip)
+    const float* dyn_coeffs;    // device [2] = {kl_coeff, entropy_coeff} read at run time (a captured launch keeps working
+                                // when the adaptive KL coefficient changes), or null: the by-value fields above
 };
 
 __global__ void ppo_head_kernel(const PpoHeadArgs a) {
@@ -159,6 +164,8 @@ __global__ void ppo_head_kernel(const PpoHeadArgs a) {
             g_mu0 = s * z0 / s0; g_mu1 = s * z1 / s1;
             g_ls0 = s * (z0 * z0 - 1.0f); g_ls1 = s * (z1 * z1 - 1.0f);
         } else {
+            const float kl_coeff = a.dyn_coeffs ? a.dyn_coeffs[0] : a.kl_coeff;
+            const float ent_coeff = a.dyn_coeffs ? a.dyn_coeffs[1] : a.ent_coeff;
             float ratio = expf(logp - a.old_logp[m]);
             float adv = a.adv[m];
             float lo = 1.0f - a.clip, hi = 1.0f + a.clip;
@@ -169,17 +176,17 @@ __global__ void ppo_head_kernel(const PpoHeadArgs a) {
             float dsurr = (inside || t1 < t2) ? adv : 0.0f;       // d surr / d ratio
             float c = -s * dsurr * ratio;                           // d(total)/d logp
             g_mu0 = c * z0 / s0; g_mu1 = c * z1 / s1;
-            g_ls0 = c * (z0 * z0 - 1.0f) - s * a.ent_coeff;
-            g_ls1 = c * (z1 * z1 - 1.0f) - s * a.ent_coeff;
+            g_ls0 = c * (z0 * z0 - 1.0f) - s * ent_coeff;
+            g_ls1 = c * (z1 * z1 - 1.0f) - s * ent_coeff;
             st[0] = -surr;
             st[4] = (l.z + l.w) + 2.8378770664093453f;             // entropy: sum(ls) + log(2 pi e)
-            if (a.kl_coeff > 0.0f) {
+            if (kl_coeff > 0.0f) {
                 float4 o = reinterpret_cast<const float4*>(a.old_logits)[m];
                 float so0 = expf(o.z), so1 = expf(o.w);
                 float d0 = o.x - l.x, d1 = o.y - l.y;
                 float q0 = (so0 * so0 + d0 * d0) / (s0 * s0), q1 = (so1 * so1 + d1 * d1) / (s1 * s1);
                 st[5] = (l.z - o.z + 0.5f * q0 - 0.5f) + (l.w - o.w + 0.5f * q1 - 0.5f);
-                float k = s * a.kl_coeff;
+                float k = s * kl_coeff;
                 g_mu0 += k * (l.x - o.x) / (s0 * s0); g_mu1 += k * (l.y - o.y) / (s1 * s1);
                 g_ls0 += k * (1.0f - q0); g_ls1 += k * (1.0f - q1);
             }
@@ -270,6 +277,12 @@ int b2c_head_backward(const float* dy, int ldy, const float* h, int ldh, const f
 
 int b2c_head_backward_split(const float* dy, int ldy, const float* h, int ldh, const float* W, float* dz, int ldz,
                             uint16_t* dz_split, float* dW, float* db, int M, int K, int N, int dtanh, void* stream) {
+    return b2c_head_backward_tc(dy, ldy, h, ldh, W, dz, ldz, dz_split, dW, db, nullptr, M, K, N, dtanh, stream);
+}
+
+int b2c_head_backward_tc(const float* dy, int ldy, const float* h, int ldh, const float* W, float* dz, int ldz,
+                         uint16_t* dz_split, float* dW, float* db, float* dz_colsum, int M, int K, int N, int dtanh,
+                         void* stream) {
     if (M == 0) return B2C_OK;
     if (!dy || !h || !W || N < 1 || N > HEAD_MAX_N) return b2c_set_error(B2C_ERR_ARG, "b2c_head_backward: bad argument");
     if (dz_split && (K % 64)) return b2c_set_error(B2C_ERR_ARG, "b2c_head_backward: dz_split needs K to be a multiple of 64");
@@ -280,7 +293,7 @@ int b2c_head_backward_split(const float* dy, int ldy, const float* h, int ldh, c
     rows = rows < 32 ? 32 : (rows > 256 ? 256 : rows);
     dim3 grid((M + rows - 1) / rows, (K + 255) / 256);
     cudaStream_t s = (cudaStream_t)stream;
-#define B2C_HB(n) case n: head_backward_kernel<n><<<grid, 256, 0, s>>>(dy, ldy, h, ldh, W, dz, ldz, dz_split, dW, db, M, K, rows, dtanh); break;
+#define B2C_HB(n) case n: head_backward_kernel<n><<<grid, 256, 0, s>>>(dy, ldy, h, ldh, W, dz, ldz, dz_split, dW, db, dz_colsum, M, K, rows, dtanh); break;
     switch (N) { B2C_HB(1) B2C_HB(2) B2C_HB(3) B2C_HB(4) B2C_HB(5) B2C_HB(6) B2C_HB(7) B2C_HB(8) }
 #undef B2C_HB
     B2C_CUDA(cudaGetLastError());
@@ -302,7 +315,7 @@ int b2c_ppo_head(const b2c_ppo_head_args* p, void* stream) {
     if (!p || !p->logits || !p->actions || !p->dlogits || p->n_heads < 0 || p->n_heads > 3)
         return b2c_set_error(B2C_ERR_ARG, "b2c_ppo_head: bad argument");
     if (p->mode == 0 && (!p->old_logp || !p->adv)) return b2c_set_error(B2C_ERR_ARG, "b2c_ppo_head: missing columns");
-    if (p->mode == 0 && p->kl_coeff > 0.0f && !p->old_logits)
+    if (p->mode == 0 && (p->kl_coeff > 0.0f || p->dyn_coeffs) && !p->old_logits)
         return b2c_set_error(B2C_ERR_ARG, "b2c_ppo_head: kl_coeff > 0 needs the behaviour distribution inputs");
     PpoHeadArgs a;
     a.logits = p->logits; a.actions = p->actions; a.old_logp = p->old_logp; a.old_logits = p->old_logits; a.adv = p->adv;
@@ -315,6 +328,7 @@ int b2c_ppo_head(const b2c_ppo_head_args* p, void* stream) {
     a.clip = p->clip_param; a.vf_clip = p->vf_clip_param; a.vf_coeff = p->vf_loss_coeff; a.ent_coeff = p->entropy_coeff;
     a.kl_coeff = p->kl_coeff; a.inv_rows = 1.0f / (float)(p->norm_rows > 0 ? p->norm_rows : p->rows);
     a.plain_vf = p->plain_value_loss ? 1 : 0;
+    a.dyn_coeffs = p->dyn_coeffs;
     ppo_head_kernel<<<(p->rows + 255) / 256, 256, 0, (cudaStream_t)stream>>>(a);
     B2C_CUDA(cudaGetLastError());
     return B2C_OK;

@@ -27,6 +27,8 @@ namespace tc {
 struct LinearArgs {
     const float* bias;        // [256] or null
     const float* dtanh_src;   // [M][ld_src] or null: multiply the result by (1 - h^2)
+    const uint16_t* dtanh_split;   // [M][512] bf16 [hi | lo] or null: the same factor with h = hi + lo (the layer's own
+                                   // tensor-core operand: the forward pass need not keep an fp32 copy of h)
     float* out_f32;           // [M][ld_out] or null
     uint16_t* out_split;      // [M][512] bf16 (hi | lo) or null
     int M, kp_blocks;         // kp_blocks = Kp / 64 reduction blocks, four products each
@@ -237,6 +239,22 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 }
                 }
                 if (live) {
+                    if (args.dtanh_split) {
+                        const uint4* hh = reinterpret_cast<const uint4*>(args.dtanh_split + (size_t)row * 512 + c * 32);
+                        const uint4* hl = reinterpret_cast<const uint4*>(args.dtanh_split + (size_t)row * 512 + 256 + c * 32);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {            // 8 columns per 16-byte load of each half
+                            const uint4 a = hh[j], b = hl[j];
+                            const uint32_t ah[4] = {a.x, a.y, a.z, a.w}, al[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float h0 = __uint_as_float(ah[e] << 16) + __uint_as_float(al[e] << 16);
+                                const float h1 = __uint_as_float(ah[e] & 0xffff0000u) + __uint_as_float(al[e] & 0xffff0000u);
+                                v[8 * j + 2 * e] *= (1.0f - h0 * h0);
+                                v[8 * j + 2 * e + 1] *= (1.0f - h1 * h1);
+                            }
+                        }
+                    }
                     if (args.dtanh_src) {
                         const float4* hs = reinterpret_cast<const float4*>(args.dtanh_src + (size_t)row * args.ld_src + c * 32);
 #pragma unroll
@@ -351,11 +369,14 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 }
 
 // x fp32 [M][K] -> [M][2*Kp] bf16: hi in columns [0, Kp), lo in [Kp, 2Kp), zero padding beyond K
-__global__ void split_rows_kernel(const float* __restrict__ x, int ldx, uint16_t* __restrict__ out, int M, int K, int Kp) {
+// ones_col: column K (the first padding column) holds 1.0 - the weight-gradient kernel then returns the bias gradient in
+// that column (dz^T [x | 1]); the forward weights are zero there, so the forward pass does not see it
+__global__ void split_rows_kernel(const float* __restrict__ x, int ldx, uint16_t* __restrict__ out, int M, int K, int Kp,
+                                  int ones_col) {
     const size_t total = (size_t)M * Kp;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         size_t m = i / Kp; int k = (int)(i - m * Kp);
-        float v = (k < K) ? x[m * ldx + k] : 0.0f;
+        float v = (k < K) ? x[m * ldx + k] : ((ones_col && k == K) ? 1.0f : 0.0f);
         __nv_bfloat16 h = __float2bfloat16_rn(v);
         __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
         out[m * 2 * Kp + k] = __bfloat16_as_ushort(h);
@@ -532,14 +553,17 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_constan
     }
 }
 
-// dW[n][k] += sum_c partial[c][n][k]  (k < K), fixed summation order
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dW, int parts, int kp, int K) {
+// dW[n][k] += sum_c partial[c][n][k]  (k < K), fixed summation order; with db: column K of the partials (the ones column
+// of x, split_rows_kernel) is the bias gradient: db[n] += sum_c partial[c][n][K]
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dW, float* __restrict__ db,
+                                    int parts, int kp, int K) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= 256 * K) return;
-    int n = idx / K, k = idx - n * K;
+    const int W = db ? K + 1 : K;
+    if (idx >= 256 * W) return;
+    int n = idx / W, k = idx - n * W;
     float s = 0.0f;
     for (int c = 0; c < parts; ++c) s += partial[((size_t)c * 256 + n) * kp + k];
-    dW[idx] += s;
+    if (k < K) dW[n * K + k] += s; else db[n] += s;
 }
 
 }  // namespace tc
@@ -552,11 +576,16 @@ extern "C" {
 int b2c_tc_padded_k(int K) { return (K + BLOCK_K - 1) / BLOCK_K * BLOCK_K; }
 
 int b2c_tc_split_rows(const float* x, int ldx, uint16_t* out, int M, int K, int Kp, void* stream) {
+    return b2c_tc_split_rows_ones(x, ldx, out, M, K, Kp, 0, stream);
+}
+
+int b2c_tc_split_rows_ones(const float* x, int ldx, uint16_t* out, int M, int K, int Kp, int ones_col, void* stream) {
     if (M == 0) return B2C_OK;
     if (!x || !out || K < 1 || Kp < K || Kp % BLOCK_K) return b2c_set_error(B2C_ERR_ARG, "b2c_tc_split_rows: bad argument");
+    if (ones_col && K >= Kp) return b2c_set_error(B2C_ERR_ARG, "b2c_tc_split_rows_ones: no padding column to hold the ones");
     size_t total = (size_t)M * Kp;
     int grid = (int)((total + 255) / 256 > 148 * 32 ? 148 * 32 : (total + 255) / 256);
-    split_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, out, M, K, Kp);
+    split_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, out, M, K, Kp, ones_col);
     B2C_CUDA(cudaGetLastError());
     return B2C_OK;
 }
@@ -572,7 +601,7 @@ int b2c_tc_prep_weight(const float* W, uint16_t* out, int N, int K, int Kp, int 
 
 static int tc_linear_launch(const uint16_t* a_split, const uint16_t* w_prep, const float* bias, const float* dtanh_src,
                             int ld_src, float* out_f32, int ld_out, uint16_t* out_split, int M, int Kp, int act,
-                            const b2c_tc_head* head, void* stream);
+                            const b2c_tc_head* head, void* stream, const uint16_t* dtanh_split = nullptr);
 
 int b2c_tc_linear(const uint16_t* a_split, const uint16_t* w_prep, const float* bias, const float* dtanh_src, int ld_src,
                   float* out_f32, int ld_out, uint16_t* out_split, int M, int Kp, int act, void* stream) {
@@ -593,9 +622,18 @@ int b2c_tc_linear_head(const uint16_t* a_split, const uint16_t* w_prep, const fl
     return tc_linear_launch(a_split, w_prep, bias, nullptr, 0, out_f32, ld_out, nullptr, M, Kp, act, head, stream);
 }
 
+int b2c_tc_linear_dgrad(const uint16_t* dz_split, const uint16_t* wT_prep, const uint16_t* h_split, float* out_f32,
+                        int ld_out, uint16_t* out_split, int M, int Kp, void* stream) {
+    if (M == 0) return B2C_OK;
+    if (!out_f32 && !out_split) return b2c_set_error(B2C_ERR_ARG, "b2c_tc_linear_dgrad: no output requested");
+    if (!h_split || ((uintptr_t)h_split & 15)) return b2c_set_error(B2C_ERR_ARG, "b2c_tc_linear_dgrad: h_split must be 16-byte aligned");
+    return tc_linear_launch(dz_split, wT_prep, nullptr, nullptr, 0, out_f32, ld_out, out_split, M, Kp, 0, nullptr, stream,
+                            h_split);
+}
+
 static int tc_linear_launch(const uint16_t* a_split, const uint16_t* w_prep, const float* bias, const float* dtanh_src,
                             int ld_src, float* out_f32, int ld_out, uint16_t* out_split, int M, int Kp, int act,
-                            const b2c_tc_head* head, void* stream) {
+                            const b2c_tc_head* head, void* stream, const uint16_t* dtanh_split) {
     if (M == 0) return B2C_OK;
     if (!a_split || !w_prep || Kp < BLOCK_K || Kp % BLOCK_K || M < 0)
         return b2c_set_error(B2C_ERR_ARG, "b2c_tc_linear: bad argument");
@@ -622,7 +660,7 @@ static int tc_linear_launch(const uint16_t* a_split, const uint16_t* w_prep, con
     rc = make_map(&map_w, w_prep, (uint64_t)BLOCK_N, (uint64_t)2 * Kp, BLOCK_N);
     if (rc) return rc;
     LinearArgs a;
-    a.bias = bias; a.dtanh_src = dtanh_src; a.out_f32 = out_f32; a.out_split = out_split; a.M = M;
+    a.bias = bias; a.dtanh_src = dtanh_src; a.dtanh_split = dtanh_split; a.out_f32 = out_f32; a.out_split = out_split; a.M = M;
     a.kp_blocks = Kp / BLOCK_K; a.ld_out = ld_out; a.ld_src = ld_src; a.act = act;
     a.wide_f32 = (out_f32 && ((uintptr_t)out_f32 & 31) == 0 && (ld_out & 7) == 0) ? 1 : 0;
     a.wide_split = (out_split && ((uintptr_t)out_split & 31) == 0) ? 1 : 0;
@@ -675,7 +713,13 @@ int b2c_tc_wgrad_parts(void) {
 
 int b2c_tc_wgrad(const uint16_t* dz_split, const uint16_t* x_split, float* workspace, float* dW, int M, int K, int Kp,
                  void* stream) {
+    return b2c_tc_wgrad_bias(dz_split, x_split, workspace, dW, nullptr, M, K, Kp, stream);
+}
+
+int b2c_tc_wgrad_bias(const uint16_t* dz_split, const uint16_t* x_split, float* workspace, float* dW, float* db, int M, int K,
+                      int Kp, void* stream) {
     if (M == 0) return B2C_OK;
+    if (db && K >= Kp) return b2c_set_error(B2C_ERR_ARG, "b2c_tc_wgrad_bias: x has no ones column (K == Kp)");
     if (!dz_split || !x_split || !workspace || !dW || Kp < BLOCK_K || Kp > 256 || Kp % BLOCK_K || K > Kp || M < 0)
         return b2c_set_error(B2C_ERR_ARG, "b2c_tc_wgrad: bad argument (Kp must be 64..256)");
     static int attr_set = 0;
@@ -697,7 +741,7 @@ int b2c_tc_wgrad(const uint16_t* dz_split, const uint16_t* x_split, float* works
     cudaStream_t s = (cudaStream_t)stream;
     tc_wgrad_kernel<<<num_sms, NUM_THREADS, WG_SMEM_BYTES, s>>>(map_dz, map_x, a);
     B2C_CUDA(cudaGetLastError());
-    wgrad_reduce_kernel<<<(256 * K + 255) / 256, 256, 0, s>>>(workspace, dW, num_sms, Kp, K);
+    wgrad_reduce_kernel<<<(256 * (K + 1) + 255) / 256, 256, 0, s>>>(workspace, dW, db, num_sms, Kp, K);
     B2C_CUDA(cudaGetLastError());
     return B2C_OK;
 }

@@ -104,15 +104,19 @@ class _Net:
     def forward_train(self, x, tc_version=None, x_split=None):
         if tc_version is not None and self.tc_ok():
             w1, w2, _ = self.tc_weights(tc_version)
-            s0 = x_split if x_split is not None else ops.tc_split_rows(x)
-            h1, s1 = ops.tc_linear(s0, w1, self.b[0], act=1, want_f32=True, want_split=True)
+            # the first layer's operand carries a ones column when it has a padding column to spare: its weight-gradient
+            # launch then returns the bias gradient too (backward below)
+            ones = ops.tc_has_ones_col(self.in_dim) and self.in_dim <= 256
+            s0 = x_split if x_split is not None else ops.tc_split_rows(x, ones_col=ones)
+            # h1 only leaves as the [hi | lo] operand of layer 2: the backward pass takes 1 - h1^2 from it
+            _, s1 = ops.tc_linear(s0, w1, self.b[0], act=1, want_f32=False, want_split=True)
             if self.out_dim in (1, 4):   # output layer in the layer-2 epilogue; h2 is kept for the backward pass
                 out, _, _, h2 = ops.tc_linear_head(s1, w2, self.b[1], self.W[2], self.b[2], act=1, want_f32=True)
             else:
                 h2, _ = ops.tc_linear(s1, w2, self.b[1], act=1)
                 out = ops.linear_forward(h2, self.W[2], self.b[2], 0)
             # the [hi | lo] operands are kept: the weight gradients read them again
-            return [x, h1, h2, out, s0, s1]
+            return [x, None, h2, out, s0, s1, ones]
         acts = [x]
         for k in range(len(self.shapes)):
             last = k == len(self.shapes) - 1
@@ -122,14 +126,19 @@ class _Net:
     def backward(self, acts, dout, tc_version=None):
         """Accumulates dW / db of every layer given d(loss)/d(out)."""
         if tc_version is not None and self.tc_ok():
-            x, h1, h2, _, s0, s1 = acts
-            # output layer backward also emits dz2 as the tensor-core operand
-            dz2, dz2s = ops.head_backward_split(dout, h2, self.W[2], self.dW[2], self.db[2])
-            # layer 2: input gradient and weight gradient on the tensor cores from the same [hi | lo] operand
-            dz1, dz1s = ops.tc_linear(dz2s, self.tc_weights(tc_version)[2], None, act=0, dtanh_src=h1, want_split=True)
+            x, _, h2, _, s0, s1, ones = acts
+            # output layer backward: dz2 leaves only as the tensor-core operand; its column sums are the bias gradient of
+            # layer 2 (the kernel's threads own columns)
+            _, dz2s = ops.head_backward_split(dout, h2, self.W[2], self.dW[2], self.db[2], db_hidden=self.db[1],
+                                              want_f32=False)
+            # layer 2: input gradient ((dz2 W2) * (1 - h1^2), h1 from its own operand) and weight gradient on the tensor
+            # cores from the same [hi | lo] operand
+            narrow = s0.shape[1] <= 512
+            dz1, dz1s = ops.tc_linear_dgrad(dz2s, self.tc_weights(tc_version)[2], s1, want_f32=not (narrow and ones))
             ops.tc_wgrad(dz2s, s1, self.dW[1])
-            ops.colsum(dz2, self.db[1])
-            if s0.shape[1] <= 512:
+            if narrow and ones:
+                ops.tc_wgrad(dz1s, s0, self.dW[0], db=self.db[0])       # bias gradient from the ones column
+            elif narrow:
                 ops.tc_wgrad(dz1s, s0, self.dW[0])
                 ops.colsum(dz1, self.db[0])
             else:                                    # very wide critic inputs (concat fusion): fp32 path

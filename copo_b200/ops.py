@@ -30,7 +30,7 @@ class PpoHeadArgs(ctypes.Structure):
                  ("rows", ctypes.c_int32), ("n_heads", ctypes.c_int32), ("mode", ctypes.c_int32)] +
                 [(n, ctypes.c_float) for n in ("clip_param", "vf_clip_param", "vf_loss_coeff", "entropy_coeff",
                                                "kl_coeff")] +
-                [("norm_rows", ctypes.c_int32), ("plain_value_loss", ctypes.c_int32)])
+                [("norm_rows", ctypes.c_int32), ("plain_value_loss", ctypes.c_int32), ("dyn_coeffs", ctypes.c_void_p)])
 
 
 class GaeArgs(ctypes.Structure):
@@ -67,15 +67,16 @@ def linear_forward(x, W, b, act, out=None):
     return y
 
 
-def head_backward_split(dy, h, W, dW, db):
-    """Backward of a narrow output layer on tanh activations h: returns (dz fp32, dz as [hi | lo] bf16)."""
+def head_backward_split(dy, h, W, dW, db, db_hidden=None, want_f32=True):
+    """Backward of a narrow output layer on tanh activations h: returns (dz fp32 or None, dz as [hi | lo] bf16).
+    db_hidden [K]: += column sums of dz, the bias gradient of the layer that produced h (then nobody needs dz fp32)."""
     lib = _lib_ready()
     pdy, M, N, ldy = _rows2d(dy)
     ph, _, K, ldh = _rows2d(h)
-    dz = torch.empty((M, K), dtype=torch.float32, device=dy.device)
+    dz = torch.empty((M, K), dtype=torch.float32, device=dy.device) if want_f32 else None
     dzs = torch.empty((M, 2 * K), dtype=torch.bfloat16, device=dy.device)
-    _lib.check(lib.b2c_head_backward_split(pdy, c_int(ldy), ph, c_int(ldh), P(W), P(dz), c_int(K), P(dzs), P(dW), P(db),
-                                           c_int(M), c_int(K), c_int(N), c_int(1), _lib.stream_ptr()))
+    _lib.check(lib.b2c_head_backward_tc(pdy, c_int(ldy), ph, c_int(ldh), P(W), P(dz), c_int(K), P(dzs), P(dW), P(db),
+                                        P(db_hidden), c_int(M), c_int(K), c_int(N), c_int(1), _lib.stream_ptr()))
     return dz, dzs
 
 
@@ -138,6 +139,8 @@ def ppo_head(logits, actions, old_logp, old_logits, adv, heads, cfg, mode=0, sta
     a.clip_param, a.vf_clip_param = cfg["clip_param"], cfg["vf_clip_param"]
     a.vf_loss_coeff, a.entropy_coeff, a.kl_coeff = cfg["vf_loss_coeff"], cfg["entropy_coeff"], cfg["kl_coeff"]
     a.norm_rows, a.plain_value_loss = int(norm_rows), 0 if cfg.get("old_value_loss", True) else 1
+    dyn = cfg.get("dyn_coeffs")                      # device [kl_coeff, entropy_coeff], read by the kernel at run time
+    a.dyn_coeffs = dyn.data_ptr() if dyn is not None else None
     _lib.check(lib.b2c_ppo_head(ctypes.byref(a), _lib.stream_ptr()))
     return dlogits, dvs, stats
 
@@ -256,15 +259,22 @@ def tc_padded_k(K):
     return (K + 63) // 64 * 64
 
 
-def tc_split_rows(x, out=None):
-    """fp32 [M, K] -> bf16 [M, 2*Kp] (hi | lo)."""
+def tc_split_rows(x, out=None, ones_col=False):
+    """fp32 [M, K] -> bf16 [M, 2*Kp] (hi | lo).  ones_col (needs K < Kp): 1.0 in the first padding column, so that
+    tc_wgrad(..., db=) can return the bias gradient with the weight gradient."""
     lib = _lib_ready()
     px, M, K, ldx = _rows2d(x)
     Kp = tc_padded_k(K)
     if out is None:
         out = torch.empty((M, 2 * Kp), dtype=torch.bfloat16, device=x.device)
-    _lib.check(lib.b2c_tc_split_rows(px, c_int(ldx), P(out), c_int(M), c_int(K), c_int(Kp), _lib.stream_ptr()))
+    _lib.check(lib.b2c_tc_split_rows_ones(px, c_int(ldx), P(out), c_int(M), c_int(K), c_int(Kp), c_int(int(ones_col)),
+                                          _lib.stream_ptr()))
     return out
+
+
+def tc_has_ones_col(K):
+    """True when a [*, K] input has a padding column for the ones of tc_split_rows(ones_col=True)."""
+    return K < tc_padded_k(K)
 
 
 def tc_prep_weight(W, transpose=False):
@@ -303,8 +313,23 @@ def tc_linear(a_split, w_prep, bias=None, act=0, want_f32=True, want_split=False
 _WGRAD_WS = {}
 
 
-def tc_wgrad(dz_split, x_split, dW):
-    """dW[256, K] += dz^T x on the tensor cores from the [hi | lo] operands (dz_split [M, 512], x_split [M, 2*Kp])."""
+def tc_linear_dgrad(dz_split, wT_prep, h_split, want_f32=False):
+    """Input gradient of a 256-wide tanh layer: (dz W) * (1 - h^2) with h = hi + lo taken from the layer's own operand
+    h_split [M, 512].  Returns (fp32 [M, 256] or None, bf16 split [M, 512])."""
+    lib = _lib_ready()
+    M = dz_split.shape[0]
+    Kp = dz_split.shape[1] // 2
+    assert h_split.shape == (M, 512) and h_split.is_contiguous() and wT_prep.shape == (256, 2 * Kp)
+    out_f32 = torch.empty((M, 256), dtype=torch.float32, device=dz_split.device) if want_f32 else None
+    out_split = torch.empty((M, 512), dtype=torch.bfloat16, device=dz_split.device)
+    _lib.check(lib.b2c_tc_linear_dgrad(P(dz_split), P(wT_prep), P(h_split), P(out_f32), c_int(256 if want_f32 else 0),
+                                       P(out_split), c_int(M), c_int(Kp), _lib.stream_ptr()))
+    return out_f32, out_split
+
+
+def tc_wgrad(dz_split, x_split, dW, db=None):
+    """dW[256, K] += dz^T x on the tensor cores from the [hi | lo] operands (dz_split [M, 512], x_split [M, 2*Kp]).
+    db: x_split was made with ones_col=True; db[256] += sum of dz over the rows (column K of the product)."""
     lib = _lib_ready()
     M = dz_split.shape[0]
     Kp = x_split.shape[1] // 2
@@ -314,8 +339,8 @@ def tc_wgrad(dz_split, x_split, dW):
     if key not in _WGRAD_WS:
         parts = lib.b2c_tc_wgrad_parts()
         _WGRAD_WS[key] = torch.empty(parts * 256 * Kp, dtype=torch.float32, device=dz_split.device)
-    _lib.check(lib.b2c_tc_wgrad(P(dz_split), P(x_split), P(_WGRAD_WS[key]), P(dW), c_int(M), c_int(K), c_int(Kp),
-                                _lib.stream_ptr()))
+    _lib.check(lib.b2c_tc_wgrad_bias(P(dz_split), P(x_split), P(_WGRAD_WS[key]), P(dW), P(db), c_int(M), c_int(K),
+                                     c_int(Kp), _lib.stream_ptr()))
     return dW
 
 

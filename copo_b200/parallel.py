@@ -52,17 +52,28 @@ def gather_row_counts(n_rows, dist=None, device="cpu"):
     return [int(p.item()) for p in parts]
 
 
-def minibatch_plan(row_counts, rank, minibatch_size):
-    """The reference cuts the WHOLE train batch (all workers' rows) into minibatches of `sgd_minibatch_size` rows
-    (rllib.utils.sgd.minibatches, called from train_one_step; algo_copo.py:555).  Data parallel: the global batch is
-    the union of the ranks' rows, k = ceil(total / minibatch_size), and rank r contributes the j-th of k near-equal
-    slices of its own (shuffled) rows to minibatch j.  Returns (this rank's k slices, the k GLOBAL minibatch sizes):
-    losses and gradients are normalised by the global size, so the all-reduced sum of the ranks' gradients is the
-    gradient of the whole-minibatch mean whatever the split."""
-    total = sum(row_counts)
-    k = max(1, math.ceil(total / max(1, int(minibatch_size))))
-    per_rank = [minibatch_bounds(n, k) for n in row_counts]
+def minibatch_plan_all(row_counts, minibatch_size):
+    """The reference cuts the WHOLE train batch (all workers' rows) into consecutive minibatches of
+    `sgd_minibatch_size` rows, the last one ragged (rllib.utils.sgd.minibatches, called from train_one_step;
+    algo_copo.py:555).  Data parallel: the global batch is the union of the ranks' rows and every rank contributes a
+    FIXED quota of q = minibatch_size // world of its own (shuffled) rows to each minibatch while it has rows left -
+    with one rank this is exactly rllib's slicing, and the per-rank minibatch shape repeats from step to step and from
+    iteration to iteration (so the captured gradient step, policy._graphed_step, is reused; only the ragged tail runs
+    eagerly).  k = max over ranks of ceil(n_r / q); a rank that has run out contributes an empty slice.  Returns
+    (per-rank lists of k [begin, end) slices, the k GLOBAL minibatch sizes): losses and gradients are normalised by the
+    global size, so the all-reduced sum of the ranks' gradients is the gradient of the whole-minibatch mean whatever the
+    split."""
+    world = max(1, len(row_counts))
+    q = max(1, int(minibatch_size) // world)
+    k = max(1, max(math.ceil(int(n) / q) for n in row_counts))
+    per_rank = [[(min(j * q, int(n)), min((j + 1) * q, int(n))) for j in range(k)] for n in row_counts]
     sizes = [sum(b[j][1] - b[j][0] for b in per_rank) for j in range(k)]
+    return per_rank, sizes
+
+
+def minibatch_plan(row_counts, rank, minibatch_size):
+    """This rank's slices of minibatch_plan_all and the global minibatch sizes."""
+    per_rank, sizes = minibatch_plan_all(row_counts, minibatch_size)
     return per_rank[rank], sizes
 
 

@@ -13,6 +13,8 @@ adds the data-parallel gradient all-reduce and the Adam step.  `postprocess_roll
 import math
 
 import numpy as np
+import os
+
 import torch
 
 from . import ops
@@ -89,6 +91,14 @@ class IPPOPolicy:
         self.model = self._build_model(self.config.get("seed", 0))
         self.kl_coeff = float(self.config["kl_coeff"])
         self.entropy_coeff = float(self.config["entropy_coeff"])
+        # the two coefficients that change while training, mirrored on the device: the loss kernels read them there, so a
+        # captured minibatch step (below) stays valid across KL-coefficient updates
+        self._coeffs_dev = torch.zeros(2, dtype=torch.float32, device=self.device)
+        self._coeffs_host = None
+        self._graphs = {}                                # captured minibatch steps, by batch signature
+        self._graph_seen = {}
+        self.graph_batch_rows = None                     # set by the trainer: this rank's rows in a full minibatch
+        self._graph_off = os.environ.get("B2C_LEARN_GRAPH", "1") == "0"
         self._optimizer = _Adam(self.model.flat, self.config["lr"])
         self.dist = dist                                 # torch.distributed module when data parallel, else None
         self.ar_timer = None                             # parallel.AllReduceTimer when the trainer wants the share
@@ -131,7 +141,8 @@ class IPPOPolicy:
         losses gives the whole-minibatch mean; default: this batch's rows)."""
         cfg = dict(clip_param=self.config["clip_param"], vf_clip_param=self.config["vf_clip_param"],
                    vf_loss_coeff=self.config["vf_loss_coeff"], entropy_coeff=self.entropy_coeff,
-                   kl_coeff=self.kl_coeff, old_value_loss=self.config.get("old_value_loss", True))
+                   kl_coeff=self.kl_coeff, old_value_loss=self.config.get("old_value_loss", True),
+                   dyn_coeffs=self._sync_coeffs())
         B = train_batch[OBS].shape[0]
         rows = int(global_rows) if global_rows else B
         if B == 0:                                   # a rank without rows in this minibatch contributes nothing
@@ -147,7 +158,9 @@ class IPPOPolicy:
                 return None
             key = (t.data_ptr(), tuple(t.shape))
             if key not in splits:
-                splits[key] = ops.tc_split_rows(t)
+                # ones column where the input has a padding column (the first layer's bias gradient rides in its weight
+                # gradient, models._Net.backward); the forward weights are zero in the padding
+                splits[key] = ops.tc_split_rows(t, ones_col=ops.tc_has_ones_col(t.shape[1]) and t.shape[1] <= 256)
             return splits[key]
 
         acts_p = pol.forward_train(train_batch[OBS], tc, split_of(train_batch[OBS]))
@@ -164,8 +177,18 @@ class IPPOPolicy:
             model.nets[net_name].backward(acts, dv.unsqueeze(1), tc)
         return self._fill_tower_stats(model, st / rows, cfg, train_batch)
 
+    def _sync_coeffs(self):
+        """[kl_coeff, entropy_coeff] on the device, refreshed when the host values changed."""
+        cur = (self.kl_coeff, self.entropy_coeff)
+        if cur != self._coeffs_host:
+            self._coeffs_dev.copy_(torch.tensor(cur, dtype=torch.float32))
+            self._coeffs_host = cur
+        return self._coeffs_dev
+
     def _fill_tower_stats(self, model, m, cfg, train_batch):
-        total = m[0] + cfg["vf_loss_coeff"] * (m[1] + m[2] + m[3]) - cfg["entropy_coeff"] * m[4] + cfg["kl_coeff"] * m[5]
+        c = cfg.get("dyn_coeffs")
+        klc, entc = (c[0], c[1]) if c is not None else (cfg["kl_coeff"], cfg["entropy_coeff"])
+        total = m[0] + cfg["vf_loss_coeff"] * (m[1] + m[2] + m[3]) - entc * m[4] + klc * m[5]
         ts = model.tower_stats
         ts["total_loss"], ts["mean_policy_loss"], ts["mean_vf_loss"] = total, m[0], m[1]
         ts["mean_entropy"], ts["mean_kl_loss"] = m[4], m[5]
@@ -191,13 +214,92 @@ class IPPOPolicy:
             return int(t.item())
         return B
 
+    def _grad_step(self, train_batch, rows):
+        """zero grads -> loss forward + backward.  Device work only (no host reads): this is what gets captured."""
+        self.model.zero_grad()
+        self.loss(self.model, None, train_batch, global_rows=rows)
+
+    def _graphed_step(self, train_batch, rows):
+        """The minibatch's forward + backward as ONE CUDA-graph launch: ~110 kernel launches and
+        the tiny statistics kernels replay without per-launch host work.  Captured once per batch signature (row count,
+        columns); the minibatch is copied into the graph's static input buffers by one multi-tensor copy.  Returns False
+        when this batch runs eagerly (graphs off, data-dependent shapes, capture failed)."""
+        B = train_batch[OBS].shape[0]
+        if self._graph_off or B == 0 or self.model._tc() is None:
+            return False
+        tensors = {k: v for k, v in train_batch.items() if torch.is_tensor(v)}
+        key = (B, rows) + tuple(sorted((k, tuple(v.shape), v.dtype) for k, v in tensors.items()))
+        g = self._graphs.get(key)
+        if g is None:
+            # what to capture: full-size minibatches repeat from step to step and iteration to iteration
+            # (parallel.minibatch_plan_all); the ragged tail of an epoch comes back once per SGD epoch and then never
+            # again, so it runs eagerly.  The trainer names the steady size (graph_batch_rows); without that hint a
+            # signature is captured once it has shown up more often than any tail would
+            if self.graph_batch_rows is not None:
+                if B != self.graph_batch_rows:
+                    return False
+            else:
+                seen = self._graph_seen.get(key, 0)
+                if seen < 8:
+                    if len(self._graph_seen) > 64:
+                        self._graph_seen.clear()
+                    self._graph_seen[key] = seen + 1
+                    return False
+            if len(self._graphs) >= 2:
+                self._graphs.clear()
+            static, by_ptr = {}, {}
+            for k, v in tensors.items():                 # columns that alias one tensor keep aliasing one buffer
+                if v.data_ptr() not in by_ptr:
+                    by_ptr[v.data_ptr()] = torch.empty_like(v, memory_format=torch.contiguous_format)
+                static[k] = by_ptr[v.data_ptr()]
+            g = dict(static=static, dst=list(by_ptr.values()), graph=None)
+            try:
+                self._sync_coeffs()
+                torch._foreach_copy_(g["dst"], [tensors[k] for k in self._first_keys(tensors)])
+                side = torch.cuda.Stream(device=self.device)
+                side.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(side):            # warm-up outside capture: lazy initialisation, workspaces
+                    self._grad_step(static, rows)
+                torch.cuda.current_stream(self.device).wait_stream(side)
+                for net in self.model.nets.values():     # the weight operands are rebuilt INSIDE the graph on every replay
+                    net._tc_version = None
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    self._grad_step(static, rows)
+                g["graph"] = graph
+                g["out"] = (self.stats_vector, dict(self.model.tower_stats))
+            except Exception as e:                       # pragma: no cover - depends on the driver / torch build
+                import warnings
+                warnings.warn("learn_on_batch: CUDA-graph capture failed (%r); running eagerly" % (e,))
+                self._graph_off = True
+                return False
+            self._graphs[key] = g
+        torch._foreach_copy_(g["dst"], [tensors[k] for k in self._first_keys(tensors)])
+        self._sync_coeffs()
+        g["graph"].replay()
+        self.stats_vector, ts = g["out"]
+        self.model.tower_stats.update(ts)
+        for net in self.model.nets.values():             # eager users must not trust the operands cached at capture time
+            net._tc_version = None
+        return True
+
+    @staticmethod
+    def _first_keys(tensors):
+        """One key per distinct tensor, in dict order (the order the static buffers were made in)."""
+        seen, keys = set(), []
+        for k, v in tensors.items():
+            if v.data_ptr() not in seen:
+                seen.add(v.data_ptr())
+                keys.append(k)
+        return keys
+
     def learn_on_batch(self, train_batch, global_rows=None):
         """zero grads -> loss fwd+bwd -> (all-reduce) -> Adam.  Returns the stats dict of this minibatch.  Data
         parallel: every rank's loss is normalised by the GLOBAL minibatch row count, so the all-reduced SUM of the
         gradients is the gradient of the whole-minibatch mean (ranks may hold different numbers of rows)."""
         rows = self._global_rows(train_batch[OBS].shape[0], global_rows)
-        self.model.zero_grad()
-        self.loss(self.model, None, train_batch, global_rows=rows)
+        if not self._graphed_step(train_batch, rows):
+            self._grad_step(train_batch, rows)
         parallel.allreduce_sum_(self.model.grad, self.dist, self.ar_timer)  # one NCCL all-reduce of the flat gradient
         self._optimizer.apply(self.model.grad)
         self.model.mark_weights_changed()

@@ -215,6 +215,7 @@ class IPPOTrainer:
     def _learn(self, ro):
         cols, scal, wide, valid = self._flatten(ro)
         self._row_counts = parallel.gather_row_counts(valid.numel(), _dist(), self.device)
+        self.policy.graph_batch_rows = max(1, int(self.config["sgd_minibatch_size"]) // max(1, len(self._row_counts)))
         acc, n = torch.zeros(len(self.LEARNER_KEYS), dtype=torch.float64, device=self.device), 0
         for _ in range(int(self.config["num_sgd_iter"])):
             for batch, rows in self._minibatches(cols, scal, wide, valid, int(self.config["sgd_minibatch_size"])):

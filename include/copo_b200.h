@@ -161,6 +161,9 @@ typedef struct {
                                      whole-minibatch mean even when ranks hold different numbers of rows */
     int32_t plain_value_loss;     /* 1: old_value_loss=False, vf_loss = clamp((v - target)^2, 0, vf_clip_param)
                                      (algo_ippo.py:146-148, algo_copo.py:358-363) */
+    const float* dyn_coeffs;      /* NULL, or device [2] = {kl_coeff, entropy_coeff} read by the kernel at run time instead
+                                     of the two by-value fields (KLCoeffMixin.update_kl changes kl_coeff between
+                                     iterations; a launch captured in a CUDA graph keeps working) */
 } b2c_ppo_head_args;
 int b2c_ppo_head(const b2c_ppo_head_args* args, void* stream);
 
@@ -262,6 +265,20 @@ int b2c_tc_wgrad(const uint16_t* dz_split, const uint16_t* x_split, float* works
                  void* stream);
 int b2c_tc_linear(const uint16_t* a_split, const uint16_t* w_prep, const float* bias, const float* dtanh_src, int ld_src,
                   float* out_f32, int ld_out, uint16_t* out_split, int M, int Kp, int act, void* stream);
+/* Learner backward without fp32 intermediates (replaces the autograd of SlimFC layers, algo_copo.py:311-424 loss.backward()):
+ *   b2c_tc_split_rows_ones  as b2c_tc_split_rows, with 1.0 in the first padding column (K < Kp)
+ *   b2c_tc_linear_dgrad     out = (dz W) * (1 - h^2), h = hi + lo read from the layer's own [hi | lo] operand h_split [M][512]
+ *   b2c_tc_wgrad_bias       as b2c_tc_wgrad; db[256] += column K of dz^T x (x from b2c_tc_split_rows_ones)
+ *   b2c_head_backward_tc    as b2c_head_backward_split; dz_colsum[K] += column sums of dz (bias gradient of the layer
+ *                           below); dz may be NULL (only the tensor-core operand leaves) */
+int b2c_tc_split_rows_ones(const float* x, int ldx, uint16_t* out, int M, int K, int Kp, int ones_col, void* stream);
+int b2c_tc_linear_dgrad(const uint16_t* dz_split, const uint16_t* wT_prep, const uint16_t* h_split, float* out_f32,
+                        int ld_out, uint16_t* out_split, int M, int Kp, void* stream);
+int b2c_tc_wgrad_bias(const uint16_t* dz_split, const uint16_t* x_split, float* workspace, float* dW, float* db, int M, int K,
+                      int Kp, void* stream);
+int b2c_head_backward_tc(const float* dy, int ldy, const float* h, int ldh, const float* W, float* dz, int ldz,
+                         uint16_t* dz_split, float* dW, float* db, float* dz_colsum, int M, int K, int N, int dtanh,
+                         void* stream);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -61,7 +61,7 @@ def _worker(rank, world, port, q):
         grads.append(g)
         kls.append(float(kl))
     # single-process reference over the same global minibatches (rank 0 rows then rank 1 rows of each slice)
-    all_bounds = [parallel.minibatch_bounds(n, len(sizes)) for n in counts]
+    all_bounds = parallel.minibatch_plan_all(counts, 32)[0]
     err = 0.0
     for j in range(len(sizes)):
         idx = list(range(all_bounds[0][j][0], all_bounds[0][j][1])) + [30 + r for r in range(all_bounds[1][j][0],
@@ -126,8 +126,10 @@ def test_world_size_two_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res[0]["k"] == res[1]["k"] == 6 and res[0]["bounds_ok"] and res[1]["bounds_ok"]
-    assert res[0]["counts"] == res[1]["counts"] == [30, 70] and res[0]["sizes"] == res[1]["sizes"] == [26, 26, 24, 24]
-    assert res[0]["bounds"] == [(0, 8), (8, 16), (16, 23), (23, 30)]
+    assert res[0]["counts"] == res[1]["counts"] == [30, 70] and res[0]["sizes"] == res[1]["sizes"] == [32, 30, 16, 16, 6]
+    # a fixed quota of 32 // 2 rows per rank and minibatch; the rank with fewer rows runs out and contributes empty slices
+    assert res[0]["bounds"] == [(0, 16), (16, 30), (30, 30), (30, 30), (30, 30)]
+    assert res[1]["bounds"] == [(0, 16), (16, 32), (32, 48), (48, 64), (64, 70)]
     assert res[0]["dp_grad_err"] < 1e-12 and res[1]["dp_grad_err"] < 1e-12
     for r in (0, 1):
         assert np.allclose(res[r]["mean_std"], res[r]["want_mean_std"], rtol=1e-6)
@@ -142,7 +144,10 @@ def test_single_process_helpers():
     b = parallel.minibatch_bounds(10, 3)
     assert b == [(0, 4), (4, 7), (7, 10)]
     assert parallel.minibatch_bounds(2, 4) == [(0, 1), (1, 2), (2, 2), (2, 2)]      # empty slices only when rows < k
-    assert parallel.minibatch_plan([10], 0, 4) == ([(0, 4), (4, 7), (7, 10)], [4, 3, 3])
+    # one rank: rllib's slicing (full minibatches, ragged tail); two ranks: a fixed quota of minibatch_size // 2 rows each
+    assert parallel.minibatch_plan([10], 0, 4) == ([(0, 4), (4, 8), (8, 10)], [4, 4, 2])
+    assert parallel.minibatch_plan([5, 9], 1, 8) == ([(0, 4), (4, 8), (8, 9)], [8, 5, 1])
+    assert parallel.minibatch_plan([5, 9], 0, 8) == ([(0, 4), (4, 5), (5, 5)], [8, 5, 1])
     assert parallel.minibatch_plan([0, 5], 0, 512) == ([(0, 0)], [5])
     assert parallel.gather_row_counts(7) == [7]
     t = torch.ones(3)
