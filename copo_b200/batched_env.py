@@ -160,12 +160,17 @@ class BatchedDrivingEnv:
             self.d2h_bytes_per_step = sum(v.numel() * v.element_size() for v in self._host.values())
         return self._host
 
-    def step_host(self, actions_host, obs_split=None, wait=True):
+    def step_host(self, actions_host, obs_split=None, wait=True, outputs=None):
         """actions_host: float32 [S, A, 2] numpy array or CPU tensor (pinned tensors are read in place).  Copies it
         to the device, steps every scene and returns pinned host tensors of every output (valid until the next call).
         With wait=False the call returns as soon as the work is enqueued - the outputs travel on the copy stream
-        while the caller queues more device work on `host_step_out` - and are valid after `wait_host()`."""
+        while the caller queues more device work on `host_step_out` - and are valid after `wait_host()`.
+        `outputs`: names (of HOST_KEYS) the caller reads on the host; the others stay on the device (their host tensors
+        keep stale values) - a host policy that needs `("obs", "reward", "flags")` does not pay PCIe time for the masks,
+        lists and ids.  Default: everything.  `last_d2h_bytes` is what this call moved."""
         host = self._host_buffers()
+        sel = tuple(self.HOST_KEYS) if outputs is None else tuple(outputs)
+        assert all(k in self.HOST_KEYS for k in sel), sel
         a = torch.as_tensor(actions_host, dtype=torch.float32)
         assert tuple(a.shape) == (self.S, self.A, 2), a.shape
         cur = torch.cuda.current_stream(self.device)
@@ -186,11 +191,21 @@ class BatchedDrivingEnv:
             self.step(self._dev_act[f:f + n], out=out, scenes=(f, n))
             self._ev_chunk[c].record(cur)
             self._copy_stream.wait_event(self._ev_chunk[c])
-            with torch.cuda.stream(self._copy_stream):
-                host_obs[f:f + n].copy_(dev_obs[f:f + n], non_blocking=True)
+            if "obs" in sel:
+                with torch.cuda.stream(self._copy_stream):
+                    host_obs[f:f + n].copy_(dev_obs[f:f + n], non_blocking=True)
+        moved = host_obs.numel() * 4 if "obs" in sel else 0
         with torch.cuda.stream(self._copy_stream):
-            self._arena_host[self._rest_off:].copy_(self._arena_dev[self._rest_off:], non_blocking=True)
+            if outputs is None:                              # everything behind the observations: one copy of the arena tail
+                self._arena_host[self._rest_off:].copy_(self._arena_dev[self._rest_off:], non_blocking=True)
+                moved = self.d2h_bytes_per_step
+            else:
+                for k in sel:
+                    if k != "obs":
+                        host[k].copy_(self.host_step_out[k], non_blocking=True)
+                        moved += host[k].numel() * host[k].element_size()
             self._ev_copy.record(self._copy_stream)
+        self.last_d2h_bytes = moved
         self._copy_pending = True
         if wait:
             self.wait_host()

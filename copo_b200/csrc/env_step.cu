@@ -320,8 +320,9 @@ env_step_kernel(const __grid_constant__ EnvConfig cfg, const __grid_constant__ E
             io.reward[g] = v.rew[ia];
             io.flags[g] = (uint8_t)v.flags[ia];
             if (io.agent_id) io.agent_id[g] = v.geti(F_ID, ia);
-            if (io.lcf) io.lcf[g] = v.f(F_LCF, ia);
-            phase_observe_ego(v, cfg, ia);
+            const float lcf_now = step_lcf(v, cfg, scene0 + sl_a, ia);
+            if (io.lcf) io.lcf[g] = lcf_now;
+            phase_observe_ego(v, cfg, ia, lcf_now);
             if (!SPLIT) phase_lidar_init(v, ia);
         }
         {

@@ -133,8 +133,16 @@ class MultiAgentDrivingEnv:
         ids = out["agent_id"][0].cpu().numpy()
         nei_mask = out["nei_mask"][0].cpu().numpy().view(np.uint64)
         o, r, d, info = {}, {}, {}, {}
-        name = lambda i: "agent%d" % int(ids[i])
         part = [i for i in range(self.A) if flags[i] & (FLAG_VALID | FLAG_SPAWNED)]
+        # The agent that ACTED in slot i this step is whoever occupied it after the previous step; the kernel's agent_id
+        # is the occupant after this step.  They differ when the slot's agent terminated and the slot was refilled in
+        # the same step (delay_done = 0, or the scene's horizon restart): such a row carries two agents - the terminal
+        # reward / flags of the one that acted, the first observation of the one that spawned.
+        occupant = getattr(self, "_occupant", {})
+        new_name = lambda i: "agent%d" % int(ids[i])
+        reused = {i for i in part if not first and (flags[i] & FLAG_VALID) and (flags[i] & FLAG_SPAWNED) and
+                  i in occupant and occupant[i] != new_name(i)}
+        name = lambda i: occupant[i] if i in reused else new_name(i)        # the agent this row's step data belongs to
         self.vehicles_including_just_terminated = {name(i): _Vehicle(ff[F_X, i], ff[F_Y, i], ff[F_V, i], ff[F_H, i])
                                                    for i in part}
         self.vehicles = {name(i): self.vehicles_including_just_terminated[name(i)] for i in part
@@ -143,7 +151,7 @@ class MultiAgentDrivingEnv:
         route_len = self._sim.tables.route_len
         for i in part:
             k = name(i)
-            o[k] = obs[i].copy()
+            o[k] = self._last_obs_of.get(k, obs[i]).copy() if i in reused else obs[i].copy()
             if first:
                 continue
             f = int(flags[i])
@@ -159,22 +167,38 @@ class MultiAgentDrivingEnv:
             d2 = (dx * dx + dy * dy).astype(np.float32)
             dist = {j: float(np.sqrt(np.float64(d2[n]))) for n, j in enumerate(others)}
             order = sorted(others, key=lambda j: dist[j])
+            info[k] = dict(all_agents=[name(j) for j in part], neighbours=[name(j) for j in order],
+                           neighbours_distance=[dist[j] for j in order])
+            if not acted:
+                # a freshly spawned agent has not stepped yet: MetaDrive gives it no step_reward / velocity / cost /
+                # episode_* entries (the reference's recorder keys on that: eval/recoder.py:128), only what the wrappers add
+                continue
             total = float(route_len[int(fld[F_ROUTE, i])])
             cur = float(ff[F_DONE_LEN, i] + ff[F_S, i])
-            info[k] = dict(velocity=float(ff[F_V, i]) * 3.6, steering=float(ff[F_STEER, i]),
+            info[k].update(velocity=float(ff[F_V, i]) * 3.6, steering=float(ff[F_STEER, i]),
                            acceleration=float(ff[F_THR, i]), step_reward=r[k], cost=1.0 if f & FLAG_CRASH else 0.0,
                            episode_length=int(fld[F_EPLEN, i]), episode_reward=float(ff[F_EPREW, i]),
                            arrive_dest=bool(f & FLAG_ARRIVE), crash=bool(f & FLAG_CRASH),
                            crash_vehicle=bool(f & FLAG_CRASH), out_of_road=bool(f & FLAG_OUT),
                            max_step=bool(f & FLAG_MAXSTEP), route_completion=cur / total, track_length=total,
                            current_distance=cur, step_energy=0.0, episode_energy=0.0,
-                           raw_action=(float(ff[F_STEER, i]), float(ff[F_THR, i])),
-                           all_agents=[name(j) for j in part], neighbours=[name(j) for j in order],
-                           neighbours_distance=[dist[j] for j in order])
+                           raw_action=(float(ff[F_STEER, i]), float(ff[F_THR, i])))
         if not first:
             d["__all__"] = bool(out["scene_done"][0]) or (self.episode_step >= self.config["horizon"])
         self._last_out = out
         self._slot_now = {name(i): i for i in part}
+        # the new occupants of reused slots: first observation under their own name, acting from the next step on
+        for i in reused:
+            k2 = new_name(i)
+            o[k2] = obs[i].copy()
+            r[k2], d[k2] = 0.0, False
+            info[k2] = dict(all_agents=[name(j) for j in part], neighbours=[], neighbours_distance=[])
+            self._slot_of[k2] = i
+            self._slot_now[k2] = i
+            self.vehicles[k2] = self.vehicles_including_just_terminated[k2] = _Vehicle(ff[F_X, i], ff[F_Y, i], ff[F_V, i],
+                                                                                        ff[F_H, i])
+        self._occupant = {i: new_name(i) for i in part}
+        self._last_obs_of = dict(o)
         return o, r, d, info
 
     def reset(self, force_seed=None):

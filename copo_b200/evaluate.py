@@ -13,11 +13,13 @@ from .batched_env import (BatchedDrivingEnv, FLAG_ARRIVE, FLAG_CRASH, FLAG_DONE,
 
 
 def evaluate(model, env="MultiAgentIntersectionEnv", num_scenes=64, num_agents=None, horizon=1000, seed=0,
-             deterministic=False, lcf_mean=0.0, lcf_std=0.1, neighbours_distance=20.0, device=None, append_lcf=None):
+             deterministic=False, lcf_mean=0.0, lcf_std=0.1, neighbours_distance=20.0, device=None, append_lcf=None,
+             trace=None):
     """Runs one episode of `horizon` steps in every scene with `model` (CCModel / CoPOModel) acting for all agents.
     `neighbours_distance` is RecorderEnv's evaluation radius (default 20, recoder.py:75).  `append_lcf`: whether the
     policy takes the LCF as its last observation entry (CoPO policies); default: a CoPOModel does, any other model
-    does when its input is one wider than the map's base observation."""
+    does when its input is one wider than the map's base observation.  `trace`: a list that receives every step's
+    actions (numpy [S, A, 2]) - tests replay them through the oracle simulator and recompute the report."""
     from .maps import build_map
     from .models import CoPOModel
     map_name = MAP_OF_ENV.get(env, env)
@@ -40,6 +42,8 @@ def evaluate(model, env="MultiAgentIntersectionEnv", num_scenes=64, num_agents=N
             actions = model.forward(obs)[:, :2].contiguous()
         else:
             _, actions, _ = model.forward_sample(obs, seed, t)
+        if trace is not None:
+            trace.append(actions.view(S, A, 2).cpu().numpy().copy())
         out = sim.step(actions.view(S, A, 2))
         f = out["flags"]
         valid = (f & FLAG_VALID) > 0

@@ -374,10 +374,29 @@ class OracleSim:
         part = acted | spawned
         nb = self._neighbours(part, rew)
         # ---- 9. observations ---------------------------------------------------------------------
-        obs = self._observe(part)
+        lcf_now = self._step_lcf()
+        obs = self._observe(part, lcf_now)
         out = dict(obs=obs, reward=rew.astype(f32), flags=flags.astype(np.uint8), scene_done=scene_done,
-                   agent_id=self.agent_id.copy(), lcf=self.lcf.copy(), **nb)
+                   agent_id=self.agent_id.copy(), lcf=lcf_now.copy(), **nb)
         return out
+
+    def _step_lcf(self):
+        """The LCF the wrapper hands out this step: the episode value (lcf_map), except under a forced mean with the
+        normal distribution, where the reference redraws it at every call of _add_lcf, i.e. every step of every agent,
+        and leaves lcf_map alone (env_wrappers.py:337-342, 398-403).  Counter-based: (scene, episode, episode step,
+        slot), counters with bit 31 set (the sequential scene stream never gets there)."""
+        cfg = self.cfg
+        if (not cfg.append_lcf) or cfg.lcf_uniform or cfg.force_lcf == f32(-100.0):
+            return self.lcf
+        S, A = self.S, self.A
+        slot = np.arange(A, dtype=np.uint64)[None, :]
+        ctr0 = np.uint64(0x80000000) | (self.ep_step.astype(np.uint64)[:, None] << np.uint64(10)) | (slot << np.uint64(4))
+        z = np.zeros((S, A), f32)
+        for t in range(12):
+            z = z + u32_to_unit(rng_u32(cfg.seed, self.scene_id[:, None], self.episode[:, None], ctr0 + np.uint64(t)))
+        z = z - f32(6.0)
+        lcf = cfg.force_lcf + cfg.lcf_std * z
+        return np.where(lcf < -ONE, -ONE, np.where(lcf > ONE, ONE, lcf)).astype(f32)
 
     # ------------------------------------------------------------------------------------------
     def _neighbours(self, part, rew):
@@ -427,7 +446,7 @@ class OracleSim:
                     dist=dist)
 
     # ------------------------------------------------------------------------------------------
-    def _observe(self, part):
+    def _observe(self, part, lcf_now=None):
         S, A, m, cfg = self.S, self.A, self.m, self.cfg
         D = self.obs_dim
         obs = np.zeros((S, A, D), f32)
@@ -476,7 +495,7 @@ class OracleSim:
             obs[..., b:b + m.n_side] = self._side(l, wl, wr, hd, m.n_side)
             b += m.n_side
         if cfg.append_lcf:
-            obs[..., b] = (self.lcf + ONE) * HALF
+            obs[..., b] = ((self.lcf if lcf_now is None else lcf_now) + ONE) * HALF
         return np.where(part[:, :, None], obs, ZERO).astype(f32)
 
     @staticmethod

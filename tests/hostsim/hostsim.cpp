@@ -58,8 +58,9 @@ extern "C" int hostsim_step(const EnvConfig* cfgp, const uint32_t* map, int map_
             io->nei_mask[g] = n.nei_mask; io->mf_mask[g] = n.mf_mask; io->nei_reward[g] = n.nei_reward;
             for (int k = 0; k < NEI_K; ++k) io->nei_list[g * NEI_K + k] = n.list[k];
             io->reward[g] = v.rew[i]; io->flags[g] = (uint8_t)v.flags[i];
-            io->agent_id[g] = v.geti(F_ID, i); io->lcf[g] = v.f(F_LCF, i);
-            phase_observe_ego(v, cfg, i);
+            const float lcf_now = step_lcf(v, cfg, scene, i);
+            io->agent_id[g] = v.geti(F_ID, i); io->lcf[g] = lcf_now;
+            phase_observe_ego(v, cfg, i, lcf_now);
             phase_lidar_init(v, i);
         }
         io->global_reward[scene] = phase_global_reward(v);

@@ -231,5 +231,14 @@ def test_step_host_matches_device_step(S, chunks):
             assert torch.equal(split.reshape(S * A, -1).view(torch.int16), ws.view(torch.int16))
     assert e_host.d2h_bytes_per_step == sum(want[k].numel() * want[k].element_size()
                                             for k in BatchedDrivingEnv.HOST_KEYS)
+    # a host consumer that only reads observations, rewards and flags: the other outputs stay on the device
+    act = rng.uniform(-1, 1, (S, A, 2)).astype(np.float32)
+    want = e_dev.step(torch.from_numpy(act).cuda())
+    stale = e_host._host["nei_mask"].clone()
+    got = e_host.step_host(act, outputs=("obs", "reward", "flags"))
+    for k in ("obs", "reward", "flags"):
+        assert torch.equal(got[k], want[k].cpu()), k
+    assert torch.equal(got["nei_mask"], stale) and torch.equal(e_host.host_step_out["nei_mask"], want["nei_mask"])
+    assert e_host.last_d2h_bytes == sum(want[k].numel() * want[k].element_size() for k in ("obs", "reward", "flags"))
     e_dev.close()
     e_host.close()

@@ -70,9 +70,12 @@ def test_dict_env_follows_reference_interface():
             assert abs(inf["coordinated_rewards"] - (math.cos(inf["lcf"] * math.pi / 2) * r[k] +
                                                      math.sin(inf["lcf"] * math.pi / 2) * inf["nei_rewards"])) < 1e-9
             assert want_r[k] == r[k]                                   # return_native_reward=True
-            for key in ("velocity", "steering", "acceleration", "step_reward", "cost", "episode_length",
-                        "episode_reward", "arrive_dest", "crash", "out_of_road", "route_completion", "all_agents"):
-                assert key in inf
+            if w["flags"][0, s] & osim.F_VALID:
+                for key in ("velocity", "steering", "acceleration", "step_reward", "cost", "episode_length",
+                            "episode_reward", "arrive_dest", "crash", "out_of_road", "route_completion", "all_agents"):
+                    assert key in inf
+            else:                              # freshly spawned: only what the wrappers add (eval/recoder.py:128 keys on it)
+                assert "step_reward" not in inf and "velocity" not in inf and "all_agents" in inf
             seen_done += int(d[k])
     assert seen_done > 0
     with pytest.raises(AssertionError):
@@ -198,3 +201,60 @@ def test_attributes_the_reference_reads_off_a_metadrive_env():
     env.reset()
     assert env.engine.global_seed == 5001                 # the next episode of the same start seed
     assert set(env.agent_manager.active_agents) == set(env.vehicles)
+
+
+def test_forced_lcf_with_the_normal_distribution_is_redrawn_every_step():
+    """env_wrappers.py:337-342, 398-403: with `force_lcf` set and lcf_dist == "normal" every call of `_add_lcf` - every
+    step of every agent - draws a fresh N(force_lcf, std) value (clipped to [-1, 1]) for the observation, info["lcf"] and
+    the coordinated reward; the episode value (lcf_map) stays what it was at spawn.  With "uniform" the forced value is
+    used as is (previous test)."""
+    cls = envs.get_lcf_env(envs.MultiAgentIntersectionEnv)
+    env = cls({"num_agents": 6, "start_seed": 2, "return_native_reward": False, "force_lcf": 0.5, "lcf_normal_std": 0.2})
+    o = env.reset()
+    seen = {k: [] for k in o}
+    state_lcf = None
+    for t in range(25):
+        o, r, d, i = env.step({k: np.array([0.0, 0.3], np.float32) for k in env.vehicles})
+        st = env._sim.sim.state()["lcf"][0].copy()
+        if state_lcf is not None:
+            assert np.array_equal(st[:6], state_lcf[:6])           # the episode value does not move
+        state_lcf = st
+        for k in r:
+            lcf = i[k]["lcf"]
+            assert -1.0 <= lcf <= 1.0
+            assert o[k][-1] == np.float32((np.float32(lcf) + np.float32(1.0)) * np.float32(0.5))
+            rad = lcf * np.pi / 2
+            assert abs(r[k] - (np.cos(rad) * i[k]["native_rewards"] + np.sin(rad) * i[k]["nei_rewards"])) < 1e-6
+            seen.setdefault(k, []).append(lcf)
+    vals = np.concatenate([np.asarray(v) for v in seen.values() if len(v) > 5])
+    assert all(len(set(v)) == len(v) for v in seen.values() if len(v) > 5)      # a new draw every step
+    assert abs(vals.mean() - 0.5) < 0.1 and 0.1 < vals.std() < 0.3
+
+
+def test_delay_done_zero_reports_the_terminated_agent_and_its_successor_separately():
+    """delay_done = 0: a slot can lose its agent and get a new one in the same step.  The dict API then carries BOTH
+    agents, as MetaDrive does: the terminated one under its own name with done = True, its terminal reward and its step
+    info; the successor under a fresh name with its first observation, no step info, done = False - and the successor
+    can be driven from the next step on."""
+    cls = envs.get_lcf_env(envs.MultiAgentIntersectionEnv)
+    env = cls({"num_agents": 10, "start_seed": 4, "delay_done": 0})
+    o = env.reset()
+    born, died, both = set(o), set(), 0
+    rng = np.random.default_rng(1)
+    for t in range(160):
+        acts = {k: np.array([0.5 + 0.3 * rng.standard_normal(), 1.0], np.float32) for k in env.vehicles}
+        assert set(acts) <= set(o)                                     # everything that may act has been observed
+        o, r, d, i = env.step(acts)
+        assert set(o) == set(r) == set(i) and set(d) == set(o) | {"__all__"}
+        ended = {k for k in r if d[k]}
+        fresh = {k for k in o if k not in born}
+        for k in ended:
+            assert k in acts and "step_reward" in i[k] and k not in env.vehicles
+        for k in fresh:
+            assert not d[k] and r[k] == 0.0 and "step_reward" not in i[k] and k in env.vehicles
+        slots_of_ended = {env._slot_now[k] for k in ended}
+        both += len({env._slot_now[k] for k in fresh} & slots_of_ended)
+        assert not (ended & died)                                      # nobody is reported done twice
+        born |= fresh
+        died |= ended
+    assert both > 0 and len(died) > 5                                  # same-step reuse happened and was split

@@ -141,6 +141,59 @@ def test_batched_evaluation_of_a_shipped_policy():
     assert res["agent_steps"] > 16 * 20 * 100 and res["velocity_step_mean_episode_max"] > 1.0
 
 
+def test_evaluation_report_equals_the_oracle_replay():
+    """the report `evaluate()` reduces on the device against an independent computation - the same
+    actions replayed through the numpy oracle simulator (bit-identical step outputs), the report's quantities recomputed
+    from the oracle's outputs with plain numpy following eval/recoder.py:177-349 (rates over finished agents, step means
+    over acting agents, neighbour counts within the evaluation radius)."""
+    import os
+    from copo_b200.evaluate import evaluate
+    from copo_b200.maps import build_map
+    from copo_b200.models import CCModel
+    from oracle import sim as osim
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mlp_golden.npz"))
+    sub = {k[len("copo_inter") + 1:]: z[k] for k in z.files if k.startswith("copo_inter/")}
+    m = CCModel(92)
+    m.load_policy_npz(sub)
+    S, A, H = 3, 30, 120
+    trace = []
+    res = evaluate(m, "MultiAgentIntersectionEnv", num_scenes=S, num_agents=A, horizon=H, seed=4, lcf_mean=0.225,
+                   lcf_std=0.1, trace=trace)
+    assert len(trace) == H
+    cfg = osim.SimConfig(num_agents=A, horizon=H, auto_reset=False, append_lcf=True, seed=4, lcf_mean=0.225, lcf_std=0.1,
+                         neighbours_distance=20.0)
+    ref = osim.OracleSim(build_map("intersection"), S, A, cfg)
+    ref.reset()
+    acc = dict(done=0, success=0, crash=0, out=0, max_step=0, steps=0, reward=0.0, cost=0, nei=0)
+    vels = []
+    for t in range(H):
+        o = ref.step(trace[t])
+        f = o["flags"].astype(np.int64)
+        valid, done = (f & 1) > 0, (f & 2) > 0
+        acc["steps"] += int(valid.sum()); acc["done"] += int(done.sum())
+        acc["success"] += int(((f & 4) > 0).sum()); acc["crash"] += int(((f & 8) > 0).sum())
+        acc["out"] += int(((f & 16) > 0).sum()); acc["max_step"] += int((((f & 32) > 0) & done).sum())
+        acc["reward"] += float((o["reward"].astype(np.float64) * valid).sum())
+        acc["cost"] += int((((f & 8) > 0) & valid).sum())
+        bits = o["nei_mask"].astype(np.uint64)
+        cnt = np.zeros(bits.shape, np.int64)
+        for j in range(A):
+            cnt += ((bits >> np.uint64(j)) & np.uint64(1)).astype(np.int64)
+        acc["nei"] += int((cnt * valid).sum())
+        if valid.any():
+            vels.append(float((o["obs"][..., 3].astype(np.float64) * valid).sum() / valid.sum() * 22.22222137451172 * 3.6))
+    d = max(acc["done"], 1)
+    want = {"success_rate": acc["success"] / d, "crash_rate": acc["crash"] / d, "out_rate": acc["out"] / d,
+            "max_step_rate": acc["max_step"] / d, "num_agents_total": acc["done"], "agent_steps": acc["steps"],
+            "step_reward_mean": acc["reward"] / acc["steps"], "cost_step_mean": acc["cost"] / acc["steps"],
+            "num_neighbours_step_mean": acc["nei"] / acc["steps"], "velocity_step_mean_episode_mean": np.mean(vels),
+            "velocity_step_mean_episode_min": np.min(vels), "velocity_step_mean_episode_max": np.max(vels),
+            "num_agents_success_per_300_steps": acc["success"] / S / H * 300.0}
+    assert acc["done"] > 10 and acc["steps"] > S * 20 * H // 2
+    for k, w in want.items():
+        assert abs(res[k] - w) <= 1e-5 * max(1.0, abs(w)), (k, res[k], w)
+
+
 def test_curriculum_changes_the_population_by_slot_masking():
     from copo_b200 import trainer as T
     from copo_b200.curriculum import ChangeNCallback
