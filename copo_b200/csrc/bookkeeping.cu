@@ -134,13 +134,34 @@ __global__ void cc_obs_fuse_kernel(const float* __restrict__ obs, const float* _
         if (cnt == 0) return;
         const float inv = 1.0f / (float)cnt;
         const int W = D + (counterfactual ? AD : 0);
-        for (int d = lane; d < W; d += 32) {
-            float s = 0.0f;
-            for (unsigned long long mm = vm; mm; mm &= mm - 1) {
-                const size_t r = scene_row0 + (__ffsll((long long)mm) - 1);
-                s += (d < D) ? obs[r * D + d] : act[r * AD + (d - D)];
+        // lanes own columns (lane, lane + 32, ...: up to 8 per lane, W <= 256); the neighbours are walked once, in slot
+        // order - the mask is the same on every lane, so the walk is uniform - and every lane adds its columns of the
+        // neighbour's row (coalesced 128-byte reads)
+        float acc[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc[u] = 0.0f;
+        uint32_t lo = (uint32_t)vm, hi = (uint32_t)(vm >> 32);
+        int base = 0;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            uint32_t w = half ? hi : lo;
+            while (w) {
+                const int j = base + __ffs((int)w) - 1;
+                w &= w - 1u;
+                const float* orow = obs + (scene_row0 + j) * D;
+                const float* arow = act ? act + (scene_row0 + j) * AD : nullptr;       // only read when counterfactual
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int d = lane + 32 * u;
+                    if (d < W) acc[u] += (d < D) ? orow[d] : arow[d - D];
+                }
             }
-            out[D + d] = s * inv;
+            base = 32;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int d = lane + 32 * u;
+            if (d < W) out[D + d] = acc[u] * inv;
         }
     } else {
         const int W = D + (counterfactual ? AD : 0);
@@ -249,6 +270,8 @@ int b2c_cc_obs_fuse(const float* obs, const float* actions, const uint8_t* flags
     if (cobs_dim != want) return b2c_set_error(B2C_ERR_ARG, "b2c_cc_obs_fuse: cobs_dim %d, expected %d (algo_ccppo.py:55-71)", cobs_dim, want);
     if ((mode == 1 && !mf_mask) || (mode == 2 && !nei_list) || (mode && counterfactual && !actions))
         return b2c_set_error(B2C_ERR_ARG, "b2c_cc_obs_fuse: missing neighbour columns");
+    if (mode == 1 && obs_dim + (counterfactual ? act_dim : 0) > 256)
+        return b2c_set_error(B2C_ERR_ARG, "b2c_cc_obs_fuse: mean-field rows of more than 256 columns are not supported");
     size_t blocks = (rows + 7) / 8;
     cc_obs_fuse_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(obs, actions, flags, (const unsigned long long*)mf_mask,
                                                                           nei_list, cobs, rows, slots, obs_dim, act_dim,

@@ -554,16 +554,23 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_constan
 }
 
 // dW[n][k] += sum_c partial[c][n][k]  (k < K), fixed summation order; with db: column K of the partials (the ones column
-// of x, split_rows_kernel) is the bias gradient: db[n] += sum_c partial[c][n][K]
+// of x, split_rows_kernel) is the bias gradient: db[n] += sum_c partial[c][n][K].  Four lanes share one output element
+// (partials c = q, q + 4, ...; then q0 + q1 + q2 + q3 by two shuffles): 4x the loads in flight of one thread walking all
+// the partials, same result on every run.
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dW, float* __restrict__ db,
                                     int parts, int kp, int K) {
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 2, q = threadIdx.x & 3;
     const int W = db ? K + 1 : K;
-    if (idx >= 256 * W) return;
-    int n = idx / W, k = idx - n * W;
+    const bool live = idx < 256 * W;
+    const int n = live ? idx / W : 0, k = live ? idx - n * W : 0;
     float s = 0.0f;
-    for (int c = 0; c < parts; ++c) s += partial[((size_t)c * 256 + n) * kp + k];
-    if (k < K) dW[n * K + k] += s; else db[n] += s;
+    if (live)
+        for (int c = q; c < parts; c += 4) s += partial[((size_t)c * 256 + n) * kp + k];
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    if (live && q == 0) {
+        if (k < K) dW[n * K + k] += s; else db[n] += s;
+    }
 }
 
 }  // namespace tc
@@ -741,7 +748,7 @@ int b2c_tc_wgrad_bias(const uint16_t* dz_split, const uint16_t* x_split, float* 
     cudaStream_t s = (cudaStream_t)stream;
     tc_wgrad_kernel<<<num_sms, NUM_THREADS, WG_SMEM_BYTES, s>>>(map_dz, map_x, a);
     B2C_CUDA(cudaGetLastError());
-    wgrad_reduce_kernel<<<(256 * (K + 1) + 255) / 256, 256, 0, s>>>(workspace, dW, db, num_sms, Kp, K);
+    wgrad_reduce_kernel<<<(256 * (K + 1) * 4 + 255) / 256, 256, 0, s>>>(workspace, dW, db, num_sms, Kp, K);
     B2C_CUDA(cudaGetLastError());
     return B2C_OK;
 }
