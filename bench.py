@@ -584,8 +584,11 @@ def time_training(args, dev, world, rank):
     env_name = {v: k for k, v in MAP_OF_ENV.items()}[c["map"]]
     scenes = args.train_scenes or min(c["scenes"], 1024)
     cls = T.CoPOTrainer if c["algo"] == "copo" else T.CCPPOTrainer
+    # weak scaling: the scenes AND the SGD minibatch per GPU are fixed (sgd_minibatch_size is the GLOBAL minibatch, so
+    # it grows with the world size: 65 536 rows per rank and gradient all-reduce)
+    mb = 65536 * world
     tr = cls(dict(env=env_name, num_scenes=scenes, rollout_fragment_length=args.train_fragment,
-                  sgd_minibatch_size=65536, num_sgd_iter=5, lcf_num_iters=5, env_config={"num_agents": c["slots"]},
+                  sgd_minibatch_size=mb, num_sgd_iter=5, lcf_num_iters=5, env_config={"num_agents": c["slots"]},
                   seed=args.seed), device=dev)
     tr.train()
     torch.cuda.synchronize()
@@ -601,7 +604,8 @@ def time_training(args, dev, world, rank):
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     out = {"agent_env_steps_per_s_per_gpu": steps / dt, "iterations": args.train_iters, "seconds": dt,
-           "scenes_per_gpu": scenes, "fragment": args.train_fragment, "sgd_minibatch_size": 65536,
+           "scenes_per_gpu": scenes, "fragment": args.train_fragment, "sgd_minibatch_size": mb,
+           "sgd_minibatch_rows_per_gpu": 65536,
            "num_sgd_iter": 5, "lcf_num_iters": 5, "sample_ms": sample_ms, "learn_ms": learn_ms,
            "allreduce_ms_per_iteration": ar_ms, "allreduces_per_iteration": tr._timers.get("allreduces"),
            "what": "full %s.training_step iterations, wall clock, this rank; allreduce_ms = CUDA-event time inside "

@@ -28,6 +28,7 @@
 namespace b2c {
 namespace tc {
 
+constexpr uint32_t IDESC_N128 = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((BLOCK_M >> 4) << 24);
 constexpr int F_EPI = 16;                                 // epilogue warps: 4 TMEM lane quarters x 4 column groups
 constexpr int F_GROUPS = F_EPI / 4;
 constexpr int F_THREADS = 128 + F_EPI * 32;
@@ -73,8 +74,9 @@ tc_mlp2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint64_t* full = reinterpret_cast<uint64_t*>(misc);          // [STAGES] TMA bytes landed
     uint64_t* empty = full + STAGES;                             // [STAGES] the stage's MMAs have retired
     uint64_t* hfull = empty + STAGES;                            // [STAGES] the hidden block is in the stage's A half
-    uint64_t* d1_full = hfull + STAGES;
-    uint64_t* d1_empty = d1_full + 1;
+    uint64_t* d1a_full = hfull + STAGES;                         // hidden columns 0..127 of layer 1 are in TMEM
+    uint64_t* d1b_full = d1a_full + 1;                           // ... and 128..255
+    uint64_t* d1_empty = d1b_full + 1;
     uint64_t* d2_full = d1_empty + 1;
     uint64_t* d2_empty = d2_full + 1;
     uint64_t* part_full = d2_empty + 1;                          // [2] the 16 epilogue warps posted their partial sums
@@ -98,7 +100,7 @@ tc_mlp2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&hfull[s], F_EPI); }
-        mbar_init(d1_full, 1); mbar_init(d1_empty, F_EPI);
+        mbar_init(d1a_full, 1); mbar_init(d1b_full, 1); mbar_init(d1_empty, F_EPI);
         mbar_init(d2_full, 1); mbar_init(d2_empty, F_EPI);
         for (int k = 0; k < 2; ++k) { mbar_init(&part_full[k], F_EPI); mbar_init(&part_empty[k], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -168,19 +170,57 @@ tc_mlp2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 }
                 umma_commit(&empty[s]);                          // frees the stage when these MMAs retire
             };
+            // one 128-column half of a first-layer block: N = 128 MMAs on rows 128 half .. of the W tile (16 KB further on)
+            auto issue_half = [&](uint32_t s, uint32_t tmem_d, uint32_t half, bool first_block) {
+                const uint32_t sa = smem_u32(ring + s * STAGE_BYTES);
+                const uint32_t sw = sa + 2 * A_STAGE_BYTES + half * (uint32_t)(128 * 128);
+                const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + A_STAGE_BYTES);
+                const uint64_t w_hi = make_desc(sw), w_lo = make_desc(sw + B_STAGE_BYTES);
+                const uint32_t td = tmem_d + half * 128u;
+#pragma unroll
+                for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                    const uint64_t o = (uint64_t)(k * 2);
+                    umma_bf16(td, a_hi + o, w_hi + o, IDESC_N128, (first_block && k == 0) ? 0u : 1u);
+                    umma_bf16(td, a_lo + o, w_hi + o, IDESC_N128, 1u);
+                    umma_bf16(td, a_hi + o, w_lo + o, IDESC_N128, 1u);
+                    if (args.products == 4) umma_bf16(td, a_lo + o, w_lo + o, IDESC_N128, 1u);
+                }
+            };
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t_local) {
                 // ---- layer 1 -> D1 (epilogue 1 is done with the previous tile's D1) ----
                 mbar_wait(d1_empty, (t_local & 1u) ^ 1u);
                 F_TRACE(13);
                 tc_fence_after();
-                for (int b = 0; b < nb1; ++b, ++g) {
-                    const int s = (int)(g & 1u);
-                    mbar_wait(&full[s], (g >> 1) & 1u);
-                    if (b < 2) F_TRACE(b);
-                    tc_fence_after();
-                    issue_block(s, tmem_d1, b == 0);
+                if (nb1 <= STAGES) {
+                    // every first-layer block is resident at once: hidden columns 0..127 first (over all blocks), then
+                    // 128..255 - epilogue 1 starts on reduction blocks 0 and 1 of layer 2 while the tensor core is still
+                    // on the second half, so layer 2 can follow layer 1 without a gap (profiles/r02_c_fused_trace.md)
+                    for (int b = 0; b < nb1; ++b) {
+                        const uint32_t gb = g + (uint32_t)b;
+                        mbar_wait(&full[gb & 1u], (gb >> 1) & 1u);
+                        if (b < 2) F_TRACE(b);
+                        tc_fence_after();
+                        issue_half(gb & 1u, tmem_d1, 0u, b == 0);
+                    }
+                    umma_commit(d1a_full);
+                    for (int b = 0; b < nb1; ++b) {
+                        const uint32_t gb = g + (uint32_t)b;
+                        issue_half(gb & 1u, tmem_d1, 1u, b == 0);
+                        umma_commit(&empty[gb & 1u]);            // frees the stage when both halves have read it
+                    }
+                    umma_commit(d1b_full);
+                    g += (uint32_t)nb1;
+                } else {
+                    for (int b = 0; b < nb1; ++b, ++g) {
+                        const int s = (int)(g & 1u);
+                        mbar_wait(&full[s], (g >> 1) & 1u);
+                        if (b < 2) F_TRACE(b);
+                        tc_fence_after();
+                        issue_block(s, tmem_d1, b == 0);
+                    }
+                    umma_commit(d1a_full);
+                    umma_commit(d1b_full);
                 }
-                umma_commit(d1_full);
                 // ---- layer 2 -> D2 (epilogue 2 is done with the previous tile's D2) ----
                 mbar_wait(d2_empty, (t_local & 1u) ^ 1u);
                 F_TRACE(2);
@@ -308,12 +348,17 @@ tc_mlp2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
             if (i < my_tiles) {
                 // ---- E1(i): 16 columns of every reduction block ----
-                mbar_wait_backoff(d1_full, t_local & 1u);
-                if (warp == 4 && lane == 0) F_TRACE(7);
-                tc_fence_after();
                 const uint32_t g_base = t_local * (uint32_t)nb + (uint32_t)nb1;
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c) {                    // reduction block of layer 2 = hidden columns 64 c ..
+                    if (c == 0) {
+                        mbar_wait_backoff(d1a_full, t_local & 1u);
+                        if (warp == 4 && lane == 0) F_TRACE(7);
+                        tc_fence_after();
+                    } else if (c == 2) {
+                        mbar_wait_backoff(d1b_full, t_local & 1u);
+                        tc_fence_after();
+                    }
                     const uint32_t g = g_base + (uint32_t)c;
                     const int s = (int)(g & 1u);
                     uint8_t* a_hi = ring + s * STAGE_BYTES + row_off;
