@@ -590,7 +590,8 @@ def time_training(args, dev, world, rank):
     tr = cls(dict(env=env_name, num_scenes=scenes, rollout_fragment_length=args.train_fragment,
                   sgd_minibatch_size=mb, num_sgd_iter=5, lcf_num_iters=5, env_config={"num_agents": c["slots"]},
                   seed=args.seed), device=dev)
-    tr.train()
+    for _ in range(2):        # warm-up: the first iteration captures the minibatch graph, the second is the first with a
+        tr.train()            # ragged last minibatch (eager path: its buffers come from the caching allocator once)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     steps = 0
