@@ -43,8 +43,6 @@ def load():
                            "(there is no CPU fallback for the hot path)")
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.b2c_last_error.restype = ctypes.c_char_p
-        for name in dir(_lib):
-            pass
     return _lib
 
 

@@ -612,7 +612,28 @@ env_lidar_kernel(const __grid_constant__ LidarIO io) {
             // whole rows as the policy's [hi | lo] bf16 operand
             const int half = io.kp >> 1;                          // 32-bit words per half row (2 columns each)
             uint32_t* g_sp = io.obs_split + (size_t)scene0 * A * io.kp;
-            if ((D & 3) == 0 && (half & 1) == 0) {
+            if ((D & 3) == 0 && (half & 3) == 0 && half <= 64) {
+                // eight columns per lane (two 16-byte shared loads, one 16-byte store into each half), two rows per warp
+                // pass: lanes 0-15 take the even row, lanes 16-31 the odd one (kp <= 128: one pass covers a row)
+                const int sub = lane & 15, rsel = lane >> 4;
+                const int n_oct = half >> 2;                      // 16-byte cells per half row
+                for (int row = 2 * warp + rsel; row < n_rows; row += 2 * n_warps) {
+                    if (sub < n_oct) {
+                        const float4* trow = reinterpret_cast<const float4*>(s_tile + (size_t)row * D);
+                        uint4* srow = reinterpret_cast<uint4*>(g_sp + (size_t)row * io.kp);
+                        const float4 z = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                        const float4 x0 = (8 * sub < D) ? trow[2 * sub] : z;
+                        const float4 x1 = (8 * sub + 4 < D) ? trow[2 * sub + 1] : z;
+                        uint4 hi, lo;
+                        split_pair(x0.x, x0.y, hi.x, lo.x);
+                        split_pair(x0.z, x0.w, hi.y, lo.y);
+                        split_pair(x1.x, x1.y, hi.z, lo.z);
+                        split_pair(x1.z, x1.w, hi.w, lo.w);
+                        srow[sub] = hi;
+                        srow[n_oct + sub] = lo;
+                    }
+                }
+            } else if ((D & 3) == 0 && (half & 1) == 0) {
                 // four columns per lane: one 16-byte shared load, one 8-byte store into each half
                 for (int row = warp; row < n_rows; row += n_warps) {
                     const float4* trow = reinterpret_cast<const float4*>(s_tile + (size_t)row * D);

@@ -242,3 +242,32 @@ def test_step_host_matches_device_step(S, chunks):
     assert e_host.last_d2h_bytes == sum(want[k].numel() * want[k].element_size() for k in ("obs", "reward", "flags"))
     e_dev.close()
     e_host.close()
+
+
+@pytest.mark.parametrize("name,S,A", [("intersection", 64, 40), ("tollgate", 20, 40), ("parking_lot", 50, 10),
+                                      ("intersection", 9, 64)])
+def test_optional_outputs_left_out_do_not_change_the_others(name, S, A):
+    """The scene step computes the mean-field mask and the nearest-neighbour list only on request (CoPO without a fused
+    critic input asks for neither; the kernel then takes the reward sum in a uniform loop instead of the mask walk):
+    every other output and the simulator state stay bit-identical."""
+    from copo_b200.batched_env import BatchedDrivingEnv
+    full = BatchedDrivingEnv(name, num_scenes=S, num_slots=A, num_agents=A, seed=9)
+    lean = BatchedDrivingEnv(name, num_scenes=S, num_slots=A, num_agents=A, seed=9)
+    out_lean = dict(lean.out)
+    out_lean["mf_mask"] = None
+    out_lean["nei_list"] = None
+    a, b = full.reset(), lean.reset(out=out_lean)
+    rng = np.random.default_rng(3)
+    for t in range(80):
+        act = rng.uniform(-1, 1, (S, A, 2)).astype(np.float32)
+        act[..., 0] *= 0.3
+        a = full.step(torch.from_numpy(act).cuda())
+        b = lean.step(torch.from_numpy(act).cuda(), out=out_lean)
+        for k, v in a.items():
+            if k in ("mf_mask", "nei_list") or v is None:
+                continue
+            assert torch.equal(v.view(torch.uint8) if v.dtype.is_floating_point else v,
+                               b[k].view(torch.uint8) if b[k].dtype.is_floating_point else b[k]), (t, k)
+    assert np.array_equal(full.get_state(), lean.get_state())
+    full.close()
+    lean.close()
