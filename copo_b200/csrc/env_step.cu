@@ -269,29 +269,36 @@ env_step_kernel(const __grid_constant__ EnvConfig cfg, const __grid_constant__ E
         if (has_agent && !cfg.do_reset) phase_crash_slot(v, ia);
         __syncthreads();
         // ---- P3: reward / termination (thread = slot) ----------------------------------------------------
+        int my_need = 0;
         if (has_agent) {
             phase_outcome(v, cfg, ia);
             if (ia == 0) { v.masks[2] = 0ull; v.masks[3] = 0ull; }      // the overlap phase is done with them
-            if (v.status(ia) == ST_EMPTY || v.hdr(H_EP_STEP) >= cfg.horizon) s_need[sl_a] = 1;
+            if (cfg.do_reset || v.status(ia) == ST_EMPTY || v.hdr(H_EP_STEP) >= cfg.horizon) { s_need[sl_a] = 1; my_need = 1; }
         }
-        __syncthreads();
-        // ---- P4: spawn-place occupancy, only for scenes that have something to spawn ----------------------
-        const int n_sp = (int)s_map[M_NSPAWN];
-        for (int idx = tid; idx < ng * n_sp; idx += NT) {
-            int sl = idx / n_sp, p = idx - sl * n_sp;
-            if (s_need[sl]) phase_place_free(view(sl), cfg, p);
-        }
-        __syncthreads();
-        // ---- P5: respawn, sequential per scene; scenes are spread over distinct warps ---------------------
-        {
-            int w = tid >> 5, lane = tid & 31;
-            int sl = lane * n_warps + w;
-            if (sl < ng) {
-                int need = s_need[sl];
-                s_done[sl] = need ? phase_respawn(view(sl), cfg, scene0 + sl) : 0;
+        // the barrier doubles as a vote: most steps no scene of the group has anything to spawn or restart, and the two
+        // spawn phases with their barriers are skipped
+        const int any_need = __syncthreads_or(my_need);
+        if (any_need) {
+            // ---- P4: spawn-place occupancy, only for scenes that have something to spawn ------------------
+            const int n_sp = (int)s_map[M_NSPAWN];
+            for (int idx = tid; idx < ng * n_sp; idx += NT) {
+                int sl = idx / n_sp, p = idx - sl * n_sp;
+                if (s_need[sl]) phase_place_free(view(sl), cfg, p);
             }
+            __syncthreads();
+            // ---- P5: respawn, sequential per scene; scenes are spread over distinct warps -----------------
+            {
+                int w = tid >> 5, lane = tid & 31;
+                int sl = lane * n_warps + w;
+                if (sl < ng) {
+                    int need = s_need[sl];
+                    s_done[sl] = need ? phase_respawn(view(sl), cfg, scene0 + sl) : 0;
+                }
+            }
+            __syncthreads();
+        } else if (tid < ng) {
+            s_done[tid] = 0;                                 // read after the barrier below
         }
-        __syncthreads();
         // ---- P6a: slot masks (participants / present vehicles) ---------------------------------------------
         if (has_agent) {
             phase_pose_refresh(v, ia);
