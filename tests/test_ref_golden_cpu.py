@@ -1,0 +1,114 @@
+"""Pins the oracle - and the product's host-side logic - against tests/golden/ref_golden.npz: outputs of the REFERENCE's
+own functions executed in the build container (tests/golden/make_ref_golden.py extracts them from /root/reference with
+`ast` and runs them on stand-ins for the RLlib names).  Covered: CCEnv distance map / neighbour lists, neighbourhood and
+global advantages, both centralized-critic fusions, the IPPO / CCPPO / CoPO losses with their gradients, the CoPO meta
+update.  The GPU twin (tests/test_ref_golden_gpu.py) holds the CUDA kernels to the same numbers."""
+import json
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import gae as og
+from oracle import models as om
+from oracle import wrappers as ow
+
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_golden.npz"))
+META = json.loads(bytes(G["meta_json"]).decode())
+
+
+def _model(key, algo, prefix="w"):
+    m = META[key]
+    cls = om.CoPOModel if algo == "copo" else om.CCModel
+    net = cls(m["odim"], hiddens=tuple(m["hiddens"]), cdim=m.get("cdim", m["odim"]))
+    sd = {k[len(key) + len(prefix) + 2:]: torch.from_numpy(G[k]) for k in G.files if k.startswith("%s/%s/" % (key, prefix))}
+    net.load_state_dict(sd)
+    return net
+
+
+def _batch(key):
+    return {k[len(key) + 7:]: torch.from_numpy(G[k]) for k in G.files if k.startswith(key + "/batch/")}
+
+
+def test_distance_map_and_neighbour_lists():
+    w = META["wrappers"]
+    pos = G["wrappers/pos"]
+    veh = {n: (None if n in w["none"] else pos[i]) for i, n in enumerate(w["names"])}
+    dm = ow.update_distance_map(veh)
+    for key, (ids, ds) in w["neighbours"].items():
+        name, dist = key.split("@")
+        got_ids, got_ds = ow.find_in_range(dm, name, int(dist))
+        assert got_ids == ids and got_ds == ds, key             # same order (stable on ties), same float64 distances
+
+
+def test_neighbourhood_and_global_advantages():
+    nv, nr = G["adv/nei_values"], G["adv/nei_rewards"]
+    gv, gr = G["adv/global_values"], G["adv/global_rewards"]
+    for tag in ("cut", "done"):
+        adv, tgt = og.compute_nei_advantage(nr, nv, float(nv[-1]) if tag == "cut" else 0.0, 0.99, 0.95)
+        assert np.array_equal(adv, G["adv/%s/nei_advantage" % tag]) and np.array_equal(tgt, G["adv/%s/nei_target" % tag])
+        adv, tgt = og.compute_global_advantage(gr, gv, float(gv[-1]) if tag == "cut" else 0.0, 1.0, 0.95)
+        assert np.array_equal(adv, G["adv/%s/global_advantages" % tag])
+        assert np.array_equal(tgt, G["adv/%s/global_target" % tag])
+
+
+@pytest.mark.parametrize("mode", ["concat", "mf"])
+@pytest.mark.parametrize("cf", [True, False])
+def test_critic_obs_fusion_of_one_trajectory(mode, cf):
+    """The product's per-trajectory hook (host logic of CCPPOPolicy.postprocess_trajectory) against the reference's
+    concat_ccppo_process / mean_field_ccppo_process."""
+    from copo_b200 import policy as P
+    f = META["fuse"]
+    names = sorted(f["infos"])
+    batches = {n: {"t": G["fuse/in/%s/t" % n], "obs": G["fuse/in/%s/obs" % n], "actions": G["fuse/in/%s/actions" % n],
+                   "infos": f["infos"][n]} for n in names}
+    odim, adim = f["odim"], f["adim"]
+    cdim = odim + (f["num_neighbours"] if mode == "concat" else 1) * (odim + (adim if cf else 0))
+    fake = types.SimpleNamespace(config=dict(fuse_mode=mode, counterfactual=cf, num_neighbours=f["num_neighbours"],
+                                             mf_nei_distance=f["mf_nei_distance"]),
+                                 model=types.SimpleNamespace(cobs_dim=cdim))
+    for n in names:
+        others = {m: (None, batches[m]) for m in names if m != n}
+        got = P.CCPPOPolicy._trajectory_critic_obs(fake, dict(batches[n]), batches[n]["obs"], others, episode=object())
+        want = G["fuse/%s/cf%d/%s" % (mode, int(cf), n)]
+        assert got.shape == want.shape and np.array_equal(got, want), (mode, cf, n)
+
+
+@pytest.mark.parametrize("algo", ["copo", "ccppo", "ippo"])
+@pytest.mark.parametrize("cname", ["default", "plain_vf"])
+def test_losses_and_gradients(algo, cname):
+    key = "loss/%s/%s" % (algo, cname)
+    net, batch, m = _model(key, algo), _batch(key), META[key]
+    total, st = om.ppo_loss(net, batch, dict(om.DEFAULT_CFG, **m["cfg"]), algo)
+    net.zero_grad()
+    total.backward()
+    g = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in net.parameters()])
+    want = torch.from_numpy(G[key + "/grad"])
+    assert float((g - want).abs().max()) <= 1e-6 * max(1.0, float(want.abs().max()))
+    for k, v in m["stats"].items():
+        if k in st:
+            assert abs(float(st[k]) - v) <= 1e-6 * max(1.0, abs(v)), (k, float(st[k]), v)
+    assert {"total_loss", "mean_policy_loss", "mean_vf_loss", "mean_entropy", "mean_kl_loss"} <= set(m["stats"])
+
+
+def test_meta_update():
+    m = META["meta"]
+    net = om.CoPOModel(m["odim"], hiddens=tuple(m["hiddens"]))
+    old = om.CoPOModel(m["odim"], hiddens=tuple(m["hiddens"]))
+    net.load_state_dict({k[len("meta/w/"):]: torch.from_numpy(G[k]) for k in G.files if k.startswith("meta/w/")})
+    old.load_state_dict({k[len("meta/w_old/"):]: torch.from_numpy(G[k]) for k in G.files if k.startswith("meta/w_old/")})
+    batch = {k[len("meta/batch/"):]: torch.from_numpy(G[k]) for k in G.files if k.startswith("meta/batch/")}
+    final, g_lcf, st, _ = om.meta_gradient(net, old, batch, dict(clip_param=m["clip_param"]), m["raw_mean"], m["raw_std"],
+                                           torch.from_numpy(G["meta/eps"]))
+    for k in ("new_policy_ego_loss", "old_policy_logp_loss", "lcf_lcf_adv_loss", "lcf_final_loss", "grad_value",
+              "coordinated_adv", "global_adv"):
+        assert abs(st[k] - m["stats"][k]) <= 2e-6 * max(1.0, abs(m["stats"][k])), (k, st[k], m["stats"][k])
+    # one Adam step on the LCF parameters (torch.optim.Adam, lr = lcf_lr) lands where the reference's optimizer did
+    p = net.lcf_parameters.detach().double()
+    p2, _, _ = om.adam_step(p, g_lcf.double(), torch.zeros(2, dtype=torch.float64), torch.zeros(2, dtype=torch.float64), 1,
+                            m["lcf_lr"])
+    p2 = np.asarray(p2)
+    assert np.allclose(p2, G["meta/lcf_parameters_after"], rtol=0, atol=1e-6)
+    assert abs(float(np.tanh(p2[0])) - m["stats"]["lcf"]) < 1e-6 and abs(float(np.exp(p2[1])) - m["stats"]["lcf_std"]) < 1e-6
