@@ -8,6 +8,7 @@ The reference imports ray / rllib / metadrive at module level, which are not ins
 imported; but the bodies this path depends on are plain numpy / torch code:
 
   torch_copo/utils/env_wrappers.py   CCEnv._update_distance_map, CCEnv._find_in_range            (:125-158)
+                                     CCEnv.step, LCFEnv.step, LCFEnv._add_lcf over a scripted base env (:89-123, 307-418)
   torch_copo/algo_copo.py            compute_nei_advantage, compute_global_advantage             (:189-204)
                                      CoPOModel.compute_coordinated / lcf_dist / lcf_mean / lcf_std (:155-177)
                                      CoPOPolicy.loss, CoPOPolicy.meta_update                     (:228-424)
@@ -208,6 +209,63 @@ def main():
             nb["%s@%d" % (n, dist)] = [list(ids), [float(x) for x in ds]]
     out["wrappers/pos"] = pos
     meta["wrappers"] = dict(names=names, none=["agent9"], neighbours=nb)
+
+    # ---- A2. CCEnv.step + LCFEnv.step + _add_lcf over a stand-in base env ------------------------------------------
+    # (the reference's methods with their own super() chain: TMP(LCFEnv, Base) as get_lcf_env builds it, :463-471)
+    from math import cos, sin
+    ns = namespace(WRAP)
+    draws = np.random.RandomState(123)
+    ns.update(cos=cos, sin=sin, clip=lambda a, lo, hi: min(max(a, lo), hi), get_np_random=lambda *a, **k: draws)
+
+    class Base:
+        def step(self, actions):
+            o, r, d, i, pos = self._script.pop(0)
+            self.vehicles_including_just_terminated = {k: type("V", (), {"position": np.asarray(p, np.float64)})()
+                                                       for k, p in pos.items()}
+            return o, r, d, i
+
+    cc = type("CCEnv", (), {k: load(ns, WRAP, "CCEnv." + k) for k in ("step", "_find_in_range", "_update_distance_map")})
+    lcf_cls = type("LCFEnv", (cc,), {k: load(ns, WRAP, "LCFEnv." + k) for k in ("step", "_add_lcf", "enable_copo")})
+    ns["CCEnv"], ns["LCFEnv"] = cc, lcf_cls
+    tmp = type("TMP", (lcf_cls, Base), {})
+    steps_meta = []
+    for scen, over in (("angle_native", {}), ("linear_coord", dict(lcf_mode="linear", return_native_reward=False)),
+                       ("forced_normal", dict(force_lcf=0.4, return_native_reward=False)),
+                       ("uniform", dict(lcf_dist="uniform"))):
+        env = tmp()
+        env.config = dict(neighbours_distance=40, lcf_mode="angle", lcf_dist="normal", lcf_normal_std=0.1,
+                          return_native_reward=True, force_lcf=-100, enable_copo=True, add_traffic_light=False,
+                          communication={ns["COMM_METHOD"]: "none"})
+        env.config.update(over)
+        env.distance_map = defaultdict(lambda: defaultdict(lambda: float("inf")))
+        env.lcf_map, env.force_lcf = {}, env.config["force_lcf"]
+        lcf_mean = 0.5 if env.config["lcf_mode"] == "linear" else 0.2        # linear mode asserts 0 <= lcf <= 1 (:347)
+        env.current_lcf_mean, env.current_lcf_std = lcf_mean, 0.1
+        env._last_obs, env._traffic_light_counter = None, 0
+        alive = ["agent%d" % k for k in range(6)]
+        script, rec = [], []
+        for t in range(7):
+            if t == 3:
+                alive = [a for a in alive if a != "agent2"] + ["agent6"]        # one leaves, a fresh one joins
+            pos = {a: rng.uniform(-30, 30, 2) for a in alive}
+            o = {a: rng.uniform(0, 1, 5).astype(np.float32) for a in alive}
+            r = {a: float(rng.normal()) for a in alive}
+            d = {a: False for a in alive}
+            script.append((o, dict(r), d, {a: {} for a in alive}, pos))
+            rec.append(dict(pos={a: [float(x) for x in pos[a]] for a in alive}, reward=r,
+                            obs={a: [float(x) for x in o[a]] for a in alive}))
+        env._script = script
+        draws.seed(123)
+        for t in range(7):
+            no, nr, nd, ni = env.step({})
+            rec[t]["out_reward"] = {k: float(v) for k, v in nr.items()}
+            rec[t]["out_obs_last"] = {k: float(v[-1]) for k, v in no.items()}
+            rec[t]["info"] = {k: {q: (list(v[q]) if isinstance(v[q], list) else float(v[q]))
+                                   for q in ("neighbours", "neighbours_distance", "nei_rewards", "global_rewards", "lcf",
+                                             "coordinated_rewards", "native_rewards")} for k, v in ni.items()}
+        steps_meta.append(dict(name=scen, config={k: v for k, v in env.config.items() if k != "communication"},
+                               lcf_mean=lcf_mean, lcf_std=0.1, rng_seed=123, steps=rec))
+    meta["lcf_env"] = steps_meta
 
     # ---- B. neighbourhood / global advantages ----------------------------------------------------------------
     ns = namespace(A_COPO)

@@ -112,3 +112,36 @@ def test_meta_update():
     p2 = np.asarray(p2)
     assert np.allclose(p2, G["meta/lcf_parameters_after"], rtol=0, atol=1e-6)
     assert abs(float(np.tanh(p2[0])) - m["stats"]["lcf"]) < 1e-6 and abs(float(np.exp(p2[1])) - m["stats"]["lcf_std"]) < 1e-6
+
+
+@pytest.mark.parametrize("scenario", range(4))
+def test_wrapper_steps_against_the_reference_methods(scenario):
+    """CCEnv.step + LCFEnv.step + _add_lcf of the reference, executed over a scripted base env (agents leaving and
+    joining; angle / linear mixing, native / coordinated return, forced + normal redraw every step, uniform draws),
+    against the oracle's restatement fed with the same random stream."""
+    sc = META["lcf_env"][scenario]
+    cfg = sc["config"]
+    rng = np.random.RandomState(sc["rng_seed"])
+    lcf_map = {}
+    for step in sc["steps"]:
+        names = list(step["reward"].keys())
+        pos = {k: np.asarray(step["pos"][k], np.float64) for k in names}
+        infos = ow.cc_step(pos, step["reward"], cfg["neighbours_distance"])
+        now = {}
+        for k in names:                                          # the reference draws inside its per-agent loop, in order
+            lcf, obs = ow.add_lcf(np.asarray(step["obs"][k], np.float32), lcf_map.get(k), rng, True, cfg["force_lcf"],
+                                  cfg["lcf_dist"], sc["lcf_mean"], sc["lcf_std"])
+            lcf_map.setdefault(k, lcf)                           # the episode value is set once (:341-342)
+            now[k] = lcf
+            assert abs(float(obs[-1]) - step["out_obs_last"][k]) < 1e-7
+        got_r = ow.lcf_step(dict(step["reward"]), infos, now, cfg["lcf_mode"], cfg["return_native_reward"])
+        for k in names:
+            want = step["info"][k]
+            assert infos[k]["neighbours"] == want["neighbours"]
+            assert infos[k]["neighbours_distance"] == want["neighbours_distance"]
+            for q in ("nei_rewards", "global_rewards", "lcf", "coordinated_rewards", "native_rewards"):
+                assert abs(infos[k][q] - want[q]) <= 1e-12 * max(1.0, abs(want[q])), (k, q)
+            assert abs(got_r[k] - step["out_reward"][k]) <= 1e-12 * max(1.0, abs(step["out_reward"][k]))
+    if cfg["force_lcf"] != -100:                                 # forced + normal: a fresh value every step
+        a = [s["info"]["agent0"]["lcf"] for s in sc["steps"]]
+        assert len(set(a)) == len(a)
