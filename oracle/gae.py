@@ -10,8 +10,9 @@
   lcf_mix_standardize                    torch_copo/algo_copo.py:539-551 (+ rllib.utils.sgd.standardized:
                                          (x - mean) / max(1e-4, std), population std)
 
-PINNING: the reference ships no tests; `discount_cumsum` is pinned here by scipy.signal.lfilter itself (the very
-call rllib makes) and by the closed form checked in tests/test_bookkeeping_cpu.py.
+PINNING: `discount_cumsum` is pinned by scipy.signal.lfilter itself (the very call rllib makes) and by the closed form
+checked in tests/test_bookkeeping_cpu.py; compute_nei_advantage / compute_global_advantage by the reference's own
+functions executed in the build container (tests/golden/ref_golden.npz, bit-equal in tests/test_ref_golden_cpu.py).
 
 `rollout_gae3` is the driver that cuts the batched [T, N] rollout columns (N = scenes x slots) into the
 per-agent trajectories RLlib would hand to postprocess_trajectory and applies the functions above to each.

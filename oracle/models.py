@@ -17,7 +17,11 @@ and, from ray 2.2.0 (not vendored; restated from the published implementation):
 
 PINNING: the policy forward is pinned against the reference's own numpy forward on the shipped weights
 (tests/golden/mlp_golden.npz, made by tests/golden/make_mlp_golden.py from copo/eval/get_policy_function.py:54-98).
-The losses have no reference vectors (the reference has no tests): parity of the losses is "oracle = restatement".
+The losses and the meta update are pinned against the reference's OWN code executed in the build container: the bodies of
+IPPOPolicy.loss / CCPPOPolicy.loss / CoPOPolicy.loss / CoPOPolicy.meta_update (and CoPOModel.compute_coordinated /
+lcf_mean / lcf_std) are extracted from /root/reference with `ast` and run on seeded batches; total loss, statistics,
+full gradient and the LCF parameters after the Adam step are stored in tests/golden/ref_golden.npz
+(tests/golden/make_ref_golden.py; checked in tests/test_ref_golden_cpu.py to 1e-6).
 Parameter names equal RLlib's state_dict names so the shipped ccppo_*.npz load directly.
 Only tests/, __graft_entry__.smoke() and bench.py may import this.
 """

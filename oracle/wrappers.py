@@ -12,7 +12,12 @@ reference itself owns (everything below MetaDrive's `super().step`):
 
 It works on the per-scene python dicts the reference works on, so tests can feed it the positions and
 native rewards of one scene of oracle/sim.py (or of the CUDA kernel) and compare neighbour lists, masks,
-nei/global rewards.  Only tests/, __graft_entry__.smoke() and bench.py may import this.
+nei/global rewards.
+
+PINNING: the reference's own CCEnv.step / _update_distance_map / _find_in_range / LCFEnv.step / _add_lcf, extracted from
+/root/reference and executed over a scripted base env (tests/golden/make_ref_golden.py -> tests/golden/ref_golden.npz),
+give the neighbour lists, distances, rewards and LCF values tests/test_ref_golden_cpu.py holds this file to.
+Only tests/, __graft_entry__.smoke() and bench.py may import this.
 """
 from collections import defaultdict
 from math import cos, sin
