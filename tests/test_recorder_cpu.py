@@ -58,3 +58,53 @@ def test_episode_report_matches_the_reference_recorder(cls, agents, seed):
         assert got["num_agents_total"] > agents / 2 and 0 < got["velocity_step_mean_episode_mean"] < 80
         assert got["success_rate"] + got["crash_rate"] + got["out_rate"] <= 1 + 1e-9          # the rest: max_step
         assert got["num_agents_success"] > 0 and got["num_agents_crash"] + got["num_agents_out"] > 0
+
+
+class _Replay:
+    """Feeds a recorded step stream (tests/golden/recorder_golden.json.gz) to a recorder wrapper."""
+
+    def __init__(self, episode):
+        self.episode, self.t, self.vehicles = episode, 0, {}
+
+    def reset(self):
+        self.t = 0
+        return {}
+
+    def step(self, actions=None):
+        import types
+        s = self.episode["steps"][self.t]
+        self.t += 1
+        self.vehicles = {k: types.SimpleNamespace(position=np.asarray(p, np.float64)) for k, p in s["vehicles"].items()}
+        return {}, dict(s["reward"]), dict(s["done"]), {k: dict(v) for k, v in s["info"].items()}
+
+
+@pytest.mark.parametrize("index", [0, 1])
+def test_episode_report_equals_what_the_reference_class_returned(index):
+    """The reference's own `RecorderEnv` (copo/eval/recoder.py, executed in the build container by
+    tests/golden/make_recorder_golden.py over recorded episodes of the dict-API env) against this repo's wrapper and the
+    oracle restatement, replaying the same stream: step reports every 25 steps and the 31-column episode report."""
+    import gzip
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "recorder_golden.json.gz")
+    ep = json.load(gzip.open(path, "rt"))[index]
+    env = RecorderEnv(_Replay(ep))
+    ref = orec.Recorder(20)
+    env.reset()
+    ref.episode_step = 0
+    for t in range(len(ep["steps"])):
+        _, r, d, i = env.step({})
+        ref.step({k: v.position for k, v in env.vehicles.items()}, r, d, i)
+        want = ep["step_results"].get(str(t))
+        if want is not None:
+            for got in (env.get_step_result(), ref.step_result()):
+                assert set(got) == set(want), set(got) ^ set(want)
+                for k, v in want.items():
+                    assert np.isclose(got[k], v, rtol=1e-9, atol=1e-12), (t, k, got[k], v)
+    want = ep["episode_result"]
+    for got in (env.get_episode_result(), ref.episode_result()):
+        assert [k for k in ep["episode_result_keys"] if k in got] == list(got.keys())
+        assert set(REFERENCE_COLUMNS) <= set(want)
+        for k in got:
+            assert np.isclose(got[k], want[k], rtol=1e-9, atol=1e-12), (k, got[k], want[k])
+    assert want["num_agents_total"] >= 3 and len(ep["step_results"]) >= 4
