@@ -22,6 +22,14 @@
 
 namespace b2c {
 
+#ifndef B2C_LIDAR_OWN
+#define B2C_LIDAR_OWN 1
+#endif
+static constexpr int LIDAR_OWN = B2C_LIDAR_OWN;
+static constexpr int SPREAD_TAB_WORDS = 160;       // per warp: float4[32] {ox, oy, cc, ss} + int[32] {(k - excl + 4096) << 8 | row}
+static constexpr int SPREAD_BITS_WORDS = 72;       // per warp: 32 pairs x up to 72 lasers = 2304 start bits
+static constexpr int SPREAD_MAX_RAYS = 72;         // more lasers than this per observer: everything goes through the own-lane loop
+
 // Shared-memory plan of one CTA working on `G` scenes at a time (offsets in bytes, every region 16-byte aligned).
 struct SmemPlan {
     int map, st, obs, f, i, need, masks, queue, geom, total;
@@ -38,7 +46,7 @@ __host__ __device__ inline SmemPlan smem_plan(int G, int A, int D, int map_words
     p.need = o;  o += ((3 * G + 4 + 3) & ~3) * 4;        // need[G], scene_done[G], queue fill (1 or per scene)
     p.masks = o; o += G * 4 * 8;                         // per scene: four slot masks (SceneView::masks)
     p.queue = o; o += split ? 0 : ((G * A * A + 7) & ~7) * 2;    // two-kernel mode: the lidar kernel builds the pair list
-    p.geom = o;  (void)n_warps;
+    p.geom = o;  o += split ? 0 : n_warps * (SPREAD_TAB_WORDS + SPREAD_BITS_WORDS) * 4;     // lidar_spread's per-warp scratch
     p.total = o;
     return p;
 }
@@ -70,6 +78,7 @@ struct EnvIO {
     int obs_bulk;   // 1 when the obs tiles can leave through a bulk store (16-byte aligned base)
     int group;      // scenes one CTA works on at a time
     int rec_stride; // two-kernel mode: words between two non-laser columns of the record (odd, >= A)
+    int* lidar_next; // two-kernel mode: the lidar kernel's scene-group counter, reset here for the launch that follows
     SmemPlan pl;    // shared-memory offsets, computed once on the host (read from the constant bank instead of being
                     // re-derived - the 48-register state kernel rematerialises them at every use)
 };
@@ -128,45 +137,76 @@ __device__ __forceinline__ void split_pair(float v0, float v1, uint32_t& hi, uin
     lo = *reinterpret_cast<uint32_t*>(&l2);
 }
 
-// One warp holds up to 32 (observer, box) pairs, set up one per lane (PairGeom + the observer's laser row offset).
-// Their lasers are spread evenly over the lanes: laser r of the warp (0 <= r < total) belongs to the pair whose
-// [excl, excl + cnt) holds r.  Every live pair gets cnt >= 1 (an extra laser outside the window is harmless: the
-// slab test is exact) and dead lanes only trail the live ones, so the owner changes exactly at the set bits of
-// `starts` - the pair starts inside the current batch of 32 lasers, OR-reduced over the warp (REDUX) - and
-// owner lane = (pairs started before the batch) + popc(starts up to my laser) - 1.  No search.
-__device__ __forceinline__ void lidar_spread(const PairGeom& g, int lid_off, bool live, int n_ray, const float2* ray,
-                                             float* lasers) {
+// One warp holds up to 32 (observer, box) pairs, set up one per lane (PairGeom + the observer's tile row).
+//   1. Every pair's own lane casts the pair's first LIDAR_OWN lasers: most pairs are far boxes with a window of one or
+//      two lasers (Intersection, 40 agents: 36 % one, 28 % two; 3.7 on average), so this needs no distribution at all.
+//   2. The remaining lasers (rest = cnt - LIDAR_OWN of the pairs that have more) are spread evenly over the lanes: laser
+//      r of the warp (0 <= r < total) belongs to the pair whose [excl, excl + rest) holds r.  The pairs with rest > 0
+//      are ranked (ballot); pair `rank` leaves {ox, oy, cc, ss} and {first laser - excl, tile row} in the warp's
+//      scratch table and sets bit `excl` of the warp's start bitmap.  excl is strictly increasing over the ranks, so
+//      the owner of laser r0 + lane is (start bits before the batch) + popc(start bits of the batch up to my lane) - 1:
+//      one broadcast load of a bitmap word and two 16 / 4-byte loads per batch of 32 lasers, no search, no shuffles.
+// A window that is empty still gets one laser (harmless: the slab test is exact).
+__device__ __forceinline__ int laser_wrap(int k, int n_ray) {     // 0 <= k < 2 * n_ray
+    const unsigned a = (unsigned)k, b = (unsigned)(k - n_ray);
+    return (int)(a < b ? a : b);
+}
+
+__device__ __forceinline__ void lidar_spread(const PairGeom& g, int row, bool live, int n_ray, int D, const float2* ray,
+                                             float* lasers, uint32_t* tab, uint32_t* bits) {
     const int lane = threadIdx.x & 31;
     const int cnt = live ? (g.cnt > 0 ? g.cnt : 1) : 0;
-    int incl = cnt;
+    const int own = (n_ray <= SPREAD_MAX_RAYS) ? LIDAR_OWN : n_ray;
+    {
+        float* dst = lasers + (size_t)row * D;
+        for (int q = 0; q < own; ++q) {
+            if (n_ray > SPREAD_MAX_RAYS && !__any_sync(0xffffffffu, q < cnt)) break;
+            if (q < cnt) {
+                const int k = laser_wrap(g.k0 + q, n_ray);
+                const float2 rd = ray[k];
+                lidar_ray(g.nx1, g.nx2, g.ny1, g.ny2, g.cc, g.ss, rd.x, rd.y, dst + k);
+            }
+        }
+    }
+    const int rest = cnt > own ? cnt - own : 0;
+    const unsigned has = __ballot_sync(0xffffffffu, rest > 0);
+    if (has == 0u) return;
+    int incl = rest;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         int nb = __shfl_up_sync(0xffffffffu, incl, d);
         if (lane >= d) incl += nb;
     }
     const int total = __shfl_sync(0xffffffffu, incl, 31);
-    const int excl = incl - cnt;
+    const int excl = incl - rest;
+    float4* tab4 = reinterpret_cast<float4*>(tab);
+    int* tabi = reinterpret_cast<int*>(tab + 128);
+    bits[lane] = 0u; bits[lane + 32] = 0u;
+    if (lane < SPREAD_BITS_WORDS - 64) bits[lane + 64] = 0u;
+    __syncwarp();
+    if (rest > 0) {
+        const int rank = __popc(has & ((1u << lane) - 1u));
+        tab4[rank] = make_float4(g.ox, g.oy, g.cc, g.ss);
+        tabi[rank] = ((g.k0 + own - excl + 4096) << 8) | row;
+        atomicOr(bits + (excl >> 5), 1u << (excl & 31));
+    }
+    __syncwarp();
     const unsigned upto = 0xffffffffu >> (31 - lane);
     int before = 0;
     for (int r0 = 0; r0 < total; r0 += 32) {
-        const int pos = excl - r0;
-        const unsigned starts = __reduce_or_sync(0xffffffffu, (cnt > 0 && pos >= 0 && pos < 32) ? (1u << pos) : 0u);
-        const int lo = before + __popc(starts & upto) - 1;
+        const unsigned starts = bits[r0 >> 5];
+        const int owner = before + __popc(starts & upto) - 1;
         before += __popc(starts);
-        const bool act = r0 + lane < total;
-        const int ex0 = __shfl_sync(0xffffffffu, excl, lo);
-        const int k0 = __shfl_sync(0xffffffffu, g.k0, lo);
-        const int off = __shfl_sync(0xffffffffu, lid_off, lo);
-        const float nx1 = __shfl_sync(0xffffffffu, g.nx1, lo), nx2 = __shfl_sync(0xffffffffu, g.nx2, lo);
-        const float ny1 = __shfl_sync(0xffffffffu, g.ny1, lo), ny2 = __shfl_sync(0xffffffffu, g.ny2, lo);
-        const float cc = __shfl_sync(0xffffffffu, g.cc, lo), ss = __shfl_sync(0xffffffffu, g.ss, lo);
-        if (act) {
-            int k = k0 + (r0 + lane - ex0);
-            k = (k >= n_ray) ? k - n_ray : k;
-            float2 rd = ray[k];
-            lidar_ray(nx1, nx2, ny1, ny2, cc, ss, rd.x, rd.y, lasers + off + k);
+        if (r0 + lane < total) {
+            const float4 t = tab4[owner];
+            const int code = tabi[owner];
+            const int k = laser_wrap((code >> 8) - 4096 + r0 + lane, n_ray);       // first laser of the rest + (r - excl)
+            const float2 rd = ray[k];
+            lidar_ray(-HALF_L - t.x, HALF_L - t.x, -HALF_W - t.y, HALF_W - t.y, t.z, t.w, rd.x, rd.y,
+                      lasers + (size_t)(code & 255) * D + k);
         }
     }
+    __syncwarp();                                        // the table and the bitmap are free for the warp's next 32 pairs
 }
 
 // SPLIT = false: the whole step in one kernel (observation tile in shared memory, lidar included).
@@ -242,7 +282,12 @@ env_step_kernel(const __grid_constant__ EnvConfig cfg, const __grid_constant__ E
         }
         // the map and the state tiles are already on their way; the actions (and every output buffer) belong to the
         // kernel before this one in the stream until pdl_wait() returns
-        if constexpr (SPLIT) { if (first) pdl_wait(); }
+        if constexpr (SPLIT) {
+            if (first) {
+                pdl_wait();
+                if (blockIdx.x == 0 && tid == 0 && io.lidar_next) *io.lidar_next = 0;     // nobody reads it before this grid is done
+            }
+        }
         float act0 = 0.0f, act1 = 0.0f;
         if (has_agent && !cfg.do_reset) {
             float2 a = reinterpret_cast<const float2*>(io.actions)[(size_t)scene0 * A + tid];
@@ -349,18 +394,20 @@ env_step_kernel(const __grid_constant__ EnvConfig cfg, const __grid_constant__ E
             const int lane = tid & 31, warp = tid >> 5;
             const int n_ray = (int)s_map[M_NRAY];
             const float2* ray2 = reinterpret_cast<const float2*>(s_map + s_map[M_OFF_RAY]);
+            uint32_t* s_spread = reinterpret_cast<uint32_t*>(smem_raw + pl.geom) + warp * (SPREAD_TAB_WORDS + SPREAD_BITS_WORDS);
             for (int base = warp * 32; base < nq; base += n_warps * 32) {
                 const int e = base + lane;
                 PairGeom g;
-                g.nx1 = g.nx2 = g.ny1 = g.ny2 = g.cc = g.ss = 0.0f; g.k0 = 0; g.cnt = 0;
-                int lid_off = 0;
+                g.nx1 = g.nx2 = g.ny1 = g.ny2 = g.cc = g.ss = g.ox = g.oy = 0.0f; g.k0 = 0; g.cnt = 0;
+                int row = 0;
                 if (e < nq) {
                     int code = s_queue[e];
                     int sl = code >> 12, oi = (code >> 6) & 63, oj = code & 63;
                     lidar_pair_setup(view(sl), oi, oj, g);
-                    lid_off = (sl * A + oi) * D + EGO_DIM + NAVI_DIM;
+                    row = sl * A + oi;                           // < 256: one CTA's slots
                 }
-                lidar_spread(g, lid_off, e < nq, n_ray, ray2, s_obs);
+                lidar_spread(g, row, e < nq, n_ray, D, ray2, s_obs + EGO_DIM + NAVI_DIM, s_spread,
+                             s_spread + SPREAD_TAB_WORDS);
             }
         }
         }
@@ -432,26 +479,38 @@ struct LidarIO {
     const float* pose;
     float* obs;
     uint32_t* obs_split;
+    int* next_group;      // groups handed out beyond the first one of every CTA (0 at launch), or null: static striding
     int pair_stride, rec_words, rec_stride, kp, group, S, A, D, n_ray, ray_off;
 };
 static constexpr int LIDAR_RAYS = 72;      // laser count of every shipped map (the specialised kernels assume it)
 
 struct LidarPlan {
-    int ray, rec, pairs, nq, excl, tile, total;
+    int ray, rec, pairs, nq, excl, tab, tile, total;
 };
-__host__ __device__ inline LidarPlan lidar_plan(int G, int A, int D, int n_ray, int rec_words, int pair_stride,
-                                                int n_warps) {
+// lidar_spread's scratch: the start bitmap shares the per-warp rows of `excl` (the pair-list bases are dead once the
+// list is built); the table lives in the record's non-laser columns of the group's first scene, which the tile
+// layout has consumed before the pair pass starts - when they are large enough (and 16-byte aligned), else in a
+// region of its own.
+__host__ __device__ inline bool lidar_tab_in_record(int A, int D, int n_ray, int rec_stride, int n_warps) {
+    return ((6 * A + 4) & 3) == 0 && (D - n_ray) * rec_stride >= n_warps * SPREAD_TAB_WORDS;
+}
+__host__ __device__ inline LidarPlan lidar_plan(int G, int A, int D, int n_ray, int rec_words, int rec_stride,
+                                                int pair_stride, int n_warps) {
     LidarPlan p;
     int o = 16;                                           // mbarrier
     p.ray = o;   o += (n_ray * 8 + 15) & ~15;
     p.rec = o;   o += G * rec_words * 4;                  // rec_words is a multiple of 4
     p.pairs = o; o += G * pair_stride * 2;                // pair_stride is a multiple of 8
-    p.nq = o;    o += ((G + 3) & ~3) * 4;
-    p.excl = o;  o += n_warps * MAX_SLOTS * 4;                    // per warp: exclusive pair-list bases of the observers
+    p.nq = o;    o += ((G + 1 + 3) & ~3) * 4;             // pair counts of the group's scenes, then the CTA's next group
+    p.excl = o;  o += n_warps * SPREAD_BITS_WORDS * 4;    // per warp: exclusive pair-list bases of the observers (MAX_SLOTS),
+                                                          // then the start bitmap of lidar_spread
+    p.tab = lidar_tab_in_record(A, D, n_ray, rec_stride, n_warps) ? p.rec + (6 * A + 4) * 4 : o;
+    if (p.tab == o) o += n_warps * SPREAD_TAB_WORDS * 4;
     p.tile = o;  o += ((G * A * D + 3) & ~3) * 4;
     p.total = o;
     return p;
 }
+static_assert(SPREAD_BITS_WORDS >= MAX_SLOTS, "the start bitmap shares the rows of the pair-list bases");
 
 template <int TA, int TD>
 __global__ void __launch_bounds__(ENV_MAX_THREADS)
@@ -461,7 +520,7 @@ env_lidar_kernel(const __grid_constant__ LidarIO io) {
     const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, n_warps = NT >> 5;
     const int n_ray = TA ? LIDAR_RAYS : io.n_ray;
     const int rec = io.rec_words;
-    const LidarPlan pl = lidar_plan(G, A, D, n_ray, rec, io.pair_stride, n_warps);
+    const LidarPlan pl = lidar_plan(G, A, D, n_ray, rec, io.rec_stride, io.pair_stride, n_warps);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);          // record arrivals
     float2* s_ray = reinterpret_cast<float2*>(smem_raw + pl.ray);
     float* s_rec = reinterpret_cast<float*>(smem_raw + pl.rec);
@@ -494,7 +553,10 @@ env_lidar_kernel(const __grid_constant__ LidarIO io) {
     int parts = NT / A;                                           // threads that share one observer's mask expansion
     parts = parts < 1 ? 1 : (parts > 4 ? 4 : parts);
     const int span = (A + parts - 1) / parts;                     // slots per thread
-    for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+    // Scene groups are handed out dynamically: a CTA starts on group blockIdx.x and draws the next one from a global
+    // counter when it is done with the record of the current one (scenes differ in their pair counts, and the scene
+    // count is no multiple of the resident CTAs: static striding left 100 of 1332 CTAs a fourth scene at the C2 shape).
+    for (int grp = blockIdx.x; grp < n_groups; grp = s_nq[G]) {
         const int scene0 = grp * G;
         const int ng = (io.S - scene0 < G) ? io.S - scene0 : G;
         if (tid == 0) mbar_wait(bar, parity);                     // one thread polls, the others sleep at the barrier
@@ -520,7 +582,7 @@ env_lidar_kernel(const __grid_constant__ LidarIO io) {
                     if (lane >= d) { i0 += n0; i1 += n1; }
                 }
                 const int t0 = __shfl_sync(0xffffffffu, i0, 31), t1 = __shfl_sync(0xffffffffu, i1, 31);
-                int* my_excl = s_excl + warp * MAX_SLOTS;
+                int* my_excl = s_excl + warp * SPREAD_BITS_WORDS;
                 my_excl[o0] = i0 - c0;                            // exclusive bases of observers lane / lane + 32
                 my_excl[o1] = t0 + i1 - c1;
                 __syncwarp();
@@ -579,6 +641,8 @@ env_lidar_kernel(const __grid_constant__ LidarIO io) {
             }
         }
         __syncthreads();
+        uint32_t* my_tab = reinterpret_cast<uint32_t*>(smem_raw + pl.tab) + warp * SPREAD_TAB_WORDS;
+        uint32_t* my_bits = reinterpret_cast<uint32_t*>(s_excl + warp * SPREAD_BITS_WORDS);
         for (int sl = 0; sl < ng; ++sl) {
             const float* ps = s_rec + sl * rec;
             const int nq = s_nq[sl];
@@ -587,20 +651,27 @@ env_lidar_kernel(const __grid_constant__ LidarIO io) {
             for (int base = warp * 32; base < nq; base += n_warps * 32) {
                 const int e = base + lane;
                 PairGeom g;
-                g.nx1 = g.nx2 = g.ny1 = g.ny2 = g.cc = g.ss = 0.0f; g.k0 = 0; g.cnt = 0;
-                int lid_off = 0;
+                g.nx1 = g.nx2 = g.ny1 = g.ny2 = g.cc = g.ss = g.ox = g.oy = 0.0f; g.k0 = 0; g.cnt = 0;
+                int oi = 0;
                 if (e < nq) {
                     int code = gq[e];
-                    int oi = (code >> 6) & 63, oj = code & 63;
+                    oi = (code >> 6) & 63;
+                    const int oj = code & 63;
                     lidar_pair_geom(ps[oi], ps[A + oi], ps[2 * A + oi], ps[3 * A + oi], ps[oj], ps[A + oj], ps[2 * A + oj],
                                     ps[3 * A + oj], n_ray, g);
-                    lid_off = oi * D;
                 }
-                lidar_spread(g, lid_off, e < nq, n_ray, s_ray, tile);
+                lidar_spread(g, oi, e < nq, n_ray, D, s_ray, tile, my_tab, my_bits);
             }
         }
         fence_async_smem();
         __syncthreads();
+        // the record is dead from here on: the next one travels while this group's rows are stored and converted (the
+        // bulk copy only writes the record region, which nothing below reads)
+        if (tid == 0) {
+            const int nxt = io.next_group ? (int)gridDim.x + atomicAdd(io.next_group, 1) : grp + (int)gridDim.x;
+            s_nq[G] = nxt;                                        // read by every thread after the barrier that ends the group
+            if (nxt < n_groups) fetch_record(nxt);
+        }
         // the group's observation rows are one contiguous block of HBM
         float* g_obs = io.obs + (size_t)scene0 * A * D;
         const int n_rows = ng * A;
@@ -673,10 +744,7 @@ env_lidar_kernel(const __grid_constant__ LidarIO io) {
             }
         }
         __syncthreads();
-        if (tid == 0) {
-            bulk_wait_read0();                                    // the tile has left shared memory
-            if (grp + (int)gridDim.x < n_groups) fetch_record(grp + gridDim.x);
-        }
+        if (tid == 0) bulk_wait_read0();                          // the tile has left shared memory
     }
 }
 
@@ -726,6 +794,7 @@ struct b2c_env {
     int lidar_group, lidar_threads, lidar_ctas, ray_off;
     size_t lidar_smem;
     float* d_pose;
+    int* d_next;             // the lidar kernel's scene-group counter
     int pair_stride, n_ray, rec_words, rec_stride;
     uint32_t* d_map;
     uint32_t* d_state;
@@ -802,7 +871,7 @@ int b2c_env_create(const b2c_env_config* c, const uint32_t* map_blob, int map_wo
     }
     e->smem = (size_t)smem_plan(e->group, k.A, k.D, map_words, e->tile_words, e->threads / 32, e->split).total;
     e->n_ray = (int)map_blob[M_NRAY];
-    e->d_pose = nullptr; e->rec_words = 0; e->pair_stride = 0; e->rec_stride = 0;
+    e->d_pose = nullptr; e->d_next = nullptr; e->rec_words = 0; e->pair_stride = 0; e->rec_stride = 0;
     const bool generic = getenv("B2C_ENV_GENERIC") != nullptr || e->n_ray != LIDAR_RAYS;
     e->step_fn = pick_step_kernel(e->split != 0, k.A, k.D, generic);
     e->lidar_fn = pick_lidar_kernel(k.A, k.D, generic);
@@ -827,7 +896,8 @@ int b2c_env_create(const b2c_env_config* c, const uint32_t* map_blob, int map_wo
         e->rec_stride = k.A | 1;
         e->rec_words = (6 * k.A + 4 + (k.D - e->n_ray) * e->rec_stride + 3) & ~3;
         auto lsm = [&](int g) {
-            return (size_t)lidar_plan(g, k.A, k.D, e->n_ray, e->rec_words, e->pair_stride, e->lidar_threads / 32).total;
+            return (size_t)lidar_plan(g, k.A, k.D, e->n_ray, e->rec_words, e->rec_stride, e->pair_stride,
+                                      e->lidar_threads / 32).total;
         };
         while (e->lidar_group > 1 && lsm(e->lidar_group) > 100 * 1024) e->lidar_group -= 1;
         if (e->lidar_group > k.S) e->lidar_group = k.S;
@@ -835,6 +905,8 @@ int b2c_env_create(const b2c_env_config* c, const uint32_t* map_blob, int map_wo
         B2C_CUDA_OR(cudaFuncSetAttribute(e->lidar_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->lidar_smem),
                     delete e);
         B2C_CUDA_OR(cudaMalloc(&e->d_pose, (size_t)k.S * e->rec_words * 4), delete e);
+        B2C_CUDA_OR(cudaMalloc(&e->d_next, sizeof(int)), delete e);
+        B2C_CUDA_OR(cudaMemset(e->d_next, 0, sizeof(int)), delete e);
     } else {
         B2C_CUDA_OR(cudaFuncSetAttribute(e->step_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem),
                     delete e);
@@ -852,6 +924,7 @@ int b2c_env_destroy(b2c_env* e) {
     cudaFree(e->d_map);
     cudaFree(e->d_state);
     cudaFree(e->d_pose);
+    cudaFree(e->d_next);
     delete e;
     return B2C_OK;
 }
@@ -861,6 +934,7 @@ static void launch_lidar(b2c_env* e, float* obs, uint32_t* obs_split, int kp, cu
     EnvConfig cfg = e->cfg;
     if (count >= 0) cfg.S = count;
     LidarIO li;
+    li.next_group = getenv("B2C_LIDAR_STATIC") ? nullptr : e->d_next;
     li.map = e->d_map; li.pose = e->d_pose ? e->d_pose + (size_t)first * e->rec_words : nullptr; li.obs = obs; li.obs_split = obs_split;
     li.pair_stride = e->pair_stride; li.rec_words = e->rec_words; li.n_ray = e->n_ray; li.ray_off = e->ray_off;
     li.rec_stride = e->rec_stride;
@@ -894,7 +968,7 @@ static int launch_env(b2c_env* e, const float* actions, const b2c_env_io* o, int
     io.obs_bulk = ((((size_t)cfg.A * cfg.D * 4) % 16 == 0) && (((uintptr_t)o->obs) % 16 == 0)) ? 1 : 0;
     io.group = e->group;
     io.pose = e->d_pose ? e->d_pose + (size_t)first * e->rec_words : nullptr; io.rec_words = e->rec_words;
-    io.rec_stride = e->rec_stride;
+    io.rec_stride = e->rec_stride; io.lidar_next = e->d_next;
     io.pl = smem_plan(e->group, cfg.A, cfg.D, e->map_words, e->tile_words, e->threads / 32, e->split != 0);
     int ctas_per_sm = (int)(227 * 1024 / (e->smem + 1024));
     int by_threads = 2048 / e->threads;
@@ -946,6 +1020,7 @@ int b2c_env_set_num_agents(b2c_env* e, int n) {
 int b2c_env_relaunch_lidar(b2c_env* e, const b2c_env_io* o, void* stream) {
     if (!e || !o || !o->obs) return b2c_set_error(B2C_ERR_ARG, "b2c_env_relaunch_lidar: null argument");
     if (!e->split) return b2c_set_error(B2C_ERR_STATE, "b2c_env_relaunch_lidar: the env runs the fused kernel");
+    B2C_CUDA(cudaMemsetAsync(e->d_next, 0, sizeof(int), (cudaStream_t)stream));     // the state kernel's job in a full step
     launch_lidar(e, o->obs, (uint32_t*)o->obs_split, (e->cfg.D + 63) / 64 * 64, (cudaStream_t)stream);
     B2C_CUDA(cudaGetLastError());
     return B2C_OK;

@@ -575,7 +575,7 @@ class CoPOPolicy(CCPPOPolicy):
         return ro
 
     # ---- meta-gradient (a18) -------------------------------------------------------------------------------
-    def _policy_grad(self, model, batch, mode, adv, rows, out):
+    def _policy_grad(self, model, batch, mode, adv, rows, out, x_split=None):
         """Gradient of the policy network only, into `out` (this rank's share of the global-minibatch mean)."""
         cfg = dict(clip_param=self.config["clip_param"], vf_clip_param=0.0, vf_loss_coeff=0.0, entropy_coeff=0.0,
                    kl_coeff=0.0)
@@ -583,12 +583,23 @@ class CoPOPolicy(CCPPOPolicy):
         model.grad[model.policy_slice()].zero_()
         st = torch.zeros(8, dtype=torch.float64, device=self.device)
         if batch[OBS].shape[0] > 0:
-            acts = pol.forward_train(batch[OBS], model._tc())
+            acts = pol.forward_train(batch[OBS], model._tc(), x_split)
             dlogits, _, st = ops.ppo_head(acts[3], batch[ACTIONS], batch[ACTION_LOGP], None, adv, [], cfg, mode=mode,
                                           norm_rows=rows, stats=st)
             pol.backward(acts, dlogits, model._tc())
         out.copy_(model.grad[model.policy_slice()])
         return st
+
+    def _meta_grads(self, batch, rows, g_new, g_old):
+        """Both policy-gradient vectors of the meta step (algo_copo.py:236-262): the surrogate of the CURRENT policy on
+        the global advantage, the log-probability gradient of the OLD policy.  Device work only."""
+        sp = None                                        # both networks read the same [hi | lo] operand of the observations
+        if self.model._tc() is not None and batch[OBS].shape[0] > 0:
+            d = self.model.nets["policy"].in_dim
+            sp = ops.tc_split_rows(batch[OBS], ones_col=ops.tc_has_ones_col(d) and d <= 256)
+        st_new = self._policy_grad(self.model, batch, 0, batch[GLOBAL_ADVANTAGES], rows, g_new, sp)
+        st_old = self._policy_grad(self.target_model, batch, 1, None, rows, g_old, sp)
+        return st_new, st_old
 
     def meta_update(self, train_batch, eps=None, global_rows=None):
         B = train_batch[OBS].shape[0]
@@ -597,8 +608,7 @@ class CoPOPolicy(CCPPOPolicy):
         if getattr(self, "_meta_g", None) is None:
             self._meta_g = torch.empty(2 * n, dtype=torch.float32, device=self.device)
         g_new, g_old = self._meta_g[:n], self._meta_g[n:]
-        st_new = self._policy_grad(self.model, train_batch, 0, train_batch[GLOBAL_ADVANTAGES], rows, g_new)
-        st_old = self._policy_grad(self.target_model, train_batch, 1, None, rows, g_old)
+        st_new, st_old = self._meta_grads(train_batch, rows, g_new, g_old)
         # reduce BOTH gradient vectors (one all-reduce) BEFORE the dot product: it is bilinear
         parallel.allreduce_sum_(self._meta_g, self.dist, self.ar_timer)
         grad_value = ops.dot(g_new, g_old)[0]

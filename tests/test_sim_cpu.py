@@ -225,34 +225,57 @@ def test_procedural_maps(seed, num_blocks):
 
 
 def test_laser_ownership_formula():
-    """Model of `lidar_spread` (env_step.cu): 32 pairs per warp, pair p owns lasers [excl_p, excl_p + cnt_p); live pairs
-    have cnt >= 1 and dead lanes only trail.  For the batch of lasers r0 .. r0+31 the owner of laser r0 + lane is
-    (pairs started before the batch) + popcount(starts at positions <= lane) - 1, where `starts` has a bit per pair that
-    begins inside the batch - the kernel gets it from one warp-wide OR.  Checked against a plain search."""
+    """Model of `lidar_spread` (env_step.cu): 32 pairs per warp, each with a window of cnt lasers starting at k0.  Every
+    pair's own lane casts its first LIDAR_OWN lasers; the pairs that have more are ranked, pair `rank` owns the warp's
+    lasers [excl, excl + rest) and sets bit `excl` of a start bitmap; for the batch of lasers r0 .. r0+31 the owner of
+    laser r0 + lane is (start bits before the batch) + popcount(start bits of the batch at positions <= lane) - 1, and
+    its laser index is (k0 + LIDAR_OWN - excl) + r wrapped once.  Checked against the plain enumeration: every
+    (pair, laser) of every window exactly once."""
+    NRAY = 72
+    src = open(os.path.join(ROOT, "copo_b200", "csrc", "env_step.cu")).read()
+    OWN = int(re.search(r"#define B2C_LIDAR_OWN (\d+)", src).group(1))
+    assert 0 <= OWN <= 4
+    assert int(re.search(r"SPREAD_BITS_WORDS = (\d+);", src).group(1)) * 32 >= 32 * (NRAY - OWN)
     rng = np.random.default_rng(0)
     for trial in range(300):
-        n_live = int(rng.integers(1, 33))
-        cnt = np.zeros(32, np.int64)
-        cnt[:n_live] = rng.integers(1, 73, n_live)
+        live = rng.random(32) < (1.0 if trial % 5 == 0 else 0.8)
+        cnt = np.where(live, rng.integers(1, NRAY + 1, 32), 0)
         if trial % 3 == 0:
-            cnt[:n_live] = 1                                   # every pair a single laser
-        excl = np.concatenate([[0], np.cumsum(cnt)[:-1]])
-        total = int(cnt.sum())
+            cnt = np.where(live, rng.integers(1, 4, 32), 0)        # short windows: few or no pairs reach the spread
+        if trial % 7 == 0:
+            cnt = np.where(live, NRAY, 0)                          # every pair the full circle
+        k0 = rng.integers(0, NRAY, 32)
+        want = sorted((p, (k0[p] + q) % NRAY) for p in range(32) for q in range(cnt[p]))
+        got = [(p, (k0[p] + q) % NRAY) for p in range(32) for q in range(min(cnt[p], OWN))]
+        rest = np.maximum(cnt - OWN, 0)
+        ranked = [p for p in range(32) if rest[p] > 0]
+        excl = np.concatenate([[0], np.cumsum(rest)[:-1]])
+        total = int(rest.sum())
+        bits = [0] * ((total + 31) // 32 + 1)
+        table = []
+        for p in ranked:
+            assert not (bits[excl[p] >> 5] >> (excl[p] & 31)) & 1
+            bits[excl[p] >> 5] |= 1 << int(excl[p] & 31)
+            code = ((int(k0[p]) + OWN - int(excl[p]) + 4096) << 8) | p
+            assert 0 < code < 2 ** 31
+            table.append(code)
         before = 0
         for r0 in range(0, total, 32):
-            pos = excl - r0
-            starts = 0
-            for p in range(32):
-                if cnt[p] > 0 and 0 <= pos[p] < 32:
-                    starts |= 1 << int(pos[p])
+            starts = bits[r0 >> 5]
             for lane in range(32):
                 r = r0 + lane
                 if r >= total:
                     continue
-                lo = before + bin(starts & (0xffffffff >> (31 - lane))).count("1") - 1
-                want = int(np.searchsorted(excl[:n_live], r, side="right")) - 1
-                assert lo == want and excl[lo] <= r < excl[lo] + cnt[lo], (trial, r0, lane)
+                owner = before + bin(starts & (0xffffffff >> (31 - lane))).count("1") - 1
+                code = table[owner]
+                k = (code >> 8) - 4096 + r
+                assert 0 <= k < 2 * NRAY
+                k = min(k, (k - NRAY) & 0xffffffff)
+                p = code & 255
+                assert excl[p] <= r < excl[p] + rest[p]
+                got.append((p, k))
             before += bin(starts).count("1")
+        assert sorted(got) == want, trial
 
 
 def test_sampled_scenes_of_a_large_batch_replay_in_the_oracle():
