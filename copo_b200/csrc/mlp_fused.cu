@@ -47,6 +47,9 @@ struct FusedArgs {
     int M, kp1_blocks, head_n, products;
     uint32_t seed, step;
     long long* trace;         // diagnostics (b2c_tc_mlp2_set_trace): CTA 0 stamps clock64() at 16 pipeline events per tile
+    // training forward (TRAIN = true): what the backward pass reads again leaves the SM as a by-product of the epilogues
+    uint16_t* h1_split;       // [M][512] bf16: the first hidden layer as [hi | lo] (layer 2's A operand; 1 - h1^2 in dgrad)
+    float* h2;                // [M][256] fp32: the second hidden layer (head_backward)
 };
 #define F_TRACE(k) do { if (args.trace && blockIdx.x == 0) args.trace[t_local * 16 + (k)] = clock64(); } while (0)
 
@@ -62,6 +65,7 @@ __device__ __forceinline__ void fence_async_shared() { asm volatile("fence.proxy
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+template <bool TRAIN>
 __global__ void __launch_bounds__(F_THREADS, 1)
 tc_mlp2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w1,
                const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ FusedArgs args) {
@@ -296,7 +300,7 @@ tc_mlp2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
         // bias + tanh on 32 raw accumulator columns, then the output layer's (even, odd) partial sums
-        auto e2_half = [&](const uint32_t* rr, int c, uint64_t* hacc2) {
+        auto e2_half = [&](const uint32_t* rr, int c, uint64_t* hacc2, float* h2_row) {
             uint64_t vv[16];
             const ulonglong2* bp = reinterpret_cast<const ulonglong2*>(s_b2 + c * 32);
 #pragma unroll
@@ -304,6 +308,19 @@ tc_mlp2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const ulonglong2 bb = bp[j];
                 vv[2 * j] = fast_tanh2(add2(pk2(__uint_as_float(rr[4 * j]), __uint_as_float(rr[4 * j + 1])), bb.x));
                 vv[2 * j + 1] = fast_tanh2(add2(pk2(__uint_as_float(rr[4 * j + 2]), __uint_as_float(rr[4 * j + 3])), bb.y));
+            }
+            if constexpr (TRAIN) {
+                if (h2_row) {                                    // 32 columns of this row: four 32-byte stores
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float f[8];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) upk2(vv[4 * j + u], f[2 * u], f[2 * u + 1]);
+                        st_global_256(h2_row + c * 32 + 8 * j, __float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]),
+                                      __float_as_uint(f[3]), __float_as_uint(f[4]), __float_as_uint(f[5]), __float_as_uint(f[6]),
+                                      __float_as_uint(f[7]));
+                    }
+                }
             }
             if (args.head_n == 4) {
 #pragma unroll
@@ -333,13 +350,18 @@ tc_mlp2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const uint32_t tp = (uint32_t)(i - 1);               // tile of E2 in this iteration
             uint64_t hacc2[HEAD_MAX] = {0ull, 0ull, 0ull, 0ull};
             uint32_t rb[32];                                     // second half of E2's columns, raw, held across E1
+            float* h2_row = nullptr;                             // TRAIN: this thread's row of h2 for tile i - 1
+            if constexpr (TRAIN) {
+                const long long row2 = ((long long)blockIdx.x + (long long)(i - 1) * gridDim.x) * BLOCK_M + r;
+                if (i > 0 && row2 < args.M) h2_row = args.h2 + row2 * BLOCK_N;
+            }
             if (i > 0) {
                 mbar_wait_backoff(d2_full, tp & 1u);
                 if (warp == 4 && lane == 0) { if (args.trace && blockIdx.x == 0) args.trace[tp * 16 + 10] = clock64(); }
                 tc_fence_after();
                 uint32_t ra[32];
                 tmem_ld32(tmem_d2 + lane_base + (uint32_t)(sub * 64), ra);
-                e2_half(ra, 2 * sub, hacc2);
+                e2_half(ra, 2 * sub, hacc2, h2_row);
                 tmem_ld32(tmem_d2 + lane_base + (uint32_t)(sub * 64 + 32), rb);
                 tc_fence_before();
                 __syncwarp();
@@ -349,6 +371,11 @@ tc_mlp2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (i < my_tiles) {
                 // ---- E1(i): 16 columns of every reduction block ----
                 const uint32_t g_base = t_local * (uint32_t)nb + (uint32_t)nb1;
+                uint16_t* h1_row = nullptr;                      // TRAIN: this thread's row of the [hi | lo] hidden operand
+                if constexpr (TRAIN) {
+                    const long long row1 = ((long long)blockIdx.x + (long long)i * gridDim.x) * BLOCK_M + r;
+                    if (row1 < args.M) h1_row = args.h1_split + row1 * (2 * BLOCK_N);
+                }
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c) {                    // reduction block of layer 2 = hidden columns 64 c ..
                     if (c == 0) {
@@ -381,6 +408,13 @@ tc_mlp2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         split2(t0, hi[2 * j], lo[2 * j]);
                         split2(t1, hi[2 * j + 1], lo[2 * j + 1]);
                     }
+                    if constexpr (TRAIN) {
+                        if (h1_row) {                            // the same 16 columns to HBM: 32 bytes into each half of the row
+                            uint16_t* dst = h1_row + c * 64 + sub * 16;
+                            st_global_256(dst, hi[0], hi[1], hi[2], hi[3], hi[4], hi[5], hi[6], hi[7]);
+                            st_global_256(dst + BLOCK_N, lo[0], lo[1], lo[2], lo[3], lo[4], lo[5], lo[6], lo[7]);
+                        }
+                    }
                     mbar_wait_backoff(&empty[s], ((g >> 1) & 1u) ^ 1u);          // the stage's previous MMAs have retired
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {                // 16-byte chunks 2 sub + j of the row, XOR-swizzled
@@ -396,7 +430,7 @@ tc_mlp2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
             if (i > 0) {
                 // ---- E2(i-1), second half, and the partial sums for the finaliser (double-buffered by tile parity) ----
-                e2_half(rb, 2 * sub + 1, hacc2);
+                e2_half(rb, 2 * sub + 1, hacc2, h2_row);
                 const int buf = (int)(tp & 1u);
                 float hs[HEAD_MAX];
 #pragma unroll
@@ -434,20 +468,25 @@ extern "C" {
  * into dev_buffer ([tiles of CTA 0][16]); null turns it off */
 int b2c_tc_mlp2_set_trace(long long* dev_buffer) { g_trace = dev_buffer; return B2C_OK; }
 
-int b2c_tc_mlp2_head(const uint16_t* a_split, int Kp1, const uint16_t* w1_prep, const float* b1, const uint16_t* w2_prep,
-                     const float* b2, const b2c_tc_head* head, int M, void* stream) {
+static int launch_mlp2(const uint16_t* a_split, int Kp1, const uint16_t* w1_prep, const float* b1, const uint16_t* w2_prep,
+                       const float* b2, const b2c_tc_head* head, uint16_t* h1_split, float* h2, int M, void* stream,
+                       const char* who) {
     if (M == 0) return B2C_OK;
     if (!a_split || !w1_prep || !w2_prep || !b1 || !b2 || M < 0 || Kp1 < BLOCK_K || Kp1 % BLOCK_K)
-        return b2c_set_error(B2C_ERR_ARG, "b2c_tc_mlp2_head: bad argument");
+        return b2c_set_error(B2C_ERR_ARG, "%s: bad argument", who);
     if (!head || !head->weight || !head->bias || !head->out || (head->n != 1 && head->n != 4))
-        return b2c_set_error(B2C_ERR_ARG, "b2c_tc_mlp2_head: the output layer needs weight, bias, out and n in {1, 4}");
-    if (head->actions && head->n != 4) return b2c_set_error(B2C_ERR_ARG, "b2c_tc_mlp2_head: sampling needs the 4 policy logits");
+        return b2c_set_error(B2C_ERR_ARG, "%s: the output layer needs weight, bias, out and n in {1, 4}", who);
+    if (head->actions && head->n != 4) return b2c_set_error(B2C_ERR_ARG, "%s: sampling needs the 4 policy logits", who);
     if (((uintptr_t)a_split | (uintptr_t)w1_prep | (uintptr_t)w2_prep | (uintptr_t)head->out | (uintptr_t)head->actions) & 15)
-        return b2c_set_error(B2C_ERR_ARG, "b2c_tc_mlp2_head: pointers must be 16-byte aligned");
+        return b2c_set_error(B2C_ERR_ARG, "%s: pointers must be 16-byte aligned", who);
+    const bool train = h1_split != nullptr;
+    if (train && (!h2 || (((uintptr_t)h1_split | (uintptr_t)h2) & 31)))
+        return b2c_set_error(B2C_ERR_ARG, "%s: h1_split and h2 must both be given, 32-byte aligned", who);
     static int attr_set = 0;
     static int num_sms = 0;
     if (!attr_set) {
-        B2C_CUDA(cudaFuncSetAttribute(tc_mlp2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_BYTES));
+        B2C_CUDA(cudaFuncSetAttribute(tc_mlp2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_BYTES));
+        B2C_CUDA(cudaFuncSetAttribute(tc_mlp2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_BYTES));
         int dev = 0;
         B2C_CUDA(cudaGetDevice(&dev));
         B2C_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -468,6 +507,7 @@ int b2c_tc_mlp2_head(const uint16_t* a_split, int Kp1, const uint16_t* w1_prep, 
     a.products = products == 3 ? 3 : 4;
     a.seed = head->seed; a.step = head->step;
     a.trace = g_trace;
+    a.h1_split = h1_split; a.h2 = h2;
     const int tiles = (M + BLOCK_M - 1) / BLOCK_M;
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3((unsigned)(tiles < num_sms ? tiles : num_sms));
@@ -478,8 +518,20 @@ int b2c_tc_mlp2_head(const uint16_t* a_split, int Kp1, const uint16_t* w1_prep, 
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     lc.attrs = at; lc.numAttrs = pdl ? 1 : 0;
-    B2C_CUDA(cudaLaunchKernelEx(&lc, tc_mlp2_kernel, map_a, map_w1, map_w2, a));
+    if (train) B2C_CUDA(cudaLaunchKernelEx(&lc, tc_mlp2_kernel<true>, map_a, map_w1, map_w2, a));
+    else B2C_CUDA(cudaLaunchKernelEx(&lc, tc_mlp2_kernel<false>, map_a, map_w1, map_w2, a));
     return B2C_OK;
+}
+
+int b2c_tc_mlp2_head(const uint16_t* a_split, int Kp1, const uint16_t* w1_prep, const float* b1, const uint16_t* w2_prep,
+                     const float* b2, const b2c_tc_head* head, int M, void* stream) {
+    return launch_mlp2(a_split, Kp1, w1_prep, b1, w2_prep, b2, head, nullptr, nullptr, M, stream, "b2c_tc_mlp2_head");
+}
+
+int b2c_tc_mlp2_train(const uint16_t* a_split, int Kp1, const uint16_t* w1_prep, const float* b1, const uint16_t* w2_prep,
+                      const float* b2, const b2c_tc_head* head, uint16_t* h1_split, float* h2, int M, void* stream) {
+    if (!h1_split || !h2) return b2c_set_error(B2C_ERR_ARG, "b2c_tc_mlp2_train: h1_split and h2 are required");
+    return launch_mlp2(a_split, Kp1, w1_prep, b1, w2_prep, b2, head, h1_split, h2, M, stream, "b2c_tc_mlp2_train");
 }
 
 }  // extern "C"

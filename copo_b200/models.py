@@ -22,6 +22,7 @@ from . import ops
 # inference passes (rollout actions, value predictions) run the one-kernel network (mlp_fused.cu); B2C_TC_FUSED=0 falls
 # back to the layer-by-layer kernels (same bits) for A/B measurements
 FUSED_INFERENCE = os.environ.get("B2C_TC_FUSED", "1") != "0"
+FUSED_TRAINING = os.environ.get("B2C_TC_FUSED_TRAIN", "1") != "0"      # the learner's forward in the same kernel
 
 
 def centralized_critic_obs_dim(obs_dim, act_dim, counterfactual=True, num_neighbours=4, fuse_mode="mf"):
@@ -109,6 +110,9 @@ class _Net:
             ones = ops.tc_has_ones_col(self.in_dim) and self.in_dim <= 256
             s0 = x_split if x_split is not None else ops.tc_split_rows(x, ones_col=ones)
             # h1 only leaves as the [hi | lo] operand of layer 2: the backward pass takes 1 - h1^2 from it
+            if self.out_dim in (1, 4) and FUSED_TRAINING:        # one kernel: h1's operand and h2 leave from its epilogues
+                out, s1, h2 = ops.tc_mlp2_head(s0, w1, self.b[0], w2, self.b[1], self.W[2], self.b[2], train=True)
+                return [x, None, h2, out, s0, s1, ones]
             _, s1 = ops.tc_linear(s0, w1, self.b[0], act=1, want_f32=False, want_split=True)
             if self.out_dim in (1, 4):   # output layer in the layer-2 epilogue; h2 is kept for the backward pass
                 out, _, _, h2 = ops.tc_linear_head(s1, w2, self.b[1], self.W[2], self.b[2], act=1, want_f32=True)

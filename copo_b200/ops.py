@@ -384,10 +384,13 @@ def tc_linear_head(a_split, w_prep, bias, head_w, head_b, act=1, sample=None, wa
     return out, actions, logp, h
 
 
-def tc_mlp2_head(a_split, w1_prep, b1, w2_prep, b2, head_w, head_b, sample=None, out=None, actions=None, logp=None):
+def tc_mlp2_head(a_split, w1_prep, b1, w2_prep, b2, head_w, head_b, sample=None, out=None, actions=None, logp=None,
+                 train=False):
     """The whole inference pass of a 256-256 tanh network in ONE kernel (mlp_fused.cu): both hidden layers stay on the
     SM, the narrow output layer (n = 1 or 4) and - with sample = (seed, step) - the Gaussian action draw ride in the last
-    epilogue.  Bit-identical to tc_linear + tc_linear_head.  Returns (head_out [M, n], actions or None, logp or None)."""
+    epilogue.  Bit-identical to tc_linear + tc_linear_head.  Returns (head_out [M, n], actions or None, logp or None).
+    train=True (the learner's forward, b2c_tc_mlp2_train): also writes the hidden layers the backward pass reads again and
+    returns (head_out, h1_split [M, 512] bf16, h2 [M, 256] fp32)."""
     lib = _lib_ready()
     M, two_kp = a_split.shape
     Kp = two_kp // 2
@@ -407,6 +410,12 @@ def tc_mlp2_head(a_split, w1_prep, b1, w2_prep, b2, head_w, head_b, sample=None,
             logp = torch.empty((M,), dtype=torch.float32, device=dev)
         hd.actions, hd.logp = actions.data_ptr(), logp.data_ptr()
         hd.seed, hd.step = sample[0] & 0xFFFFFFFF, sample[1] & 0xFFFFFFFF
+    if train:
+        h1_split = torch.empty((M, 512), dtype=torch.bfloat16, device=dev)
+        h2 = torch.empty((M, 256), dtype=torch.float32, device=dev)
+        _lib.check(lib.b2c_tc_mlp2_train(P(a_split), c_int(Kp), P(w1_prep), P(b1), P(w2_prep), P(b2), ctypes.byref(hd),
+                                         P(h1_split), P(h2), c_int(M), _lib.stream_ptr()))
+        return out, h1_split, h2
     _lib.check(lib.b2c_tc_mlp2_head(P(a_split), c_int(Kp), P(w1_prep), P(b1), P(w2_prep), P(b2), ctypes.byref(hd), c_int(M),
                                     _lib.stream_ptr()))
     return out, actions, logp

@@ -254,6 +254,14 @@ int b2c_tc_linear_head(const uint16_t* a_split, const uint16_t* w_prep, const fl
  * bit-identical to b2c_tc_linear followed by b2c_tc_linear_head.  w1_prep [256][2*Kp1], w2_prep [256][512]. */
 int b2c_tc_mlp2_head(const uint16_t* a_split, int Kp1, const uint16_t* w1_prep, const float* b1, const uint16_t* w2_prep,
                      const float* b2, const b2c_tc_head* head, int M, void* stream);
+/* The same kernel as the learner's forward pass (CCModel / CoPOModel forward under `loss`, algo_copo.py:311-330,
+ * algo_ccppo.py:376-400): besides head.out it leaves what the backward pass reads again - the first hidden layer as the
+ * [hi | lo] operand h1_split [M][512] (layer 2's input; 1 - h1^2 in b2c_tc_linear_dgrad) and the second hidden layer
+ * h2 [M][256] fp32 (b2c_head_backward_split) - written from the epilogues, so the hidden layers cross HBM once (out)
+ * instead of three times.  Bit-identical to b2c_tc_linear(split out) + b2c_tc_linear_head(fp32 out) in h1_split and h2.
+ * Both buffers 32-byte aligned. */
+int b2c_tc_mlp2_train(const uint16_t* a_split, int Kp1, const uint16_t* w1_prep, const float* b1, const uint16_t* w2_prep,
+                      const float* b2, const b2c_tc_head* head, uint16_t* h1_split, float* h2, int M, void* stream);
 /* Diagnostics: CTA 0 of the following b2c_tc_mlp2_head launches stamps clock64() at 16 pipeline events per tile into
  * dev_buffer ([tiles of CTA 0][16] int64); NULL turns it off (tools/fused_trace.py prints the timeline). */
 int b2c_tc_mlp2_set_trace(long long* dev_buffer);

@@ -155,5 +155,12 @@ def test_tc_one_kernel_network_matches_the_layer_kernels(M, K):
     ref = _ref(_ref(_ref(x.cpu(), W1.cpu(), b1.cpu(), 1), W2.cpu(), b2.cpu(), 1), W3.cpu(), b3.cpu(), 0)
     assert float((got.cpu().double() - ref).abs().max()) < 2e-5
     v, _, _ = ops.tc_mlp2_head(a, w1, b1, w2, b2, W3[:1].contiguous(), b3[:1].contiguous())
-    wv, _, _, _ = ops.tc_linear_head(s1, w2, b2, W3[:1].contiguous(), b3[:1].contiguous(), act=1)
+    wv, _, _, wh2 = ops.tc_linear_head(s1, w2, b2, W3[:1].contiguous(), b3[:1].contiguous(), act=1, want_f32=True)
     assert float((v - wv).abs().max()) < 2e-6
+    # the learner's forward (b2c_tc_mlp2_train): the same kernel also leaves h1's [hi | lo] operand and h2 - the bits the
+    # layer kernels write, every row of a ragged tile tail included
+    for W, b in ((W3, b3), (W3[:1].contiguous(), b3[:1].contiguous())):
+        out, t1, t2 = ops.tc_mlp2_head(a, w1, b1, w2, b2, W, b, train=True)
+        assert t1.shape == (M, 512) and t2.shape == (M, 256)
+        assert torch.equal(t1.view(torch.int16), s1.view(torch.int16)) and torch.equal(t2, wh2)
+        assert torch.equal(out, got if W.shape[0] == 4 else v)
