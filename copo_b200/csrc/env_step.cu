@@ -26,6 +26,7 @@ namespace b2c {
 #define B2C_LIDAR_OWN 1
 #endif
 static constexpr int LIDAR_OWN = B2C_LIDAR_OWN;
+static constexpr int LIDAR_RAYS = 72;      // laser count of every shipped map (the specialised kernels assume it)
 static constexpr int SPREAD_TAB_WORDS = 160;       // per warp: float4[32] {ox, oy, cc, ss} + int[32] {(k - excl + 4096) << 8 | row}
 static constexpr int SPREAD_BITS_WORDS = 72;       // per warp: 32 pairs x up to 72 lasers = 2304 start bits
 static constexpr int SPREAD_MAX_RAYS = 72;         // more lasers than this per observer: everything goes through the own-lane loop
@@ -352,6 +353,14 @@ env_step_kernel(const __grid_constant__ EnvConfig cfg, const __grid_constant__ E
         __syncthreads();
         // ---- P6b: neighbours (+ lidar pair queue), per-slot outputs, ego/navi features (thread = slot) ----
         const bool spare = (NT - ng * A) >= ng;          // idle threads take the per-scene reductions
+        // maps with many side detectors (Tollgate: 65, a sincos and a division each): when the CTA has more threads than
+        // slots - small batches run one scene per CTA, see b2c_env_create - the detectors of a slot are dealt to
+        // NT / slots threads after the per-slot phases instead of being walked by the slot's own thread
+        // (a shape-specialised kernel knows from its observation width whether its map can have that many: D = 19 + 72
+        // lasers + side detectors (+ LCF); the others carry no code for it)
+        constexpr bool MAY_SPREAD = SPLIT && (TD == 0 || TD - (EGO_DIM + NAVI_DIM + LIDAR_RAYS + 1) >= 16);
+        const int n_side_map = MAY_SPREAD ? (int)s_map[M_NSIDE] : 0;
+        const bool side_spread = MAY_SPREAD && n_side_map >= 16 && NT >= 2 * ng * A;
         if (has_agent) {
             NeiOut n = phase_neighbours(v, cfg, ia, io.mf_mask != nullptr, io.nei_list != nullptr);
             if constexpr (SPLIT) {
@@ -374,7 +383,7 @@ env_step_kernel(const __grid_constant__ EnvConfig cfg, const __grid_constant__ E
             if (io.agent_id) io.agent_id[g] = v.geti(F_ID, ia);
             const float lcf_now = step_lcf(v, cfg, scene0 + sl_a, ia);
             if (io.lcf) io.lcf[g] = lcf_now;
-            phase_observe_ego(v, cfg, ia, lcf_now);
+            phase_observe_ego(v, cfg, ia, lcf_now, side_spread);
             if (!SPLIT) phase_lidar_init(v, ia);
         }
         {
@@ -410,6 +419,16 @@ env_step_kernel(const __grid_constant__ EnvConfig cfg, const __grid_constant__ E
                              s_spread + SPREAD_TAB_WORDS);
             }
         }
+        }
+        if constexpr (MAY_SPREAD) {
+            if (side_spread) {
+                const int n_slots = ng * A, per = NT / n_slots;          // threads per slot
+                const int slot = tid % n_slots, part = tid / n_slots;
+                if (part < per) {
+                    SceneView vs = view(slot / A);
+                    for (int kk = part; kk < n_side_map; kk += per) phase_side_item(vs, slot - (slot / A) * A, kk);
+                }
+            }
         }
         fence_async_smem();
         __syncthreads();
@@ -482,7 +501,6 @@ struct LidarIO {
     int* next_group;      // groups handed out beyond the first one of every CTA (0 at launch), or null: static striding
     int pair_stride, rec_words, rec_stride, kp, group, S, A, D, n_ray, ray_off;
 };
-static constexpr int LIDAR_RAYS = 72;      // laser count of every shipped map (the specialised kernels assume it)
 
 struct LidarPlan {
     int ray, rec, pairs, nq, excl, tab, tile, total;
@@ -865,6 +883,12 @@ int b2c_env_create(const b2c_env_config* c, const uint32_t* map_blob, int map_wo
     const int smem_cap = e->split ? 36 * 1024 : 56 * 1024;
     while (e->group > 1 && smem_plan(e->group, k.A, k.D, map_words, e->tile_words, e->threads / 32, e->split).total > smem_cap)
         e->group -= 1;
+    // Small batches of a map with many side detectors (Tollgate at the C4 shape: 1024 scenes per GPU = 342 groups of 3, a
+    // third of a wave, every CTA walking 65 detectors per slot on the slot's own thread): one scene per CTA instead, its
+    // 128 threads then share each slot's detectors three ways (env_step_kernel, side_spread)
+    if (e->split && (int)map_blob[M_NSIDE] >= 16 && e->group > 1 &&
+        (k.S + e->group - 1) / e->group <= 3 * e->num_sms && e->threads >= 2 * k.A)
+        e->group = 1;
     if (const char* g = getenv("B2C_ENV_GROUP")) {
         int gg = atoi(g);
         if (gg >= 1 && gg <= fit) e->group = gg;

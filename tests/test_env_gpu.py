@@ -43,6 +43,20 @@ def _to_np(out):
 def test_env_step_bit_exact(map_name, S, A, T, kw, split, monkeypatch):
     """split = 0: the fused single-kernel step; split = 1: state kernel + lidar kernel (B2C_ENV_SPLIT)."""
     monkeypatch.setenv("B2C_ENV_SPLIT", str(split))
+    _run_bit_exact(map_name, S, A, T, kw)
+
+
+@pytest.mark.parametrize("group", [1, 3])
+def test_side_detectors_on_the_slot_thread_and_spread_over_the_cta(group, monkeypatch):
+    """Tollgate's 65 side detectors: small batches run one scene per CTA and deal each slot's detectors to three threads
+    (the default at this size, group = 1); large batches keep three scenes per CTA with the detectors on the slot's own
+    thread (forced here with B2C_ENV_GROUP = 3).  Same bits either way."""
+    monkeypatch.setenv("B2C_ENV_SPLIT", "1")
+    monkeypatch.setenv("B2C_ENV_GROUP", str(group))
+    _run_bit_exact("tollgate", 5, 40, 80, dict())
+
+
+def _run_bit_exact(map_name, S, A, T, kw):
     from copo_b200.batched_env import BatchedDrivingEnv
     tables = build_map(map_name)
     cfg = osim.SimConfig(seed=11, **kw)
