@@ -176,6 +176,85 @@ __global__ void cc_obs_fuse_kernel(const float* __restrict__ obs, const float* _
     }
 }
 
+// Mean-field fusion, one CTA per (t, scene): the scene's observation rows (contiguous in HBM) and actions are staged in
+// shared memory once, then every warp takes rows of the scene - the neighbour mask is warp-uniform, lanes own NU
+// columns each (lane + 32 u < W = D + AD), so a neighbour costs NU shared loads and adds instead of eight predicated
+// global loads; the row leaves as [own | mean] through coalesced stores.  Same sums in the same (slot) order as
+// cc_obs_fuse_kernel, mode 1.  HBM traffic is the algorithmic 4 * (D + AD) in + 4 * (2 D + AD) out per row.
+template <int NU>
+__global__ void __launch_bounds__(128)
+cc_obs_fuse_mf_scene_kernel(const float* __restrict__ obs, const float* __restrict__ act,
+                            const uint8_t* __restrict__ flags, const unsigned long long* __restrict__ mf_mask,
+                            float* __restrict__ cobs, int A, int D, int AD, int C, int counterfactual) {
+    extern __shared__ __align__(16) float s_fuse[];
+    float* s_obs = s_fuse;                                       // [A][D]
+    float* s_act = s_fuse + ((A * D + 3) & ~3);                  // [A][AD]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = blockDim.x >> 5;
+    const size_t row0 = (size_t)blockIdx.x * A;                  // first slot of this (t, scene)
+    {
+        const float* g = obs + row0 * D;
+        const int n = A * D;
+        if ((n & 3) == 0 && ((reinterpret_cast<uintptr_t>(g) & 15) == 0)) {
+            const float4* g4 = reinterpret_cast<const float4*>(g);
+            float4* s4 = reinterpret_cast<float4*>(s_obs);
+            for (int k = tid; k < (n >> 2); k += blockDim.x) s4[k] = g4[k];
+        } else {
+            for (int k = tid; k < n; k += blockDim.x) s_obs[k] = g[k];
+        }
+        if (counterfactual) {
+            const float* ga = act + row0 * AD;
+            for (int k = tid; k < A * AD; k += blockDim.x) s_act[k] = ga[k];
+        }
+    }
+    // slots of the scene that have a row at this t (the same on every warp)
+    const bool f0 = lane < A && (flags[row0 + lane] & FLAG_VALID);
+    const bool f1 = lane + 32 < A && (flags[row0 + lane + 32] & FLAG_VALID);
+    const unsigned long long have = (unsigned long long)__ballot_sync(0xffffffffu, f0) |
+                                    ((unsigned long long)__ballot_sync(0xffffffffu, f1) << 32);
+    __syncthreads();
+    const int W = D + (counterfactual ? AD : 0);
+    // this lane's columns of a neighbour's [obs | act] row: base pointer and row stride per column slot
+    const float* cbase[NU];
+    int cstride[NU];
+    bool con[NU];
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+        const int d = lane + 32 * u;
+        con[u] = d < W;
+        cbase[u] = (d < D) ? s_obs + d : s_act + (d - D);
+        cstride[u] = (d < D) ? D : AD;
+    }
+    for (int i = warp; i < A; i += n_warps) {
+        float* out = cobs + (row0 + i) * C;
+        const bool valid = (have >> i) & 1ull;
+        const unsigned long long vm = valid ? (mf_mask[row0 + i] & have) : 0ull;
+        const int cnt = __popcll(vm);
+        float acc[NU];
+#pragma unroll
+        for (int u = 0; u < NU; ++u) acc[u] = 0.0f;
+        uint32_t w = (uint32_t)vm;
+        int base = 0;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            while (w) {
+                const int j = base + __ffs((int)w) - 1;
+                w &= w - 1u;
+#pragma unroll
+                for (int u = 0; u < NU; ++u)
+                    if (con[u]) acc[u] += cbase[u][j * cstride[u]];
+            }
+            w = (uint32_t)(vm >> 32);
+            base = 32;
+        }
+        const float inv = cnt > 0 ? 1.0f / (float)cnt : 0.0f;
+        const float* own = s_obs + i * D;
+        for (int d = lane; d < D; d += 32) out[d] = valid ? own[d] : 0.0f;
+#pragma unroll
+        for (int u = 0; u < NU; ++u)
+            if (con[u]) out[D + lane + 32 * u] = acc[u] * inv;
+    }
+}
+
 __global__ void gather_rows_kernel(const float* __restrict__ src, size_t ld_src, const int64_t* __restrict__ idx,
                                    float* __restrict__ dst, size_t ld_dst, size_t rows, int width) {
     const int lane = threadIdx.x & 31;
@@ -272,6 +351,18 @@ int b2c_cc_obs_fuse(const float* obs, const float* actions, const uint8_t* flags
         return b2c_set_error(B2C_ERR_ARG, "b2c_cc_obs_fuse: missing neighbour columns");
     if (mode == 1 && obs_dim + (counterfactual ? act_dim : 0) > 256)
         return b2c_set_error(B2C_ERR_ARG, "b2c_cc_obs_fuse: mean-field rows of more than 256 columns are not supported");
+    const int W = obs_dim + (counterfactual ? act_dim : 0);
+    const size_t fuse_smem = (size_t)(((slots * obs_dim + 3) & ~3) + slots * act_dim) * sizeof(float);
+    if (mode == 1 && slots <= 64 && rows % (size_t)slots == 0 && fuse_smem <= 48 * 1024 && !getenv("B2C_FUSE_ROWWISE")) {
+        // one CTA per (t, scene); rows are (t, scene, slot) with the slot fastest, as every caller lays them out
+        const unsigned grid = (unsigned)(rows / (size_t)slots);
+        cudaStream_t st = (cudaStream_t)stream;
+#define B2C_MF(n) case n: cc_obs_fuse_mf_scene_kernel<n><<<grid, 128, fuse_smem, st>>>(obs, actions, flags, (const unsigned long long*)mf_mask, cobs, slots, obs_dim, act_dim, cobs_dim, counterfactual); break;
+        switch ((W + 31) / 32) { B2C_MF(1) B2C_MF(2) B2C_MF(3) B2C_MF(4) B2C_MF(5) B2C_MF(6) B2C_MF(7) B2C_MF(8) }
+#undef B2C_MF
+        B2C_CUDA(cudaGetLastError());
+        return B2C_OK;
+    }
     size_t blocks = (rows + 7) / 8;
     cc_obs_fuse_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(obs, actions, flags, (const unsigned long long*)mf_mask,
                                                                           nei_list, cobs, rows, slots, obs_dim, act_dim,

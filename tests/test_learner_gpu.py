@@ -209,7 +209,7 @@ def _cc_reference(obs, act, flags, nei_sorted, nei_dist, A, mode, mf_dist=10.0, 
 
 
 @pytest.mark.parametrize("mode", ["mf", "concat"])
-def test_cc_obs_fuse(mode):
+def test_cc_obs_fuse(mode, monkeypatch):
     from copo_b200 import ops
     rng = np.random.default_rng(2)
     T, S, A, D = 5, 7, 12, 23
@@ -234,6 +234,49 @@ def test_cc_obs_fuse(mode):
     got = ops.cc_obs_fuse(c(obs), c(act), c(flags), c(mf_mask.view(np.int64)), c(nei_list), A, mode, True)
     assert got.shape[1] == om.centralized_critic_obs_dim(D, 2, True, 4, mode)
     close(got, want, 1e-5, 1e-6)
+    if mode == "mf":
+        # the mean-field form has two kernels: one CTA per (t, scene) with the scene staged in shared memory (whenever the
+        # rows are whole scenes - the call above), and one warp per row (B2C_FUSE_ROWWISE, or a ragged row count)
+        monkeypatch.setenv("B2C_FUSE_ROWWISE", "1")
+        rowwise = ops.cc_obs_fuse(c(obs), c(act), c(flags), c(mf_mask.view(np.int64)), c(nei_list), A, mode, True)
+        monkeypatch.delenv("B2C_FUSE_ROWWISE")
+        assert torch.equal(rowwise, got)                             # same sums in the same order
+        ragged = ops.cc_obs_fuse(c(obs[:-A // 2]), c(act[:-A // 2]), c(flags[:-A // 2]), c(mf_mask.view(np.int64)[:-A // 2]),
+                                 None, A, mode, True)
+        assert torch.equal(ragged[:R - A], got[:R - A])
+
+
+def test_mean_field_fusion_at_the_c3_shape():
+    """40 slots x 91 observation columns + 2 action columns (three column slots per lane), every scene of a step: the
+    scene-wise kernel against the row-wise one, and the means against numpy on sampled rows."""
+    from copo_b200 import ops
+    S, A, D = 512, 40, 91
+    R = S * A
+    g = torch.Generator(device="cuda").manual_seed(4)
+    obs, act = torch.rand(R, D, device="cuda", generator=g), torch.randn(R, 2, device="cuda", generator=g)
+    flags = (torch.rand(R, device="cuda", generator=g) < 0.85).to(torch.uint8)
+    mf = torch.randint(0, 2 ** 40, (R,), device="cuda", dtype=torch.int64, generator=g) & \
+        torch.randint(0, 2 ** 40, (R,), device="cuda", dtype=torch.int64, generator=g) & \
+        torch.randint(0, 2 ** 40, (R,), device="cuda", dtype=torch.int64, generator=g)
+    mf &= ~(torch.ones(R, dtype=torch.int64, device="cuda") << (torch.arange(R, device="cuda") % A))      # not oneself
+    got = ops.cc_obs_fuse(obs, act, flags, mf, None, A, "mf", True)
+    os.environ["B2C_FUSE_ROWWISE"] = "1"
+    try:
+        rowwise = ops.cc_obs_fuse(obs, act, flags, mf, None, A, "mf", True)
+    finally:
+        del os.environ["B2C_FUSE_ROWWISE"]
+    assert got.shape == (R, 2 * D + 2) and torch.equal(got, rowwise)
+    o, a, f, m, out = obs.cpu().numpy(), act.cpu().numpy(), flags.cpu().numpy(), mf.cpu().numpy(), got.cpu().numpy()
+    for r in (0, 1, 39, 40, 777, R - 41, R - 1):
+        base = r - r % A
+        nb = [base + j for j in range(A) if (int(m[r]) >> j) & 1 and f[base + j] & 1]
+        want = np.zeros(2 * D + 2, np.float32)
+        if f[r] & 1:
+            want[:D] = o[r]
+            if nb:
+                want[D:2 * D] = o[nb].astype(np.float64).mean(0)
+                want[2 * D:] = a[nb].astype(np.float64).mean(0)
+        assert np.allclose(out[r], want, rtol=1e-5, atol=1e-6), r
 
 
 def _copo_batch(B, D, seed):
