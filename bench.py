@@ -336,8 +336,9 @@ def run_gpu(args):
 
     def critic_step(src, a, o):
         """CCPPO mean-field (C3): critic-obs fusion of this step's rows + the central value head on them"""
-        cobs = ops.cc_obs_fuse(src, a, o["flags"].view(-1), o["mf_mask"].view(-1), None, A, "mf", True)
-        return pol.model.central_value_function(cobs)
+        cobs, cobs_split = ops.cc_obs_fuse(src, a, o["flags"].view(-1), o["mf_mask"].view(-1), None, A, "mf", True,
+                                           want_split=True)
+        return pol.model.central_value_function(cobs, cobs_split)
 
     def rollout_step():
         """policy forward (one tcgen05 kernel; logits + Gaussian sample in its epilogue) -> fused scene

@@ -8,6 +8,7 @@
 //   gather_rows         minibatch assembly (rllib minibatches(): shuffled row subsets)
 //   adam_step, dot      torch.optim.Adam update (PPO lr 3e-4, LCF lr 1e-4) and <g_new, g_old> (algo_copo.py:274-278)
 // All HBM-bound: one pass over their inputs, coalesced along the slot/row dimension.
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -181,11 +182,12 @@ __global__ void cc_obs_fuse_kernel(const float* __restrict__ obs, const float* _
 // columns each (lane + 32 u < W = D + AD), so a neighbour costs NU shared loads and adds instead of eight predicated
 // global loads; the row leaves as [own | mean] through coalesced stores.  Same sums in the same (slot) order as
 // cc_obs_fuse_kernel, mode 1.  HBM traffic is the algorithmic 4 * (D + AD) in + 4 * (2 D + AD) out per row.
-template <int NU>
+template <int NU, bool SPLIT>
 __global__ void __launch_bounds__(128)
 cc_obs_fuse_mf_scene_kernel(const float* __restrict__ obs, const float* __restrict__ act,
                             const uint8_t* __restrict__ flags, const unsigned long long* __restrict__ mf_mask,
-                            float* __restrict__ cobs, int A, int D, int AD, int C, int counterfactual) {
+                            float* __restrict__ cobs, uint16_t* __restrict__ cobs_split, int kp, int A, int D, int AD,
+                            int C, int counterfactual) {
     extern __shared__ __align__(16) float s_fuse[];
     float* s_obs = s_fuse;                                       // [A][D]
     float* s_act = s_fuse + ((A * D + 3) & ~3);                  // [A][AD]
@@ -248,10 +250,22 @@ cc_obs_fuse_mf_scene_kernel(const float* __restrict__ obs, const float* __restri
         }
         const float inv = cnt > 0 ? 1.0f / (float)cnt : 0.0f;
         const float* own = s_obs + i * D;
-        for (int d = lane; d < D; d += 32) out[d] = valid ? own[d] : 0.0f;
+        // optionally the same row once more as the value network's tensor-core operand: bf16 [hi | lo], kp columns each,
+        // zero padded (tc::split_rows_kernel's bits) - the critic's first layer then needs no conversion pass over cobs
+        uint16_t* sp = SPLIT ? cobs_split + (row0 + i) * (size_t)(2 * kp) : nullptr;
+        auto emit = [&](int d, float x) {
+            out[d] = x;
+            if constexpr (SPLIT) {
+                const __nv_bfloat16 h = __float2bfloat16_rn(x);
+                sp[d] = __bfloat16_as_ushort(h);
+                sp[kp + d] = __bfloat16_as_ushort(__float2bfloat16_rn(x - __bfloat162float(h)));
+            }
+        };
+        for (int d = lane; d < D; d += 32) emit(d, valid ? own[d] : 0.0f);
 #pragma unroll
         for (int u = 0; u < NU; ++u)
-            if (con[u]) out[D + lane + 32 * u] = acc[u] * inv;
+            if (con[u]) emit(D + lane + 32 * u, acc[u] * inv);
+        if constexpr (SPLIT) for (int d = C + lane; d < kp; d += 32) { sp[d] = 0; sp[kp + d] = 0; }
     }
 }
 
@@ -341,6 +355,13 @@ int b2c_lcf_mix_apply(const uint8_t* flags, const float* adv, const float* nei_a
 int b2c_cc_obs_fuse(const float* obs, const float* actions, const uint8_t* flags, const uint64_t* mf_mask,
                     const int8_t* nei_list, float* cobs, size_t rows, int slots, int obs_dim, int act_dim, int cobs_dim,
                     int mode, int counterfactual, void* stream) {
+    return b2c_cc_obs_fuse_split(obs, actions, flags, mf_mask, nei_list, cobs, nullptr, 0, rows, slots, obs_dim, act_dim,
+                                 cobs_dim, mode, counterfactual, stream);
+}
+
+int b2c_cc_obs_fuse_split(const float* obs, const float* actions, const uint8_t* flags, const uint64_t* mf_mask,
+                          const int8_t* nei_list, float* cobs, uint16_t* cobs_split, int kp, size_t rows, int slots,
+                          int obs_dim, int act_dim, int cobs_dim, int mode, int counterfactual, void* stream) {
     if (rows == 0) return B2C_OK;
     if (!obs || !flags || !cobs || slots < 1 || mode < 0 || mode > 2)
         return b2c_set_error(B2C_ERR_ARG, "b2c_cc_obs_fuse: bad argument");
@@ -353,11 +374,16 @@ int b2c_cc_obs_fuse(const float* obs, const float* actions, const uint8_t* flags
         return b2c_set_error(B2C_ERR_ARG, "b2c_cc_obs_fuse: mean-field rows of more than 256 columns are not supported");
     const int W = obs_dim + (counterfactual ? act_dim : 0);
     const size_t fuse_smem = (size_t)(((slots * obs_dim + 3) & ~3) + slots * act_dim) * sizeof(float);
-    if (mode == 1 && slots <= 64 && rows % (size_t)slots == 0 && fuse_smem <= 48 * 1024 && !getenv("B2C_FUSE_ROWWISE")) {
+    const bool scene_wise = mode == 1 && slots <= 64 && rows % (size_t)slots == 0 && fuse_smem <= 48 * 1024 &&
+                            !getenv("B2C_FUSE_ROWWISE");
+    if (cobs_split && (!scene_wise || kp < cobs_dim || kp % 64))
+        return b2c_set_error(B2C_ERR_ARG, "b2c_cc_obs_fuse_split: the operand output needs the mean-field mode on whole scenes and kp = cobs_dim padded to 64");
+    if (scene_wise) {
         // one CTA per (t, scene); rows are (t, scene, slot) with the slot fastest, as every caller lays them out
         const unsigned grid = (unsigned)(rows / (size_t)slots);
         cudaStream_t st = (cudaStream_t)stream;
-#define B2C_MF(n) case n: cc_obs_fuse_mf_scene_kernel<n><<<grid, 128, fuse_smem, st>>>(obs, actions, flags, (const unsigned long long*)mf_mask, cobs, slots, obs_dim, act_dim, cobs_dim, counterfactual); break;
+#define B2C_MF(n) case n: if (cobs_split) cc_obs_fuse_mf_scene_kernel<n, true><<<grid, 128, fuse_smem, st>>>(obs, actions, flags, (const unsigned long long*)mf_mask, cobs, cobs_split, kp, slots, obs_dim, act_dim, cobs_dim, counterfactual); \
+        else cc_obs_fuse_mf_scene_kernel<n, false><<<grid, 128, fuse_smem, st>>>(obs, actions, flags, (const unsigned long long*)mf_mask, cobs, nullptr, 0, slots, obs_dim, act_dim, cobs_dim, counterfactual); break;
         switch ((W + 31) / 32) { B2C_MF(1) B2C_MF(2) B2C_MF(3) B2C_MF(4) B2C_MF(5) B2C_MF(6) B2C_MF(7) B2C_MF(8) }
 #undef B2C_MF
         B2C_CUDA(cudaGetLastError());

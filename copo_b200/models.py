@@ -229,8 +229,9 @@ class CCModel:
         raise ValueError("Centralized Value Function should not be called directly! "
                          "Call central_value_function(cobs) instead!")
 
-    def central_value_function(self, cobs):
-        return self.nets["value"].forward(cobs, self._tc()).reshape(-1)
+    def central_value_function(self, cobs, cobs_split=None):
+        """cobs_split: the rows as the [hi | lo] operand (ops.cc_obs_fuse(..., want_split=True)); skips the split pass."""
+        return self.nets["value"].forward(cobs, self._tc(), cobs_split).reshape(-1)
 
     def zero_grad(self):
         self.grad.zero_()
@@ -300,11 +301,11 @@ class CoPOModel(CCModel):
         self.nets["nei"] = _Net(self.NEI, self.cobs_dim, hiddens, 1)
         self.nets["global"] = _Net(self.GLOBAL, self.cobs_dim, hiddens, 1)
 
-    def get_nei_value(self, cobs):
-        return self.nets["nei"].forward(cobs, self._tc()).reshape(-1)
+    def get_nei_value(self, cobs, cobs_split=None):
+        return self.nets["nei"].forward(cobs, self._tc(), cobs_split).reshape(-1)
 
-    def get_global_value(self, cobs):
-        return self.nets["global"].forward(cobs, self._tc()).reshape(-1)
+    def get_global_value(self, cobs, cobs_split=None):
+        return self.nets["global"].forward(cobs, self._tc(), cobs_split).reshape(-1)
 
     @property
     def lcf_mean(self):

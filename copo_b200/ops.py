@@ -211,8 +211,10 @@ def stats_to_mean_std(sum_, sumsq, n):
     return mean, var ** 0.5
 
 
-def cc_obs_fuse(obs, actions, flags, mf_mask, nei_list, slots, mode, counterfactual=True):
-    """obs [R, D] with R ordered [t][scene][slot]; mode 'none' | 'mf' | 'concat'."""
+def cc_obs_fuse(obs, actions, flags, mf_mask, nei_list, slots, mode, counterfactual=True, want_split=False):
+    """obs [R, D] with R ordered [t][scene][slot]; mode 'none' | 'mf' | 'concat'.  want_split (mean-field mode on whole
+    scenes): also returns the rows as the value network's [hi | lo] tensor-core operand (what tc_split_rows(cobs) would
+    give) -> (cobs, cobs_split)."""
     lib = _lib_ready()
     R, D = obs.shape
     AD = actions.shape[1] if actions is not None else 2
@@ -220,6 +222,14 @@ def cc_obs_fuse(obs, actions, flags, mf_mask, nei_list, slots, mode, counterfact
     n_other = (0, 1, 4)[m]
     C = D + n_other * (D + (AD if counterfactual else 0))
     cobs = torch.empty((R, C), dtype=torch.float32, device=obs.device)
+    if want_split:
+        assert m == 1 and R % slots == 0 and slots <= 64
+        kp = tc_padded_k(C)
+        split = torch.empty((R, 2 * kp), dtype=torch.bfloat16, device=obs.device)
+        _lib.check(lib.b2c_cc_obs_fuse_split(P(obs), P(actions), P(flags), P(mf_mask), P(nei_list), P(cobs), P(split), c_int(kp),
+                                             c_size_t(R), c_int(slots), c_int(D), c_int(AD), c_int(C), c_int(m),
+                                             c_int(int(counterfactual)), _lib.stream_ptr()))
+        return cobs, split
     _lib.check(lib.b2c_cc_obs_fuse(P(obs), P(actions), P(flags), P(mf_mask), P(nei_list), P(cobs), c_size_t(R), c_int(slots),
                                    c_int(D), c_int(AD), c_int(C), c_int(m), c_int(int(counterfactual)), _lib.stream_ptr()))
     return cobs

@@ -325,6 +325,10 @@ class IPPOPolicy:
     def _critic_obs(self, ro):
         return ro[OBS].reshape(-1, ro[OBS].shape[-1])
 
+    def _critic_obs_operand(self, ro):
+        """(critic observations, the same rows as the value network's tensor-core operand or None)."""
+        return self._critic_obs(ro), None
+
     def _bootstrap_values(self, ro):
         """Stock rllib PPO postprocessing (IPPOPolicy overrides only `loss`, algo_ippo.py:78-79): a trajectory the
         fragment end cuts bootstraps with the value of its NEXT observation."""
@@ -335,9 +339,9 @@ class IPPOPolicy:
         """ro: dict of [T, N, ...] rollout columns (obs, actions, rewards, flags, ...; `next_obs` [N, D] = the
         observation after the last row).  Adds vf_preds, advantages, value_targets (GAE)."""
         T, N = ro["flags"].shape
-        cobs = self._critic_obs(ro)
+        cobs, cobs_split = self._critic_obs_operand(ro)
         ro[CENTRALIZED_CRITIC_OBS] = cobs.reshape(T, N, -1)
-        ro[VF_PREDS] = self.model.central_value_function(cobs).reshape(T, N)
+        ro[VF_PREDS] = self.model.central_value_function(cobs, cobs_split).reshape(T, N)
         adv, tgt = ops.gae3(ro["flags"], [ro[REWARDS]], [ro[VF_PREDS]], self.config["gamma"], self.config["lambda_"],
                             bootstrap=self._bootstrap_values(ro))
         ro[ADVANTAGES], ro[VALUE_TARGETS] = adv[0], tgt[0]
@@ -429,6 +433,16 @@ class CCPPOPolicy(IPPOPolicy):
                                ro["mf_mask"].reshape(-1) if mode == "mf" else None,
                                ro["nei_list"].reshape(T * N, 4) if mode == "concat" else None, ro["slots"], mode,
                                self.config["counterfactual"])
+
+    def _critic_obs_operand(self, ro):
+        """Mean-field fusion on the tensor-core path: the fusion kernel also emits the rows as the value network's
+        [hi | lo] operand (no conversion pass over the fused observations)."""
+        T, N, D = ro[OBS].shape
+        if self.config["fuse_mode"] != "mf" or self.model._tc() is None or N % int(ro["slots"]) or int(ro["slots"]) > 64:
+            return self._critic_obs(ro), None
+        return ops.cc_obs_fuse(ro[OBS].reshape(T * N, D), ro[ACTIONS].reshape(T * N, -1), ro["flags"].reshape(-1),
+                               ro["mf_mask"].reshape(-1), None, ro["slots"], "mf", self.config["counterfactual"],
+                               want_split=True)
 
     def _trajectory_critic_obs(self, sb, obs, other_agent_batches, episode):
         """The centralized critic observation of one trajectory (algo_ccppo.py:225-311, 328-355): own observation, then
@@ -547,11 +561,13 @@ class CoPOPolicy(CCPPOPolicy):
 
     def postprocess_rollout(self, ro):
         T, N = ro["flags"].shape
-        cobs = self._critic_obs(ro)
+        cobs, sp = self._critic_obs_operand(ro)
+        if sp is None and self.model._tc() is not None:
+            sp = ops.tc_split_rows(cobs)                 # one [hi | lo] operand for the three value networks
         ro[CENTRALIZED_CRITIC_OBS] = cobs.reshape(T, N, -1)
-        ro[VF_PREDS] = self.model.central_value_function(cobs).reshape(T, N)
-        ro[NEI_VALUES] = self.model.get_nei_value(cobs).reshape(T, N)
-        ro[GLOBAL_VALUES] = self.model.get_global_value(cobs).reshape(T, N)
+        ro[VF_PREDS] = self.model.central_value_function(cobs, sp).reshape(T, N)
+        ro[NEI_VALUES] = self.model.get_nei_value(cobs, sp).reshape(T, N)
+        ro[GLOBAL_VALUES] = self.model.get_global_value(cobs, sp).reshape(T, N)
         per_scene = ro["slots"] if ro[GLOBAL_REWARDS].shape[1] != N else 0
         adv, tgt = ops.gae3(ro["flags"], [ro[REWARDS], ro[NEI_REWARDS], ro[GLOBAL_REWARDS]],
                             [ro[VF_PREDS], ro[NEI_VALUES], ro[GLOBAL_VALUES]], self.config["gamma"],

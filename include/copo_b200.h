@@ -211,6 +211,13 @@ int b2c_lcf_mix_apply(const uint8_t* flags, const float* adv, const float* nei_a
 int b2c_cc_obs_fuse(const float* obs, const float* actions, const uint8_t* flags, const uint64_t* mf_mask,
                     const int8_t* nei_list, float* cobs, size_t rows, int slots, int obs_dim, int act_dim, int cobs_dim,
                     int mode, int counterfactual, void* stream);
+/* The same with a second output for the mean-field mode on whole scenes (rows a multiple of slots): cobs_split [rows][2*kp]
+ * bf16 = the row once more as the [hi | lo] tensor-core operand of the central value network's first layer (kp = cobs_dim
+ * padded to 64; the bits b2c_tc_split_rows would produce from cobs), so that CCPPOPolicy.postprocess_trajectory's value
+ * predictions (algo_ccppo.py:357-371) need no conversion pass over the fused observations.  NULL: as b2c_cc_obs_fuse. */
+int b2c_cc_obs_fuse_split(const float* obs, const float* actions, const uint8_t* flags, const uint64_t* mf_mask,
+                          const int8_t* nei_list, float* cobs, uint16_t* cobs_split, int kp, size_t rows, int slots,
+                          int obs_dim, int act_dim, int cobs_dim, int mode, int counterfactual, void* stream);
 /* dst[r][0..width) = src[idx[r]][0..width): minibatch assembly from a shuffled index list */
 int b2c_gather_rows(const float* src, size_t ld_src, const int64_t* idx, float* dst, size_t ld_dst, size_t rows, int width,
                     void* stream);

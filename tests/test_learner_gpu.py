@@ -266,6 +266,10 @@ def test_mean_field_fusion_at_the_c3_shape():
     finally:
         del os.environ["B2C_FUSE_ROWWISE"]
     assert got.shape == (R, 2 * D + 2) and torch.equal(got, rowwise)
+    # the operand output: the bits tc_split_rows makes of the fused rows (zero padding included)
+    got2, split = ops.cc_obs_fuse(obs, act, flags, mf, None, A, "mf", True, want_split=True)
+    assert torch.equal(got2, got) and split.shape == (R, 2 * ops.tc_padded_k(2 * D + 2))
+    assert torch.equal(split.view(torch.int16), ops.tc_split_rows(got).view(torch.int16))
     o, a, f, m, out = obs.cpu().numpy(), act.cpu().numpy(), flags.cpu().numpy(), mf.cpu().numpy(), got.cpu().numpy()
     for r in (0, 1, 39, 40, 777, R - 41, R - 1):
         base = r - r % A
