@@ -226,9 +226,10 @@ __global__ void ppo_head_kernel(const PpoHeadArgs a) {
 // with phi = (mean + std * eps) * pi/2
 __global__ void lcf_meta_terms_kernel(const float* __restrict__ adv, const float* __restrict__ nei,
                                       const float* __restrict__ eps, int M, float mean, float std,
-                                      const float* __restrict__ params, double* __restrict__ out) {
+                                      const float* __restrict__ params, double* __restrict__ out,
+                                      const float* __restrict__ gadv = nullptr) {
     int m = blockIdx.x * blockDim.x + threadIdx.x;
-    double c = 0, d = 0, de = 0;
+    double c = 0, d = 0, de = 0, ga = 0;
     if (params) {
         // CoPOModel.lcf_mean / lcf_std from the raw parameters (algo_copo.py:171-177)
         mean = fminf(fmaxf(tanhf(params[0]), -1.0f + 1e-6f), 1.0f - 1e-6f);
@@ -243,9 +244,56 @@ __global__ void lcf_meta_terms_kernel(const float* __restrict__ adv, const float
         c = cs * a + sn * n;
         float dd = (-sn * a + cs * n) * 1.57079632679489661923f;
         d = dd; de = dd * e;
+        if (gadv) ga = gadv[m];
     }
     c = warp_sum_d(c); d = warp_sum_d(d); de = warp_sum_d(de);
-    if ((threadIdx.x & 31) == 0) { atomicAdd(&out[0], c); atomicAdd(&out[1], d); atomicAdd(&out[2], de); }
+    if (gadv) ga = warp_sum_d(ga);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&out[0], c); atomicAdd(&out[1], d); atomicAdd(&out[2], de);
+        if (gadv) atomicAdd(&out[3], ga);                        // sum of the global advantage (a logged statistic)
+    }
+}
+
+// Everything CoPOPolicy.meta_update does after the two policy gradients and their dot product (algo_copo.py:264-309), in
+// one thread: the LCF advantage loss, d(loss)/d(lcf_parameters) through lcf_mean = clamp(tanh(p0)) and
+// lcf_std = exp(clamp(p1)) (algo_copo.py:171-177), the Adam step on the two parameters and the 13 logged statistics.
+// Float widths follow the torch expression it replaces: sums and losses in double, the parameters, their derivatives
+// and Adam in float.
+struct LcfFinishArgs {
+    const double* grad_value; const double* st_new; const double* st_old; const double* sums;
+    double rows, raw_mean, raw_std;
+    float* params; float* m; float* v; float* grad; double* stats;
+    float step_size, inv_sqrt_bc2, beta1, beta2, eps;
+};
+__global__ void lcf_meta_finish_kernel(const LcfFinishArgs a) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double gv = a.grad_value[0];
+    const double coordinated = a.sums[0] / a.rows, t1 = a.sums[1] / a.rows, t2 = a.sums[2] / a.rows;
+    const double adv_loss = (coordinated - a.raw_mean) / a.raw_std;
+    const float p0 = a.params[0], p1 = a.params[1];
+    const float th = tanhf(p0);
+    const float dmean = (fabsf(th) < (float)(1.0 - 1e-6)) ? 1.0f - th * th : 0.0f;
+    const float std_t = expf(fminf(fmaxf(p1, -20.0f), 2.0f));
+    const float dstd = (p1 > -20.0f && p1 < 2.0f) ? std_t : 0.0f;
+    const double dl0 = t1 * (double)dmean / a.raw_std, dl1 = t2 * (double)dstd / a.raw_std;
+    const float g[2] = {(float)(gv * dl0), (float)(gv * dl1)};
+    float pn[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {                                // adam_kernel's arithmetic
+        a.grad[k] = g[k];
+        const float mi = a.beta1 * a.m[k] + (1.0f - a.beta1) * g[k];
+        const float vi = a.beta2 * a.v[k] + (1.0f - a.beta2) * g[k] * g[k];
+        a.m[k] = mi; a.v[k] = vi;
+        const float denom = sqrtf(vi) * a.inv_sqrt_bc2 + a.eps;
+        pn[k] = a.params[k] - a.step_size * (mi / denom);
+        a.params[k] = pn[k];
+    }
+    const float lm = fminf(fmaxf(tanhf(pn[0]), -1.0f + 1e-6f), 1.0f - 1e-6f);
+    const float ls = expf(fminf(fmaxf(pn[1], -20.0f), 2.0f));
+    double* o = a.stats;
+    o[0] = a.st_new[0] / a.rows;  o[1] = a.st_old[6] / a.rows;  o[2] = adv_loss;  o[3] = gv * adv_loss;  o[4] = gv;
+    o[5] = lm;  o[6] = (double)(lm * 90.0f);  o[7] = pn[0];  o[8] = coordinated;  o[9] = a.sums[3] / a.rows;
+    o[10] = ls;  o[11] = (double)(ls * 90.0f);  o[12] = pn[1];
 }
 
 }  // namespace b2c
@@ -340,6 +388,33 @@ int b2c_lcf_meta_terms(const float* adv, const float* nei_adv, const float* eps,
     if (!adv || !nei_adv || !eps || !out3) return b2c_set_error(B2C_ERR_ARG, "b2c_lcf_meta_terms: null argument");
     lcf_meta_terms_kernel<<<(rows + 255) / 256, 256, 0, (cudaStream_t)stream>>>(adv, nei_adv, eps, rows, lcf_mean, lcf_std,
                                                                                nullptr, out3);
+    B2C_CUDA(cudaGetLastError());
+    return B2C_OK;
+}
+
+int b2c_lcf_meta_sums(const float* adv, const float* nei_adv, const float* eps, const float* global_adv, int rows,
+                      const float* lcf_parameters, double* out4, void* stream) {
+    if (rows == 0) return B2C_OK;
+    if (!adv || !nei_adv || !eps || !global_adv || !out4 || !lcf_parameters)
+        return b2c_set_error(B2C_ERR_ARG, "b2c_lcf_meta_sums: null argument");
+    lcf_meta_terms_kernel<<<(rows + 255) / 256, 256, 0, (cudaStream_t)stream>>>(adv, nei_adv, eps, rows, 0.0f, 1.0f,
+                                                                               lcf_parameters, out4, global_adv);
+    B2C_CUDA(cudaGetLastError());
+    return B2C_OK;
+}
+
+int b2c_lcf_meta_finish(const b2c_lcf_meta_finish_args* p, void* stream) {
+    if (!p || !p->grad_value || !p->st_new || !p->st_old || !p->sums || !p->lcf_parameters || !p->exp_avg || !p->exp_avg_sq ||
+        !p->lcf_grad || !p->stats || p->step < 1 || !(p->rows > 0.0) || !(p->raw_std > 0.0))
+        return b2c_set_error(B2C_ERR_ARG, "b2c_lcf_meta_finish: bad argument");
+    LcfFinishArgs a;
+    a.grad_value = p->grad_value; a.st_new = p->st_new; a.st_old = p->st_old; a.sums = p->sums;
+    a.rows = p->rows; a.raw_mean = p->raw_mean; a.raw_std = p->raw_std;
+    a.params = p->lcf_parameters; a.m = p->exp_avg; a.v = p->exp_avg_sq; a.grad = p->lcf_grad; a.stats = p->stats;
+    const double bc1 = 1.0 - pow((double)p->beta1, p->step), bc2 = 1.0 - pow((double)p->beta2, p->step);
+    a.step_size = (float)(p->lr / bc1); a.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+    a.beta1 = p->beta1; a.beta2 = p->beta2; a.eps = p->eps;
+    lcf_meta_finish_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(a);
     B2C_CUDA(cudaGetLastError());
     return B2C_OK;
 }

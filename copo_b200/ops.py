@@ -7,7 +7,7 @@ import torch
 
 from . import _lib
 
-c_int, c_float, c_size_t, c_u32 = ctypes.c_int, ctypes.c_float, ctypes.c_size_t, ctypes.c_uint32
+c_int, c_float, c_size_t, c_u32, c_void_p = ctypes.c_int, ctypes.c_float, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_void_p
 P = _lib.ptr
 
 
@@ -157,6 +157,42 @@ def lcf_meta_terms(adv, nei_adv, eps, lcf_mean=None, lcf_std=None, lcf_parameter
         _lib.check(lib.b2c_lcf_meta_terms(P(_f32(adv)), P(_f32(nei_adv)), P(_f32(eps)), c_int(adv.numel()),
                                           c_float(lcf_mean), c_float(lcf_std), P(out), _lib.stream_ptr()))
     return out
+
+
+class LcfMetaFinishArgs(ctypes.Structure):              # b2c_lcf_meta_finish_args
+    _fields_ = [("grad_value", c_void_p), ("st_new", c_void_p), ("st_old", c_void_p), ("sums", c_void_p),
+                ("rows", ctypes.c_double), ("raw_mean", ctypes.c_double), ("raw_std", ctypes.c_double),
+                ("lcf_parameters", c_void_p), ("exp_avg", c_void_p), ("exp_avg_sq", c_void_p), ("lcf_grad", c_void_p),
+                ("stats", c_void_p), ("lr", c_float), ("beta1", c_float), ("beta2", c_float), ("eps", c_float),
+                ("step", ctypes.c_int32)]
+
+
+def lcf_meta_sums(adv, nei_adv, eps, global_adv, lcf_parameters, out4):
+    """out4 (float64, zeroed by the caller) += sums of: coordinated advantage, d, d * eps (lcf_meta_terms) and the global
+    advantage - one pass over the minibatch's columns."""
+    lib = _lib_ready()
+    _lib.check(lib.b2c_lcf_meta_sums(P(_f32(adv)), P(_f32(nei_adv)), P(_f32(eps)), P(_f32(global_adv)), c_int(adv.numel()),
+                                     P(_f32(lcf_parameters)), P(out4), _lib.stream_ptr()))
+    return out4
+
+
+def lcf_meta_finish(grad_value, st_new, st_old, sums, rows, raw_mean, raw_std, lcf_parameters, exp_avg, exp_avg_sq,
+                    lcf_grad, stats, lr, step, beta1=0.9, beta2=0.999, eps=1e-8):
+    """The tail of CoPOPolicy.meta_update in one launch (b2c_lcf_meta_finish): LCF loss and gradient, Adam step on
+    lcf_parameters, the 13 logged statistics into `stats` (float64)."""
+    lib = _lib_ready()
+    a = LcfMetaFinishArgs()
+    for name, t, dt, n in (("grad_value", grad_value, torch.float64, 1), ("st_new", st_new, torch.float64, 8),
+                           ("st_old", st_old, torch.float64, 8), ("sums", sums, torch.float64, 4),
+                           ("lcf_parameters", lcf_parameters, torch.float32, 2), ("exp_avg", exp_avg, torch.float32, 2),
+                           ("exp_avg_sq", exp_avg_sq, torch.float32, 2), ("lcf_grad", lcf_grad, torch.float32, 2),
+                           ("stats", stats, torch.float64, 13)):
+        assert t.dtype == dt and t.numel() >= n and t.is_contiguous(), name
+        setattr(a, name, t.data_ptr())
+    a.rows, a.raw_mean, a.raw_std = float(rows), float(raw_mean), float(raw_std)
+    a.lr, a.beta1, a.beta2, a.eps, a.step = lr, beta1, beta2, eps, int(step)
+    _lib.check(lib.b2c_lcf_meta_finish(ctypes.byref(a), _lib.stream_ptr()))
+    return stats
 
 
 # ---- rollout bookkeeping ------------------------------------------------------------------------------------------

@@ -591,13 +591,15 @@ class CoPOPolicy(CCPPOPolicy):
         return ro
 
     # ---- meta-gradient (a18) -------------------------------------------------------------------------------
-    def _policy_grad(self, model, batch, mode, adv, rows, out, x_split=None):
-        """Gradient of the policy network only, into `out` (this rank's share of the global-minibatch mean)."""
+    def _policy_grad(self, model, batch, mode, adv, rows, out, x_split=None, st=None):
+        """Gradient of the policy network only, into `out` (this rank's share of the global-minibatch mean).  st: zeroed
+        float64 [8] the loss kernel accumulates its statistics in."""
         cfg = dict(clip_param=self.config["clip_param"], vf_clip_param=0.0, vf_loss_coeff=0.0, entropy_coeff=0.0,
                    kl_coeff=0.0)
         pol = model.nets["policy"]
         model.grad[model.policy_slice()].zero_()
-        st = torch.zeros(8, dtype=torch.float64, device=self.device)
+        if st is None:
+            st = torch.zeros(8, dtype=torch.float64, device=self.device)
         if batch[OBS].shape[0] > 0:
             acts = pol.forward_train(batch[OBS], model._tc(), x_split)
             dlogits, _, st = ops.ppo_head(acts[3], batch[ACTIONS], batch[ACTION_LOGP], None, adv, [], cfg, mode=mode,
@@ -606,55 +608,57 @@ class CoPOPolicy(CCPPOPolicy):
         out.copy_(model.grad[model.policy_slice()])
         return st
 
-    def _meta_grads(self, batch, rows, g_new, g_old):
+    def _meta_grads(self, batch, rows, g_new, g_old, st_new=None, st_old=None):
         """Both policy-gradient vectors of the meta step (algo_copo.py:236-262): the surrogate of the CURRENT policy on
         the global advantage, the log-probability gradient of the OLD policy.  Device work only."""
         sp = None                                        # both networks read the same [hi | lo] operand of the observations
         if self.model._tc() is not None and batch[OBS].shape[0] > 0:
             d = self.model.nets["policy"].in_dim
             sp = ops.tc_split_rows(batch[OBS], ones_col=ops.tc_has_ones_col(d) and d <= 256)
-        st_new = self._policy_grad(self.model, batch, 0, batch[GLOBAL_ADVANTAGES], rows, g_new, sp)
-        st_old = self._policy_grad(self.target_model, batch, 1, None, rows, g_old, sp)
+        st_new = self._policy_grad(self.model, batch, 0, batch[GLOBAL_ADVANTAGES], rows, g_new, sp, st_new)
+        st_old = self._policy_grad(self.target_model, batch, 1, None, rows, g_old, sp, st_old)
         return st_new, st_old
 
+    META_KEYS = ("new_policy_ego_loss", "old_policy_logp_loss", "lcf_lcf_adv_loss", "lcf_final_loss", "grad_value", "lcf",
+                 "lcf_deg", "lcf_param", "coordinated_adv", "global_adv", "lcf_std", "lcf_std_deg", "lcf_std_param")
+
     def meta_update(self, train_batch, eps=None, global_rows=None):
+        """algo_copo.py:228-309.  Device work: two policy gradients (new policy on the global advantage, old policy's
+        log-probability), their dot product, one pass over the advantage columns for the LCF sums, and ONE kernel for
+        everything after that (LCF loss and gradient, Adam on lcf_parameters, the logged statistics) - no host read
+        unless `sync_stats`."""
         B = train_batch[OBS].shape[0]
         rows = self._global_rows(B, global_rows)
         n = self.model.policy_slice().stop - self.model.policy_slice().start
         if getattr(self, "_meta_g", None) is None:
             self._meta_g = torch.empty(2 * n, dtype=torch.float32, device=self.device)
+            # [0:8] statistics of the new policy's loss, [8:16] of the old policy's, [16:20] LCF sums, [20] the dot product
+            self._meta_buf = torch.zeros(21, dtype=torch.float64, device=self.device)
         g_new, g_old = self._meta_g[:n], self._meta_g[n:]
-        st_new, st_old = self._meta_grads(train_batch, rows, g_new, g_old)
+        buf = self._meta_buf
+        buf.zero_()
+        st_new, st_old, sums, grad_value = buf[0:8], buf[8:16], buf[16:20], buf[20:21]
+        self._meta_grads(train_batch, rows, g_new, g_old, st_new, st_old)
         # reduce BOTH gradient vectors (one all-reduce) BEFORE the dot product: it is bilinear
         parallel.allreduce_sum_(self._meta_g, self.dist, self.ar_timer)
-        grad_value = ops.dot(g_new, g_old)[0]
         if eps is None:
             eps = torch.randn(B, dtype=torch.float32, device=self.device)
-        std_t = self.model.lcf_std
-        terms = ops.lcf_meta_terms(train_batch[ADVANTAGES], train_batch[NEI_ADVANTAGE], eps,
-                                   lcf_parameters=self.model.lcf_parameters)
-        # ranks can hold minibatches of different sizes: reduce the sums together with the row count
-        terms = self._allreduce_stats(torch.cat([terms, st_new[:1], st_old[6:7]])) / rows
-        coordinated_mean = terms[0]
-        lcf_adv_loss = (coordinated_mean - self._raw_lcf_adv_mean) / self._raw_lcf_adv_std
-        p = self.model.lcf_parameters
-        th = torch.tanh(p[0])
-        dmean = torch.where(th.abs() < 1 - 1e-6, 1 - th * th, torch.zeros_like(th))
-        dstd = torch.where((p[1] > -20) & (p[1] < 2), std_t, torch.zeros_like(std_t))
-        dl = torch.stack([terms[1] * dmean, terms[2] * dstd]) / self._raw_lcf_adv_std
-        self.model.lcf_grad.copy_((grad_value * dl).to(torch.float32))
-        final = grad_value * lcf_adv_loss
-        self._lcf_optimizer.apply(self.model.lcf_grad)
-        lm, ls, lp = self.model.lcf_mean, self.model.lcf_std, self.model.lcf_parameters
-        ga = train_batch[GLOBAL_ADVANTAGES].mean() if B > 0 else torch.zeros((), device=self.device)
-        keys = ("new_policy_ego_loss", "old_policy_logp_loss", "lcf_lcf_adv_loss", "lcf_final_loss", "grad_value", "lcf",
-                "lcf_deg", "lcf_param", "coordinated_adv", "global_adv", "lcf_std", "lcf_std_deg", "lcf_std_param")
-        vec = torch.stack([t.to(torch.float64) for t in (terms[3], terms[4], lcf_adv_loss, final, grad_value, lm, lm * 90,
-                                                         lp[0], coordinated_mean, ga, ls, ls * 90, lp[1])])
-        self.meta_stats_keys, self.meta_stats_vector = keys, vec          # device copy (no host sync) for the trainer
+        if B > 0:
+            ops.lcf_meta_sums(train_batch[ADVANTAGES], train_batch[NEI_ADVANTAGE], eps, train_batch[GLOBAL_ADVANTAGES],
+                              self.model.lcf_parameters, sums)
+        # ranks can hold minibatches of different sizes: the sums are reduced, the means taken over the global row count
+        if parallel.active(self.dist):
+            self._allreduce_stats(buf[:20])
+        ops.dot(g_new, g_old, out=grad_value)            # after the reduction above: identical on every rank already
+        opt = self._lcf_optimizer
+        opt.step += 1
+        vec = torch.empty(13, dtype=torch.float64, device=self.device)
+        ops.lcf_meta_finish(grad_value, st_new, st_old, sums, rows, self._raw_lcf_adv_mean, self._raw_lcf_adv_std,
+                            self.model.lcf_parameters, opt.m, opt.v, self.model.lcf_grad, vec, opt.lr, opt.step)
+        self.meta_stats_keys, self.meta_stats_vector = self.META_KEYS, vec   # device copy (no host sync) for the trainer
         if not self.sync_stats:
             return {}
-        return dict(zip(keys, vec.tolist()))                              # one device -> host read
+        return dict(zip(self.META_KEYS, vec.tolist()))                    # one device -> host read
 
     sync_stats = True      # False: meta_update leaves its statistics on the device (meta_stats_vector) and returns {}
 

@@ -177,6 +177,33 @@ int b2c_lcf_meta_terms(const float* adv, const float* nei_adv, const float* eps,
 int b2c_lcf_meta_terms_params(const float* adv, const float* nei_adv, const float* eps, int rows,
                               const float* lcf_parameters, double* out3, void* stream);
 
+/* The same sums plus out4[3] += sum(global_adv) (the `global_adv` statistic meta_update logs, algo_copo.py:304). */
+int b2c_lcf_meta_sums(const float* adv, const float* nei_adv, const float* eps, const float* global_adv, int rows,
+                      const float* lcf_parameters, double* out4, void* stream);
+/* Everything CoPOPolicy.meta_update does after the two policy gradients, their dot product and the sums above
+ * (algo_copo.py:264-309), in one launch: lcf_adv_loss = (mean coordinated adv - raw_mean) / raw_std, the gradient of
+ * grad_value * lcf_adv_loss w.r.t. lcf_parameters through lcf_mean = clamp(tanh(p0)) and lcf_std = exp(clamp(p1))
+ * (algo_copo.py:171-177; zero outside the clamps), torch.optim.Adam's step on the two parameters, and the 13 logged
+ * statistics in the order of meta_update's return dict (new_policy_ego_loss, old_policy_logp_loss, lcf_lcf_adv_loss,
+ * lcf_final_loss, grad_value, lcf, lcf_deg, lcf_param, coordinated_adv, global_adv, lcf_std, lcf_std_deg, lcf_std_param).
+ * st_new / st_old: the 8 statistics b2c_ppo_head accumulated for the new policy (mode 0) / the old one (mode 1); sums:
+ * b2c_lcf_meta_sums' out4; all of them over the GLOBAL minibatch of `rows` rows (all-reduce them first). */
+typedef struct {
+    const double* grad_value;     /* [1] <g_new, g_old> */
+    const double* st_new;         /* [8] */
+    const double* st_old;         /* [8] */
+    const double* sums;           /* [4] */
+    double rows, raw_mean, raw_std;
+    float* lcf_parameters;        /* [2] in / out */
+    float* exp_avg;               /* [2] Adam state */
+    float* exp_avg_sq;            /* [2] */
+    float* lcf_grad;              /* [2] out */
+    double* stats;                /* [13] out */
+    float lr, beta1, beta2, eps;
+    int32_t step;                 /* Adam step count of this update (1-based) */
+} b2c_lcf_meta_finish_args;
+int b2c_lcf_meta_finish(const b2c_lcf_meta_finish_args* args, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------
  * Rollout bookkeeping over time-major [T][N] columns (N = scenes x slots); flags are the B2C_FLAG_* bytes the
  * env wrote for the step in which the row's action was applied.

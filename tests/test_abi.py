@@ -69,13 +69,15 @@ def test_ctypes_structs_match_the_header(tmp_path):
     import subprocess
     from copo_b200 import _lib, ops
     pairs = {"b2c_env_config": _lib.EnvConfig, "b2c_env_io": _lib.EnvIO, "b2c_ppo_head_args": ops.PpoHeadArgs,
-             "b2c_gae_args": ops.GaeArgs, "b2c_tc_head": ops.TcHead}
+             "b2c_gae_args": ops.GaeArgs, "b2c_tc_head": ops.TcHead, "b2c_lcf_meta_finish_args": ops.LcfMetaFinishArgs}
     fields = {"b2c_env_config": ["num_scenes", "seed", "neighbours_distance", "force_lcf"],
               "b2c_env_io": ["obs", "scene_done", "obs_split"],
               "b2c_ppo_head_args": ["logits", "v_cur", "dlogits", "dv", "stats", "rows", "mode", "clip_param", "kl_coeff"],
               "b2c_gae_args": ["flags", "rewards", "targets", "T", "global_reward_per_scene", "gamma", "lambda_",
                                "bootstrap"],
-              "b2c_tc_head": ["weight", "out", "n", "actions", "logp", "seed", "step"]}
+              "b2c_tc_head": ["weight", "out", "n", "actions", "logp", "seed", "step"],
+              "b2c_lcf_meta_finish_args": ["grad_value", "sums", "rows", "raw_std", "lcf_parameters", "lcf_grad", "stats", "lr",
+                                           "eps", "step"]}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "copo_b200.h"', 'int main(void) {']
     for s, fs in fields.items():
         lines.append('printf("%s size %%zu\\n", sizeof(%s));' % (s, s))

@@ -435,6 +435,28 @@ def test_meta_update_matches_oracle(precision):
     pol.assign_lcf(pol.model.lcf_parameters.clone(), float(pol.model.lcf_mean), float(pol.model.lcf_std))
 
 
+def test_meta_update_outside_the_lcf_clamps():
+    """lcf_mean = clamp(tanh(p0)) and lcf_std = exp(clamp(p1, -20, 2)) (algo_copo.py:171-177) have zero derivative outside
+    their clamps: with p = (10, 3) the meta step's LCF gradient is exactly zero, Adam leaves the parameters where they
+    are, and the logged LCF is the clamped one."""
+    import math
+    from copo_b200 import policy as P
+    D, B = 92, 600
+    pol = P.CoPOPolicy(D, 2, P.copo_config())
+    pol.model.flat.add_(0.01 * torch.randn_like(pol.model.flat))
+    pol.model.mark_weights_changed()
+    pol.model.lcf_parameters.copy_(torch.tensor([10.0, 3.0]))
+    pol._raw_lcf_adv_mean, pol._raw_lcf_adv_std = 0.0, 1.0
+    batch = {k: v.cuda() for k, v in _copo_batch(B, D, 6).items()}
+    out = pol.meta_update(batch, eps=torch.randn(B, generator=torch.Generator().manual_seed(1)).cuda())
+    assert torch.equal(pol.model.lcf_grad.cpu(), torch.zeros(2))
+    assert torch.equal(pol.model.lcf_parameters.cpu(), torch.tensor([10.0, 3.0]))
+    assert abs(out["lcf"] - (1 - 1e-6)) < 1e-7 and abs(out["lcf_std"] - math.exp(2.0)) < 1e-5
+    assert out["lcf_param"] == 10.0 and out["lcf_std_param"] == 3.0 and abs(out["lcf_deg"] - 90.0) < 1e-3
+    assert math.isfinite(out["grad_value"]) and out["grad_value"] != 0.0
+    assert abs(out["global_adv"] - float(batch["global_advantages"].double().mean())) < 1e-6
+
+
 def test_adam_and_dot():
     from copo_b200 import ops
     p = torch.nn.Parameter(torch.randn(10001))
