@@ -279,6 +279,17 @@ __global__ void gather_rows_kernel(const float* __restrict__ src, size_t ld_src,
     for (int k = lane; k < width; k += 32) d[k] = s[k];
 }
 
+// dst[c][r] = src[idx[r]][c]: the scalar columns of a minibatch, gathered from the row-major stack of the rollout's
+// columns and laid out column by column, so that every column of the minibatch is a contiguous vector (no per-column
+// copy afterwards).  One thread per row: a contiguous read of the row, coalesced writes along r.
+__global__ void gather_cols_kernel(const float* __restrict__ src, size_t ld_src, const int64_t* __restrict__ idx,
+                                   float* __restrict__ dst, size_t rows, int width) {
+    const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const float* s = src + (size_t)idx[r] * ld_src;
+    for (int c = 0; c < width; ++c) dst[(size_t)c * rows + r] = s[c];
+}
+
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, size_t n, float step_size, float inv_sqrt_bc2, float b1, float b2,
                             float eps, float grad_scale) {
@@ -403,6 +414,14 @@ int b2c_gather_rows(const float* src, size_t ld_src, const int64_t* idx, float* 
     if (!src || !idx || !dst || width < 1) return b2c_set_error(B2C_ERR_ARG, "b2c_gather_rows: bad argument");
     size_t blocks = (rows + 7) / 8;
     gather_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, ld_src, idx, dst, ld_dst, rows, width);
+    B2C_CUDA(cudaGetLastError());
+    return B2C_OK;
+}
+
+int b2c_gather_cols(const float* src, size_t ld_src, const int64_t* idx, float* dst, size_t rows, int width, void* stream) {
+    if (rows == 0) return B2C_OK;
+    if (!src || !idx || !dst || width < 1) return b2c_set_error(B2C_ERR_ARG, "b2c_gather_cols: bad argument");
+    gather_cols_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, ld_src, idx, dst, rows, width);
     B2C_CUDA(cudaGetLastError());
     return B2C_OK;
 }

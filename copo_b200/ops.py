@@ -283,6 +283,17 @@ def gather_rows(src, idx, out=None):
     return dst if src.dim() == 2 else dst.squeeze(1)
 
 
+def gather_cols(src, idx):
+    """src [R, W] row-major, idx int64 [B] -> [W, B]: column c of the minibatch is the contiguous vector out[c]."""
+    lib = _lib_ready()
+    assert src.dim() == 2 and src.stride(1) == 1 and idx.dtype == torch.int64 and idx.is_contiguous()
+    B, W = idx.numel(), src.shape[1]
+    out = torch.empty((W, B), dtype=torch.float32, device=src.device)
+    _lib.check(lib.b2c_gather_cols(P(src) if src.is_contiguous() else ctypes.c_void_p(src.data_ptr()), c_size_t(src.stride(0)),
+                                   P(idx), P(out), c_size_t(B), c_int(W), _lib.stream_ptr()))
+    return out
+
+
 def adam_step(param, grad, exp_avg, exp_avg_sq, lr, step, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
     lib = _lib_ready()
     for t in (param, grad, exp_avg, exp_avg_sq):

@@ -203,9 +203,9 @@ class IPPOTrainer:
             batch = {c: ops.gather_rows(w, idx) for c, w in wide.items()}
             if P.CENTRALIZED_CRITIC_OBS not in batch:
                 batch[P.CENTRALIZED_CRITIC_OBS] = batch[P.OBS]
-            s = ops.gather_rows(scal, idx)
+            s = ops.gather_cols(scal, idx)               # [columns, rows]: every scalar column a contiguous vector
             for n, c in enumerate(cols):
-                batch[c] = s[:, n].contiguous()
+                batch[c] = s[n]
             yield batch, rows
 
     # ---- one training iteration ------------------------------------------------------------------------------

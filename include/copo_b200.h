@@ -248,6 +248,8 @@ int b2c_cc_obs_fuse_split(const float* obs, const float* actions, const uint8_t*
 /* dst[r][0..width) = src[idx[r]][0..width): minibatch assembly from a shuffled index list */
 int b2c_gather_rows(const float* src, size_t ld_src, const int64_t* idx, float* dst, size_t ld_dst, size_t rows, int width,
                     void* stream);
+/* dst[c][r] = src[idx[r]][c], dst [width][rows]: the scalar columns of a minibatch, each one a contiguous vector */
+int b2c_gather_cols(const float* src, size_t ld_src, const int64_t* idx, float* dst, size_t rows, int width, void* stream);
 /* torch.optim.Adam step (no weight decay); grad_scale multiplies the gradient first (1/world_size after an all-reduce) */
 int b2c_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1,
                   float beta2, float eps, int step, float grad_scale, void* stream);

@@ -457,6 +457,17 @@ def test_meta_update_outside_the_lcf_clamps():
     assert abs(out["global_adv"] - float(batch["global_advantages"].double().mean())) < 1e-6
 
 
+def test_gather_cols():
+    from copo_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    src = torch.randn(5000, 11, generator=g).cuda()
+    idx = torch.randperm(5000, generator=g)[:1777].cuda()
+    out = ops.gather_cols(src, idx)
+    assert out.shape == (11, 1777) and out.is_contiguous() and torch.equal(out, src[idx].t())
+    wide = torch.randn(5000, 16, generator=g).cuda()
+    assert torch.equal(ops.gather_cols(wide[:, :11], idx), wide[idx][:, :11].t())       # strided source rows
+
+
 def test_adam_and_dot():
     from copo_b200 import ops
     p = torch.nn.Parameter(torch.randn(10001))
