@@ -593,12 +593,16 @@ def time_training(args, dev, world, rank):
                   seed=args.seed), device=dev)
     for _ in range(2):        # warm-up: the first iteration captures the minibatch graph, the second is the first with a
         tr.train()            # ragged last minibatch (eager path: its buffers come from the caching allocator once)
+    import gc
+    gc.collect()              # a full collection of this long-lived process now, not inside a timed iteration
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     steps = 0
-    sample_ms, learn_ms, ar_ms = [], [], []
+    sample_ms, learn_ms, ar_ms, iter_ms = [], [], [], []
     for _ in range(args.train_iters):
+        ti = time.perf_counter()
         res = tr.train()
+        iter_ms.append((time.perf_counter() - ti) * 1e3)
         steps += res["custom_metrics"]["agent_steps"]
         sample_ms.append(tr._timers["sample_time_ms"])
         learn_ms.append(tr._timers["learn_time_ms"])
@@ -608,7 +612,7 @@ def time_training(args, dev, world, rank):
     out = {"agent_env_steps_per_s_per_gpu": steps / dt, "iterations": args.train_iters, "seconds": dt,
            "scenes_per_gpu": scenes, "fragment": args.train_fragment, "sgd_minibatch_size": mb,
            "sgd_minibatch_rows_per_gpu": 65536,
-           "num_sgd_iter": 5, "lcf_num_iters": 5, "sample_ms": sample_ms, "learn_ms": learn_ms,
+           "num_sgd_iter": 5, "lcf_num_iters": 5, "iteration_ms": iter_ms, "sample_ms": sample_ms, "learn_ms": learn_ms,
            "allreduce_ms_per_iteration": ar_ms, "allreduces_per_iteration": tr._timers.get("allreduces"),
            "what": "full %s.training_step iterations, wall clock, this rank; allreduce_ms = CUDA-event time inside "
                    "the gradient / statistics all-reduces of one iteration" % cls.__name__}
