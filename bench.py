@@ -591,28 +591,37 @@ def time_training(args, dev, world, rank):
     tr = cls(dict(env=env_name, num_scenes=scenes, rollout_fragment_length=args.train_fragment,
                   sgd_minibatch_size=mb, num_sgd_iter=5, lcf_num_iters=5, env_config={"num_agents": c["slots"]},
                   seed=args.seed), device=dev)
+    # pre-warm the caching allocator: the valid-row count (and with it the ragged last minibatch) changes from iteration
+    # to iteration, and a request that fits no cached block is a cudaMalloc in the middle of an iteration (1-2 per
+    # iteration observed, sporadically 35-100 ms each on these boxes); one 4 GiB segment, freed again, serves them all
+    del_me = torch.empty(4 << 30, dtype=torch.uint8, device=dev)
+    del del_me
     for _ in range(2):        # warm-up: the first iteration captures the minibatch graph, the second is the first with a
         tr.train()            # ragged last minibatch (eager path: its buffers come from the caching allocator once)
     import gc
-    gc.collect()              # a full collection of this long-lived process now, not inside a timed iteration
+    gc.collect()              # a full collection of this long-lived process now, and everything alive so far out of the
+    gc.freeze()               # collector's sight: a gen-2 pass over the bench's heap cost 20-60 ms inside a timed iteration
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     steps = 0
-    sample_ms, learn_ms, ar_ms, iter_ms = [], [], [], []
+    sample_ms, learn_ms, ar_ms, iter_ms, dev_allocs = [], [], [], [], []
     for _ in range(args.train_iters):
         ti = time.perf_counter()
+        n_alloc = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
         res = tr.train()
         iter_ms.append((time.perf_counter() - ti) * 1e3)
+        dev_allocs.append(torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - n_alloc)
         steps += res["custom_metrics"]["agent_steps"]
         sample_ms.append(tr._timers["sample_time_ms"])
         learn_ms.append(tr._timers["learn_time_ms"])
         ar_ms.append(tr._timers.get("allreduce_ms"))
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    gc.unfreeze()
     out = {"agent_env_steps_per_s_per_gpu": steps / dt, "iterations": args.train_iters, "seconds": dt,
            "scenes_per_gpu": scenes, "fragment": args.train_fragment, "sgd_minibatch_size": mb,
            "sgd_minibatch_rows_per_gpu": 65536,
-           "num_sgd_iter": 5, "lcf_num_iters": 5, "iteration_ms": iter_ms, "sample_ms": sample_ms, "learn_ms": learn_ms,
+           "num_sgd_iter": 5, "lcf_num_iters": 5, "iteration_ms": iter_ms, "cuda_mallocs_per_iteration": dev_allocs, "sample_ms": sample_ms, "learn_ms": learn_ms,
            "allreduce_ms_per_iteration": ar_ms, "allreduces_per_iteration": tr._timers.get("allreduces"),
            "what": "full %s.training_step iterations, wall clock, this rank; allreduce_ms = CUDA-event time inside "
                    "the gradient / statistics all-reduces of one iteration" % cls.__name__}
