@@ -278,6 +278,25 @@ def test_laser_ownership_formula():
         assert sorted(got) == want, trial
 
 
+def test_side_detector_items_cover_every_slot_and_detector_once():
+    """Model of `side_spread` (env_step.cu): with NT threads and n_slots = scenes x slots of the CTA's group, thread t takes
+    slot t % n_slots and the detectors part, part + per, ... with part = t / n_slots, per = NT / n_slots (threads with
+    part >= per idle).  Every (slot, detector) of a map with n_side detectors exactly once, whenever the kernel turns
+    the spreading on (NT >= 2 * n_slots)."""
+    src = open(os.path.join(ROOT, "copo_b200", "csrc", "env_step.cu")).read()
+    assert "NT >= 2 * ng * A" in src and "tid % n_slots" in src and "kk += per" in src
+    for NT, n_slots, n_side in ((128, 40, 65), (128, 30, 65), (128, 64, 65), (256, 40, 65), (128, 20, 16), (96, 40, 65)):
+        assert NT >= 2 * n_slots
+        per = NT // n_slots
+        seen = {}
+        for t in range(NT):
+            slot, part = t % n_slots, t // n_slots
+            if part < per:
+                for kk in range(part, n_side, per):
+                    seen[(slot, kk)] = seen.get((slot, kk), 0) + 1
+        assert len(seen) == n_slots * n_side and set(seen.values()) == {1}, (NT, n_slots, n_side)
+
+
 def test_sampled_scenes_of_a_large_batch_replay_in_the_oracle():
     """Scenes are independent and keyed by their global index: an oracle built over a few `scene_ids` reproduces
     exactly those scenes of a larger (offset) batch - the mechanism the full-size GPU parity test relies on."""
