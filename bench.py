@@ -19,6 +19,7 @@ import argparse
 import hashlib
 import json
 import os
+import re
 import subprocess
 import sys
 import threading
@@ -51,10 +52,14 @@ def _peaks():
 
 
 def _kernel_source_hash():
-    """Identifies the scene-step kernel build a committed ncu capture belongs to."""
+    """Identifies the scene-step kernel build a committed ncu capture belongs to: a hash of the two sources without their
+    comments and blank space (a comment edit compiles to the same SASS and keeps the capture valid)."""
     h = hashlib.sha1()
     for f in ("env_step.cu", "sim_core.cuh"):
-        h.update(open(os.path.join(ROOT, "copo_b200", "csrc", f), "rb").read())
+        txt = open(os.path.join(ROOT, "copo_b200", "csrc", f)).read()
+        txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+        txt = re.sub(r"//[^\n]*", "", txt)
+        h.update(" ".join(txt.split()).encode())
     return h.hexdigest()[:12]
 
 

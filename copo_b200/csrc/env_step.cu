@@ -486,13 +486,14 @@ env_step_kernel(const __grid_constant__ EnvConfig cfg, const __grid_constant__ E
 }
 
 // ---- lidar half of the two-kernel mode ---------------------------------------------------------------------------
-// One CTA works on `G` scenes at a time.  Everything a scene needs arrives in ONE bulk copy: the record the state
-// kernel left (poses, participant mask, per-slot broad-phase masks, the non-laser observation columns).  Warp 0 turns
-// the masks into the (observer, box) pair list in shared memory (prefix sum of the mask populations) while the other
-// warps lay out the observation tile: whole rows [A][D] - lasers preset to "nothing within range", non-laser columns
-// transposed in from the record.  The pair pass lowers the lasers (same pair set-up / laser distribution as the fused
-// kernel), the tile leaves as one bulk store, plus once more as the policy's bf16 [hi | lo] operand through 8-byte
-// coalesced stores.  Nothing on this path waits on a dependent global load.
+// One CTA works on `G` scenes at a time and draws its next group from a global counter.  Everything a scene needs arrives
+// in ONE bulk copy: the record the state kernel left (poses, participant mask, per-slot broad-phase masks, the non-laser
+// observation columns).  All threads turn the masks into the (observer, box) pair list in shared memory (every warp takes
+// the prefix sum of the mask populations, every thread expands one slice of one observer's mask) and lay out the
+// observation tile: whole rows [A][D] - lasers preset to "nothing within range", non-laser columns transposed in from the
+// record.  The pair pass lowers the lasers (same pair set-up / laser distribution as the fused kernel: lidar_spread); as
+// soon as it is done the next record is fetched, the tile leaves as one bulk store, plus once more as the policy's bf16
+// [hi | lo] operand through 16-byte coalesced stores.  Nothing on this path waits on a dependent global load.
 struct LidarIO {
     const uint32_t* map;
     const float* pose;

@@ -80,11 +80,10 @@ def traffic():
     for r in rows[2:]:
         if "env_" in r[ki] and r[ki] not in per:          # first launch of each scene-step kernel
             per[r[ki][:60]] = float(r[ri]) * scale[u[ri]] + float(r[wi]) * scale[u[wi]]
-    hsh = hashlib.sha1()
-    for f in ("env_step.cu", "sim_core.cuh"):
-        hsh.update(open(os.path.join(ROOT, "copo_b200", "csrc", f), "rb").read())
+    sys.path.insert(0, ROOT)
+    import bench                                          # the same hash bench.py checks (sources without comments)
     out = {"c2": {"kernel": "scene step (state + lidar kernels, policy operand included)", "dram_bytes_per_launch": sum(per.values()),
-                  "per_kernel": per, "kernel_source_hash": hsh.hexdigest()[:12],
+                  "per_kernel": per, "kernel_source_hash": bench._kernel_source_hash(),
                   "source": "profiles/%s_step_summary.md (ncu --set full of the bench command, one launch of each kernel)" % TAG}}
     json.dump(out, open(os.path.join(P, "env_step_traffic.json"), "w"), indent=1)
     print("traffic", out["c2"]["dram_bytes_per_launch"], per)
