@@ -145,3 +145,21 @@ def test_wrapper_steps_against_the_reference_methods(scenario):
     if cfg["force_lcf"] != -100:                                 # forced + normal: a fresh value every step
         a = [s["info"]["agent0"]["lcf"] for s in sc["steps"]]
         assert len(set(a)) == len(a)
+
+
+def test_metadrive_crosscheck_fixture_is_the_shipped_data():
+    """tests/golden/metadrive_crosscheck.npz (tools/metadrive_crosscheck.py): the policy in it is the shipped
+    `copo_inter.npz` (zero observation -> the mean SURVEY.md 8c quotes), and the MetaDrive statistics are the reference's
+    evaluate_results CSVs (success rates of the CoPO / IPPO Intersection populations as DrawEvalResult.ipynb shows them)."""
+    import os
+    fx = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "metadrive_crosscheck.npz"))
+    x = np.zeros((1, 92), np.float32)
+    for layer in ("fc_1_1", "fc_2_1", "fc_out_1"):
+        x = x @ fx["copo_inter/default/%s/kernel" % layer] + fx["copo_inter/default/%s/bias" % layer]
+        if layer != "fc_out_1":
+            x = np.tanh(x)
+    assert np.allclose(x[0, :2], [-0.5872524, -0.51996565], atol=1e-6)
+    assert fx["ippo_inter/default/fc_1/kernel"].shape == (91, 256)
+    assert abs(fx["copo_inter/lcf"][0] - 0.36824979071031544) < 1e-12
+    assert tuple(fx["reference/copo/episodes"]) == (100, 5) and tuple(fx["reference/ippo/episodes"]) == (120, 6)
+    assert abs(fx["reference/copo/success_rate"][0] - 0.7825) < 5e-4 and abs(fx["reference/ippo/success_rate"][0] - 0.4805) < 5e-4
