@@ -175,7 +175,7 @@ class MultiAgentDrivingEnv:
                 continue
             total = float(route_len[int(fld[F_ROUTE, i])])
             cur = float(ff[F_DONE_LEN, i] + ff[F_S, i])
-            info[k].update(velocity=float(ff[F_V, i]) * 3.6, steering=float(ff[F_STEER, i]),
+            info[k].update(velocity=float(ff[F_V, i]) * 3.6, steering=-float(ff[F_STEER, i]) + 0.0,
                            acceleration=float(ff[F_THR, i]), step_reward=r[k], cost=1.0 if f & FLAG_CRASH else 0.0,
                            episode_length=int(fld[F_EPLEN, i]), episode_reward=float(ff[F_EPREW, i]),
                            arrive_dest=bool(f & FLAG_ARRIVE), crash=bool(f & FLAG_CRASH),

@@ -8,7 +8,9 @@ repo's own written-down spec of a MetaDrive-style step (kinematic bicycle, route
 72-laser LiDAR against oriented boxes, crash / out-of-road / arrival / horizon, reward, delayed
 removal and respawn) and the CUDA kernel copo_b200/csrc/env_step.cu must reproduce it BIT FOR BIT
 (every float op below is one binary32 operation in the order written; the kernel is compiled with
--fmad=false).
+-fmad=false).  Two of its conventions ARE anchored in reference-held data: the steering sign and the order of the two
+lateral-distance observations were identified with the reference's shipped MetaDrive-trained policies
+(tools/metadrive_crosscheck.py, profiles/r02_e_metadrive_crosscheck.md).
 
 The CoPO-owned bookkeeping layered on the step *does* follow reference lines:
   * neighbour search     env_wrappers.py:125-158  (`_update_distance_map`, `_find_in_range`:
@@ -173,6 +175,11 @@ class OracleSim:
 
         # ---- 1. kinematic bicycle, NSUB sub-steps ------------------------------------------------
         a0 = np.where(act[..., 0] < -ONE, -ONE, np.where(act[..., 0] > ONE, ONE, act[..., 0])).astype(f32)
+        # MetaDrive's steering sign: a positive action turns the vehicle towards DEcreasing heading in this frame.  Identified
+        # from the reference's shipped MetaDrive-trained policies (profiles/r02_e_metadrive_crosscheck.md): with this sign
+        # and obs[0] / obs[1] in the order below they drive this simulator's roads (single agent: success 0.76 - 0.98),
+        # with the opposite sign or order none of them ever arrives.  The stored steering (obs[4], obs[5]) keeps this sign.
+        a0 = (-a0).astype(f32)
         a1 = np.where(act[..., 1] < -ONE, -ONE, np.where(act[..., 1] > ONE, ONE, act[..., 1])).astype(f32)
         st = a0 * MAX_STEER
         ss, cs = det_sincos(st)
@@ -457,8 +464,8 @@ class OracleSim:
         s, l = self._localize(seg_id, self.x, self.y)
         sn, cn = det_sincos(self.h)
         tw = wl + wr
-        obs[..., 0] = _clip01((wl - l) / tw)
-        obs[..., 1] = _clip01((l + wr) / tw)
+        obs[..., 0] = _clip01((l + wr) / tw)              # MetaDrive's order of the two lateral distances (see step())
+        obs[..., 1] = _clip01((wl - l) / tw)
         lane_h = h0 + kappa * s
         hd = wrap_pi(self.h - lane_h)
         obs[..., 2] = _clip01(hd * INV_PI + HALF)

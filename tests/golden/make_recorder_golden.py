@@ -80,7 +80,7 @@ class Replay:
 
 
 def _drive(obs):
-    return np.array([np.clip(-1.5 * (obs[2] - 0.5) * 3.14 - 2.0 * (obs[8] - 0.5), -1, 1), 0.6 if obs[3] < 0.35 else 0.0],
+    return np.array([-np.clip(-1.5 * (obs[2] - 0.5) * 3.14 - 2.0 * (obs[8] - 0.5), -1, 1), 0.6 if obs[3] < 0.35 else 0.0],
                     np.float32)
 
 

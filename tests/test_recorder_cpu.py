@@ -26,7 +26,7 @@ def host_simulator(monkeypatch):
 
 def _drive(obs):
     """lane keeping + speed control from the observation (heading error, lateral offset, speed)."""
-    return np.array([np.clip(-1.5 * (obs[2] - 0.5) * 3.14 - 2.0 * (obs[8] - 0.5), -1, 1),
+    return np.array([-np.clip(-1.5 * (obs[2] - 0.5) * 3.14 - 2.0 * (obs[8] - 0.5), -1, 1),    # a positive action turns right
                      0.6 if obs[3] < 0.35 else 0.0], np.float32)
 
 

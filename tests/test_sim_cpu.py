@@ -16,9 +16,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _policy(obs, rng, S, A):
-    a0 = np.clip(-1.5 * (obs[..., 2] - 0.5) * 3.14 - 2.0 * (obs[..., 8] - 0.5) + rng.normal(0, 0.02, (S, A)), -1, 1)
+    a0 = -np.clip(-1.5 * (obs[..., 2] - 0.5) * 3.14 - 2.0 * (obs[..., 8] - 0.5) + rng.normal(0, 0.02, (S, A)), -1, 1)
     a1 = np.where(obs[..., 3] < 0.35, 0.6, 0.0) + rng.normal(0, 0.05, (S, A))
-    a0[0, ::2] = 0.5                                  # scene 0: every other car steers off the road
+    a0[0, ::2] = -0.5                                 # scene 0: every other car steers off the road
     return np.stack([a0, a1], -1).astype(np.float32)
 
 
