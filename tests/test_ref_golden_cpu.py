@@ -163,3 +163,16 @@ def test_metadrive_crosscheck_fixture_is_the_shipped_data():
     assert abs(fx["copo_inter/lcf"][0] - 0.36824979071031544) < 1e-12
     assert tuple(fx["reference/copo/episodes"]) == (100, 5) and tuple(fx["reference/ippo/episodes"]) == (120, 6)
     assert abs(fx["reference/copo/success_rate"][0] - 0.7825) < 5e-4 and abs(fx["reference/ippo/success_rate"][0] - 0.4805) < 5e-4
+
+
+def test_shipped_metadrive_policies_follow_the_road_under_the_specified_conventions():
+    """The two conventions of the simulator specification that reference-held data pins (crosscheck_probe.py,
+    profiles/r02_e_metadrive_crosscheck.md): the reference's shipped MetaDrive-trained Intersection policies, alone on the
+    road, reach their destinations in the specified simulator - and never do when the steering sign and the order of the
+    two lateral-distance observations are put back the way they were."""
+    import crosscheck_probe as probe
+    for name, floor in (("ippo_inter", 0.7), ("copo_inter", 0.5)):
+        spec = probe.run(name, (), S=8, A=1, T=300)
+        undone = probe.run(name, ("undo_steer", "undo_lat"), S=8, A=1, T=300)
+        assert spec["finished"] >= 10 and spec["success"] >= floor and spec["crash"] == 0.0, (name, spec)
+        assert undone["success"] == 0.0 and undone["out"] >= 0.9, (name, undone)
